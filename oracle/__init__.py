@@ -1,0 +1,270 @@
+"""ctypes front-end of the CPU parity oracle (oracle/mnem_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+The product package (mnem_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+c_dp = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class NemInfo(C.Structure):
+    _fields_ = [("score", C.c_double), ("max_trace", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
+                ("min_margin", C.c_double)]
+
+
+class EmOpts(C.Structure):
+    _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
+                ("max_iter_guard", C.c_int)]
+
+
+class EmInfo(C.Structure):
+    _fields_ = [("ll", C.c_double), ("best_ll", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
+                ("n_greedy_iter", C.c_long), ("min_margin", C.c_double)]
+
+
+def build():
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def lib(acc="ld"):
+    """acc='ld': long-double accumulators (R on x86-64); acc='f64': double accumulators."""
+    if acc not in _LIBS:
+        name = "libmnem_oracle.so" if acc == "ld" else "libmnem_oracle_f64.so"
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        _LIBS[acc] = C.CDLL(path)
+        _LIBS[acc].orc_get_ll.restype = C.c_double
+        _LIBS[acc].orc_score_adj.restype = C.c_double
+        _LIBS[acc].orc_get_probs.restype = C.c_double
+    return _LIBS[acc]
+
+
+def _d(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _u8(a):
+    return a.ctypes.data_as(c_u8p)
+
+
+def _i32(a):
+    return a.ctypes.data_as(c_i32p)
+
+
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _g(a):
+    """graph(s) -> uint8 Fortran-ordered copy, last two dims S x S."""
+    return np.asfortranarray((np.asarray(a) != 0).astype(np.uint8))
+
+
+def _graphs(a):
+    """stack of graphs [n, S, S] -> contiguous buffer where each graph is column-major."""
+    a = (np.asarray(a) != 0).astype(np.uint8)
+    if a.ndim == 2:
+        a = a[None]
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 1)))  # [n][col][row] == col-major per graph
+
+
+def _ungraphs(buf, n, S):
+    return np.transpose(buf.reshape(n, S, S), (0, 2, 1)).copy()
+
+
+# ---- src/mm.cpp ------------------------------------------------------------------------------------------
+def trans_close_w(x, acc="ld"):
+    S = x.shape[0]
+    b = _graphs(x)
+    lib(acc).orc_trans_close_w(_u8(b), S)
+    return _ungraphs(b, 1, S)[0]
+
+
+def trans_close_ins(x, u, v, acc="ld"):
+    S = x.shape[0]
+    b = _graphs(x)
+    lib(acc).orc_trans_close_ins(_u8(b), S, int(u), int(v))
+    return _ungraphs(b, 1, S)[0]
+
+
+def trans_close_del(x, u, v, acc="ld"):
+    S = x.shape[0]
+    b = _graphs(x)
+    lib(acc).orc_trans_close_del(_u8(b), S, int(u), int(v))
+    return _ungraphs(b, 1, S)[0]
+
+
+def max_col_row(x, acc="ld"):
+    x = _f(x)
+    out = np.zeros(x.shape[0], dtype=np.int32)
+    lib(acc).orc_max_col_row(_d(x), x.shape[0], x.shape[1], _i32(out))
+    return out
+
+
+def matmul(A, B, acc="ld"):
+    A, B = _f(A), _f(B)
+    out = np.zeros((A.shape[0], B.shape[1]), order="F")
+    lib(acc).orc_matmul(_d(A), _d(B), A.shape[0], A.shape[1], B.shape[1], _d(out))
+    return out
+
+
+# ---- graphs ----------------------------------------------------------------------------------------------
+def mytc(x, u=None, v=None, acc="ld"):
+    S = x.shape[0]
+    b = _graphs(x)
+    if u is None or v is None:
+        lib(acc).orc_mytc(_u8(b), S)
+    else:
+        lib(acc).orc_mytc_uv(_u8(b), S, int(u), int(v))
+    return _ungraphs(b, 1, S)[0]
+
+
+def transitive_reduction(g, acc="ld"):
+    S = g.shape[0]
+    b = _graphs(g)
+    out = np.zeros_like(b)
+    lib(acc).orc_trans_reduce(_u8(b), S, _u8(out))
+    return _ungraphs(out, 1, S)[0]
+
+
+def neighbours(P, acc="ld"):
+    """unique(c(get.ins.fast, get.rev.tc, get.del.tc)(P)) -> (models [n,S,S], kind [n], n_raw)."""
+    S = P.shape[0]
+    b = _graphs(P)
+    models = np.zeros(3 * S * S * S * S + S * S, dtype=np.uint8)
+    kind = np.zeros(3 * S * S + 1, dtype=np.int8)
+    nraw = C.c_int(0)
+    n = lib(acc).orc_neighbours(_u8(b), S, _u8(models), kind.ctypes.data_as(C.POINTER(C.c_int8)), C.byref(nraw))
+    return _ungraphs(models[: n * S * S], n, S), kind[:n].copy(), nraw.value
+
+
+# ---- likelihood ------------------------------------------------------------------------------------------
+def get_affinity(L, mw=None, affinity=0, complete=False, logtype=2.0, acc="ld"):
+    L = _f(L)
+    k, Cn = L.shape
+    out = np.zeros((k, Cn), order="F")
+    mwp = _d(_f(mw)) if mw is not None else None
+    lib(acc).orc_get_affinity(_d(L), k, Cn, mwp, int(affinity), int(bool(complete)), C.c_double(logtype), _d(out))
+    return out
+
+
+def get_ll(L, mw=None, complete=False, logtype=2.0, acc="ld"):
+    L = _f(L)
+    k, Cn = L.shape
+    mwp = _d(_f(mw)) if mw is not None else None
+    return lib(acc).orc_get_ll(_d(L), k, Cn, mwp, int(bool(complete)), C.c_double(logtype))
+
+
+def mw_update(L, mw, complete=False, logtype=2.0, na_guard=False, acc="ld"):
+    L = _f(L)
+    k, Cn = L.shape
+    m = _f(mw).copy()
+    lib(acc).orc_mw_update(_d(L), k, Cn, _d(m), int(bool(complete)), C.c_double(logtype), int(na_guard))
+    return m
+
+
+# ---- M-step ----------------------------------------------------------------------------------------------
+def do_mean(D, pert, S, weights=None, acc="ld"):
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    R = np.zeros((E, S), order="F")
+    wp = _d(_f(weights)) if weights is not None else None
+    lib(acc).orc_do_mean(_d(D), E, Cn, _i32(pert), S, wp, _d(R))
+    return R
+
+
+def score_adj(R, adj, trans_close=True, acc="ld"):
+    """scoreAdj(D=R, adj, dotopo=TRUE) -> (score, theta 0..S, W)."""
+    R = _f(R)
+    E, S = R.shape
+    b = _graphs(adj)
+    theta = np.zeros(E, dtype=np.int32)
+    W = np.zeros((E, S), order="F")
+    sc = lib(acc).orc_score_adj(_d(R), E, S, _u8(b), int(bool(trans_close)), _i32(theta), _d(W))
+    return sc, theta, W
+
+
+def nem_greedy(R, start=None, acc="ld"):
+    """nem(search='greedy') on collapsed data -> dict(adj reduced, theta, score, max_trace, n_iter, n_scored)."""
+    R = _f(R)
+    E, S = R.shape
+    sb = _graphs(start) if start is not None else None
+    adj = np.zeros(S * S, dtype=np.uint8)
+    theta = np.zeros(E, dtype=np.int32)
+    info = NemInfo()
+    lib(acc).orc_nem_greedy(_d(R), E, S, _u8(sb) if sb is not None else None, _u8(adj), _i32(theta), C.byref(info))
+    return dict(adj=_ungraphs(adj, 1, S)[0], theta=theta, score=info.score, max_trace=info.max_trace,
+                n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin)
+
+
+# ---- E-step ----------------------------------------------------------------------------------------------
+def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, faithful_cost=False, acc="ld"):
+    """getProbs -> dict(probs k x C, mw, ll, theta_used k x E)."""
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    pb = _graphs(phi)
+    k = pb.shape[0]
+    th = np.ascontiguousarray(theta, dtype=np.int32) if theta is not None else None
+    L_in = _f(L_in)
+    L_out = np.zeros((k, Cn), order="F")
+    mw_out = np.zeros(k)
+    th_used = np.zeros((k, E), dtype=np.int32)
+    mwp = _d(_f(mw)) if mw is not None else None
+    ll = lib(acc).orc_get_probs(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), _i32(th) if th is not None else None,
+                                _d(L_in), mwp, int(bool(complete)), C.c_double(logtype), int(faithful_cost),
+                                _d(L_out), _d(mw_out), _i32(th_used))
+    return dict(probs=L_out, mw=mw_out, ll=ll, theta_used=th_used)
+
+
+# ---- EM --------------------------------------------------------------------------------------------------
+def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
+            max_iter_guard=0, acc="ld"):
+    """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    init_phi = np.asarray(init_phi)
+    starts, k = init_phi.shape[:2]
+    pb = _graphs(init_phi.reshape(starts * k, S, S))
+    adj = np.zeros(starts * k * S * S, dtype=np.uint8)
+    theta = np.zeros((starts, k, E), dtype=np.int32)
+    L = np.zeros((starts, Cn, k))          # per start: k x C column-major == [C][k] C-order
+    mw = np.zeros((starts, k))
+    tr = [np.zeros((starts, max_trace)) for _ in range(4)]
+    infos = (EmInfo * starts)()
+    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard)
+    best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
+                                _i32(theta), _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
+    adj = _ungraphs(adj, starts * k, S).reshape(starts, k, S, S)
+    n_iter = np.array([i.n_iter for i in infos])
+    res = dict(best=best, adj=adj, theta=theta, probs=np.transpose(L, (0, 2, 1)).copy(), mw=mw,
+               ll=np.array([i.ll for i in infos]), n_iter=n_iter,
+               n_scored=np.array([i.n_scored for i in infos]), n_greedy_iter=np.array([i.n_greedy_iter for i in infos]),
+               min_margin=np.array([i.min_margin for i in infos]),
+               lls=[tr[0][s, :n_iter[s]].copy() for s in range(starts)],
+               phievo=[tr[1][s, :n_iter[s]].copy() for s in range(starts)],
+               thetaevo=[tr[2][s, :n_iter[s]].copy() for s in range(starts)],
+               mwevo=[tr[3][s, :n_iter[s]].copy() for s in range(starts)])
+    return res
+
+
+def final_mw(L, mw_best, complete=False, logtype=2.0, acc="ld"):
+    L = _f(L)
+    k, Cn = L.shape
+    out = np.zeros(k)
+    lib(acc).orc_final_mw(_d(L), k, Cn, _d(_f(mw_best)), int(bool(complete)), C.c_double(logtype), _d(out))
+    return out

@@ -1,0 +1,734 @@
+/*
+ * mnem_oracle.c -- CPU restatement of cbg-ethz/mnem's EM hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may build, load or call it.  Nothing under mnem_b200/ links or imports it; the
+ * product path is the CUDA library and fails loudly when that library is missing.
+ *
+ * It restates, in plain C, what the reference computes in interpreted R plus 84 lines of C++.  The
+ * reference cannot be executed in this environment (no R, no Rcpp/RcppEigen headers), so every function
+ * below cites the reference lines it follows (paths relative to /root/reference).
+ *
+ * PARITY PINNING.  Pinned by reference-owned vectors: getLL/getAffinity against the 9 fitted objects of
+ * data/app.rda that carry `probs` (tests/golden/app_rda_ll.npz), transitive.closure against the roxygen
+ * example R/mnems.r:546-548.  The data contraction, doMean, scoreAdj and the greedy search have NO
+ * reference-owned expected values (the reference's only unit test is an RNG-dependent property):
+ * for those rows parity is UNPINNED and the oracle is a reading of the source.
+ *
+ * Numerics.  R's sum/colSums/rowSums accumulate in `long double` (80-bit x87 on x86-64 builds) and round
+ * once; `%*%` (reference BLAS) and Eigen's GEBP (SSE2, no FMA, one accumulator per output, depth <= 100)
+ * accumulate in double in ascending index order.  acc_t below is that long-double accumulator; build
+ * with -DORC_ACC_DOUBLE to get the behaviour of an R built with --disable-long-double (or arm64).
+ *
+ * Layout: every matrix is column-major like R.  Graphs are uint8 0/1 S x S, adj[i + j*S] = 1 <=> edge
+ * i -> j (parent row, child column).  theta is int32[E] in 0..S, 0 = unattached.  pert is int32[C] in 1..S
+ * (single knock-down per cell; the multi-KO Rho path of R/mnems_low.r:613-616 is not restated).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifdef ORC_ACC_DOUBLE
+typedef double acc_t;
+#else
+typedef long double acc_t;
+#endif
+
+#define ORC_MAXS 64
+
+/* ------------------------------------------------------------------------------------------------ */
+/* src/mm.cpp                                                                                       */
+/* ------------------------------------------------------------------------------------------------ */
+
+/* src/mm.cpp:15-30 transClose_W.  px[i*nc+j] is (row j, col i): X[j,i] |= X[k,i] && X[j,k], loops k,i,j. */
+void orc_trans_close_w(uint8_t *x, int n)
+{
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++)
+                x[i * n + j] = (uint8_t)(x[i * n + j] || (x[i * n + k] && x[k * n + j]));
+}
+
+/* src/mm.cpp:50-65 transClose_Ins, u,v 1-based: X[i,j] |= X[i,u] && X[v,j] for every (i,j), in place. */
+void orc_trans_close_ins(uint8_t *x, int n, int u, int v)
+{
+    int k = u - 1, l = v - 1;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            x[j * n + i] = (uint8_t)(x[j * n + i] || (x[j * n + l] && x[k * n + i]));
+}
+
+/* src/mm.cpp:32-48 transClose_Del, u,v 1-based: X[u,v] = X[u,v] || exists k: X[u,k] && X[k,v]. */
+void orc_trans_close_del(uint8_t *x, int n, int u, int v)
+{
+    int i = v - 1, j = u - 1;
+    for (int k = 0; k < n; k++) {
+        x[i * n + j] = (uint8_t)(x[i * n + j] || (x[i * n + k] && x[k * n + j]));
+        if (x[i * n + j] == 1) break;
+    }
+}
+
+/* src/mm.cpp:66-84 maxCol_row: per row the first strictly-greater maximum, 1-based.  Rows whose entries
+ * are all NaN / -Inf leave the reference output uninitialised; the oracle returns 0 for them. */
+void orc_max_col_row(const double *x, int nr, int nc, int32_t *out)
+{
+    for (int i = 0; i < nr; i++) {
+        double best = -INFINITY;
+        int32_t arg = 0;
+        for (int j = 0; j < nc; j++)
+            if (x[i + (size_t)j * nr] > best) { best = x[i + (size_t)j * nr]; arg = j + 1; }
+        out[i] = arg;
+    }
+}
+
+/* src/mm.cpp:8-13 eigenMapMatMult: C = A(m x p) * B(p x n), double, ascending-p sum from 0, no FMA. */
+void orc_matmul(const double *A, const double *B, int m, int p, int n, double *Cout)
+{
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < m; i++) {
+            double s = 0.0;
+            for (int l = 0; l < p; l++) {
+                s += A[i + (size_t)l * m] * B[l + (size_t)j * p];
+            }
+            Cout[i + (size_t)j * m] = s;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* graph helpers: R/mnems_low.r:1199-1215 (mytc), R/mnems.r:511-533 (transitive.reduction)          */
+/* ------------------------------------------------------------------------------------------------ */
+
+static void set_diag(uint8_t *x, int n, uint8_t v) { for (int i = 0; i < n; i++) x[i * n + i] = v; }
+
+/* mytc(x): diag(x) <- 1; transClose_W; binarise.  R/mnems_low.r:1199-1202,1211 */
+void orc_mytc(uint8_t *x, int n) { set_diag(x, n, 1); orc_trans_close_w(x, n); }
+
+/* mytc(x,u,v): diag 1, then Ins if x[u,v]==1 else Del.  R/mnems_low.r:1203-1210 */
+void orc_mytc_uv(uint8_t *x, int n, int u, int v)
+{
+    set_diag(x, n, 1);
+    if (x[(u - 1) + (v - 1) * n] == 1) orc_trans_close_ins(x, n, u, v);
+    else orc_trans_close_del(x, n, u, v);
+}
+
+/* transitive.reduction: closure (diag 1), zero diag, then the in-place order-dependent triple loop.
+ * R/mnems.r:517-532.  `type` is all zero for 0/1 input so the sign test is always true. */
+void orc_trans_reduce(const uint8_t *g_in, int n, uint8_t *g)
+{
+    memcpy(g, g_in, (size_t)n * n);
+    for (int i = 0; i < n * n; i++) g[i] = g[i] != 0;
+    orc_mytc(g, n);
+    set_diag(g, n, 0);
+    for (int y = 0; y < n; y++)
+        for (int x = 0; x < n; x++)
+            if (g[x + y * n])
+                for (int j = 0; j < n; j++)
+                    if (g[y + j * n]) g[x + j * n] = 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* responsibilities and likelihood: R/mnems.r:1390-1441 (getAffinity), R/mnems_low.r:540-552 (getLL) */
+/* ------------------------------------------------------------------------------------------------ */
+
+static double rpow(double b, double y)
+{   /* R_pow (arithmetic.c): x==1 or y==0 -> 1; y==2 -> x*x; else libm pow */
+    if (b == 1.0 || y == 0.0) return 1.0;
+    if (y == 2.0) return b * b;
+    return pow(b, y);
+}
+
+/* getAffinity(x, affinity, norm=TRUE, logtype, mw, complete).  L is k x C, out is k x C.
+ * affinity==0: soft path R/mnems.r:1419-1437.  affinity==1: hard path :1393-1417 (complete must be 0 --
+ * the reference's complete branch there reads `y` before it is defined and errors). */
+void orc_get_affinity(const double *L, int k, int C, const double *mw_in, int affinity, int complete,
+                      double logtype, double *out)
+{
+    double mwbuf[256];
+    const double *mw = mw_in;
+    if (!mw) { for (int i = 0; i < k; i++) mwbuf[i] = 1.0 / k; mw = mwbuf; }   /* :1392 */
+    if (affinity == 1) {
+        for (int c = 0; c < C; c++) {
+            double mx = -INFINITY;
+            for (int i = 0; i < k; i++) {
+                out[i + (size_t)c * k] = rpow(logtype, L[i + (size_t)c * k]) * mw[i];       /* :1403-1404 */
+                if (out[i + (size_t)c * k] > mx) mx = out[i + (size_t)c * k];
+            }
+            for (int i = 0; i < k; i++) {
+                double y = out[i + (size_t)c * k];
+                if (y < mx) y = 0.0;                                                    /* :1405-1411 */
+                if (y != 0.0) y = 1.0;                                                  /* :1415-1417 */
+                if (isnan(y)) y = 0.0;                                                  /* :1439 */
+                out[i + (size_t)c * k] = y;
+            }
+        }
+        return;
+    }
+    if (k == 1) { for (int c = 0; c < C; c++) out[c] = 1.0; return; }                    /* :1435-1437 */
+    int shift = 0;
+    if (complete) {                                                                      /* :1422 any(y > 0) */
+        for (size_t i = 0; i < (size_t)k * C; i++) if (L[i] > 0) { shift = 1; break; }
+    }
+    double shrink = log(ldexp(1.0, 1023)) / log(logtype);                                /* :1425-1426 */
+    for (int c = 0; c < C; c++) {
+        const double *x = L + (size_t)c * k;
+        double *y = out + (size_t)c * k;
+        double xmax = -INFINITY;
+        if (shift) for (int i = 0; i < k; i++) if (x[i] > xmax) xmax = x[i];
+        acc_t cs = 0;
+        for (int i = 0; i < k; i++) {
+            double v = x[i];
+            if (shift) v = v - (xmax - shrink / k);                                      /* :1427 */
+            v = rpow(logtype, v);                                                        /* :1431 */
+            v = v * mw[i];                                                               /* :1432 */
+            y[i] = v;
+            cs += v;                                                                     /* colSums :1433 */
+        }
+        double csd = (double)cs;
+        for (int i = 0; i < k; i++) {
+            double v = y[i] / csd;
+            if (isnan(v)) v = 0.0;                                                       /* :1439 */
+            y[i] = v;
+        }
+    }
+}
+
+/* getLL.  R/mnems_low.r:540-552. */
+double orc_get_ll(const double *L, int k, int C, const double *mw_in, int complete, double logtype)
+{
+    double mwbuf[256];
+    const double *mw = mw_in;
+    if (!mw) { for (int i = 0; i < k; i++) mwbuf[i] = 1.0 / k; mw = mwbuf; }
+    acc_t l = 0;
+    if (complete) {                                                                       /* :542-545 */
+        double *Z = (double *)malloc(sizeof(double) * (size_t)k * C);
+        orc_get_affinity(L, k, C, mw, 0, 1, logtype, Z);
+        double lmw[256];
+        for (int i = 0; i < k; i++) lmw[i] = log(mw[i]) / log(logtype);
+        for (int c = 0; c < C; c++) {
+            acc_t s = 0;
+            for (int i = 0; i < k; i++) s += Z[i + (size_t)c * k] * (L[i + (size_t)c * k] + lmw[i]);
+            l += (double)s;
+        }
+        free(Z);
+    } else {                                                                              /* :547-549 */
+        double lb = log(logtype);
+        for (int c = 0; c < C; c++) {
+            double s = 0.0;                                 /* rep(1,k) %*% x : double, ascending k */
+            for (int i = 0; i < k; i++) s += 1.0 * (rpow(logtype, L[i + (size_t)c * k]) * mw[i]);
+            l += log(s) / lb;
+        }
+    }
+    return (double)l;
+}
+
+/* mw <- apply(getAffinity(L, mw), 1, sum); mw <- mw/sum(mw); NA -> 1/k.  R/mnems_low.r:591-595, 653-657,
+ * R/mnems.r:1936-1940, 2113-2121 (the NA guard exists only at :595 and :1940, selected by na_guard). */
+static void mw_update(const double *L, int k, int C, double *mw, int complete, double logtype, int na_guard,
+                      double *scratch)
+{
+    orc_get_affinity(L, k, C, mw, 0, complete, logtype, scratch);
+    acc_t tot = 0;
+    double rs[256];
+    for (int i = 0; i < k; i++) {
+        acc_t s = 0;
+        for (int c = 0; c < C; c++) s += scratch[i + (size_t)c * k];
+        rs[i] = (double)s;
+    }
+    for (int i = 0; i < k; i++) tot += rs[i];
+    int bad = 0;
+    for (int i = 0; i < k; i++) { mw[i] = rs[i] / (double)tot; if (isnan(mw[i])) bad = 1; }
+    if (bad && na_guard) for (int i = 0; i < k; i++) mw[i] = 1.0 / k;
+}
+
+void orc_mw_update(const double *L, int k, int C, double *mw, int complete, double logtype, int na_guard)
+{
+    double *scratch = (double *)malloc(sizeof(double) * (size_t)k * C);
+    mw_update(L, k, C, mw, complete, logtype, na_guard, scratch);
+    free(scratch);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* M-step sufficient statistics: doMean, Rho path.  R/mnems_low.r:893-906 reached from nem() R/mnems.r:75-77, */
+/* 101-107 (nem fills Rho <- getRho(D) when NULL, so the rowsum/global-divisor branch :908-911 is never  */
+/* taken on the EM path).  R[e,s] = sum_c (D[e,c]*w[c]) * Rho[s,c], ascending c, double (BLAS dgemm).  */
+/* The caller block R/mnems.r:1986-2006 drops zero-weight cells and appends S all-zero cells: the sums  */
+/* are unchanged.  weights == NULL: plain D (k == 1 path, R/mnems.r:1851).                               */
+/* ------------------------------------------------------------------------------------------------ */
+void orc_do_mean(const double *D, int E, int C, const int32_t *pert, int S, const double *w, double *R)
+{
+    memset(R, 0, sizeof(double) * (size_t)E * S);
+    for (int c = 0; c < C; c++) {
+        if (w && w[c] == 0.0) continue;
+        double *r = R + (size_t)(pert[c] - 1) * E;
+        const double *d = D + (size_t)c * E;
+        if (w) {
+            double wc = w[c];
+            for (int e = 0; e < E; e++) r[e] += d[e] * wc;   /* built with -ffp-contract=off: mul then add */
+        } else {
+            for (int e = 0; e < E; e++) r[e] += d[e];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* scoreAdj on the collapsed E x S matrix.  R/mnems.r:416-458 with method="llr", marginal=FALSE,       */
+/* Rho = identity (R/mnems.r:104), weights = NULL: W = R %*% adj (Eigen), theta = first argmax over     */
+/* cbind(0, W) minus 1 (:447-450), score = sum(rowMaxs(cbind(0, W))) (:452-454, long-double sum).       */
+/* ------------------------------------------------------------------------------------------------ */
+static void score_cols(const double *R, int E, int S, const uint8_t *adj, const uint8_t *colsel, double *W)
+{
+    for (int j = 0; j < S; j++) {
+        if (colsel && !colsel[j]) continue;
+        double *w = W + (size_t)j * E;
+        for (int e = 0; e < E; e++) w[e] = 0.0;
+        for (int s = 0; s < S; s++)
+            if (adj[s + j * S]) {
+                const double *r = R + (size_t)s * E;
+                for (int e = 0; e < E; e++) w[e] += r[e];        /* product with 1.0 is exact */
+            }
+    }
+}
+
+static double score_total(const double *W, int E, int S, int32_t *theta)
+{
+    acc_t tot = 0;
+    for (int e = 0; e < E; e++) {
+        double best = 0.0;
+        int32_t arg = 0;
+        for (int j = 0; j < S; j++) {
+            double v = W[e + (size_t)j * E];
+            if (v > best) { best = v; arg = j + 1; }
+        }
+        if (theta) theta[e] = arg;
+        tot += best;
+    }
+    return (double)tot;
+}
+
+/* Public: scoreAdj(D=R, adj, trans.close, dotopo=TRUE).  W_out (E x S) and theta may be NULL. */
+double orc_score_adj(const double *R, int E, int S, const uint8_t *adj_in, int trans_close, int32_t *theta,
+                     double *W_out)
+{
+    uint8_t adj[ORC_MAXS * ORC_MAXS];
+    memcpy(adj, adj_in, (size_t)S * S);
+    if (trans_close) orc_mytc(adj, S);                                                   /* :428-430 */
+    double *W = W_out ? W_out : (double *)malloc(sizeof(double) * (size_t)E * S);
+    score_cols(R, E, S, adj, NULL, W);
+    double sc = score_total(W, E, S, theta);
+    if (!W_out) free(W);
+    return sc;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* neighbour generators R/mnems_low.r:1025-1084, combined as unique(c(ins, rev, del)) R/mnems.r:222-224 */
+/* ------------------------------------------------------------------------------------------------ */
+/* Writes at most 3*S*S matrices (S*S bytes each) into `models`; returns the number written BEFORE the
+ * keep-first dedupe in *n_raw and the number after it as the return value.  kind[i]: 0 ins, 1 rev, 2 del. */
+int orc_neighbours(const uint8_t *P, int S, uint8_t *models, int8_t *kind, int *n_raw)
+{
+    const int SS = S * S;
+    int n = 0;
+    uint8_t T[ORC_MAXS * ORC_MAXS];
+    /* get.ins.fast :1048-1068 */
+    for (int idx = 0; idx < SS; idx++)
+        if (P[idx] == 0) {
+            uint8_t *m = models + (size_t)n * SS;
+            memcpy(m, P, SS);
+            m[idx] = 1;
+            orc_mytc_uv(m, S, idx % S + 1, idx / S + 1);
+            kind[n++] = 0;
+        }
+    /* get.rev.tc :1025-1046 */
+    orc_trans_reduce(P, S, T);
+    for (int c = 0; c < S; c++)
+        for (int r = 0; r < S; r++)
+            if (T[r + c * S] + T[c + r * S] == 1) {
+                uint8_t *m = models + (size_t)n * SS;
+                memcpy(m, P, SS);
+                m[r + c * S] = (uint8_t)(1 - m[r + c * S]);
+                if (r != c) m[c + r * S] = (uint8_t)(1 - m[c + r * S]);
+                set_diag(m, S, 1);
+                if (m[r + c * S] == 1) orc_mytc_uv(m, S, r + 1, c + 1);
+                else orc_mytc_uv(m, S, c + 1, r + 1);
+                kind[n++] = 1;
+            }
+    /* get.del.tc :1070-1084 */
+    {
+        uint8_t P0[ORC_MAXS * ORC_MAXS];
+        memcpy(P0, P, SS);
+        for (int i = 0; i < S; i++) P0[i + i * S] = (uint8_t)(P0[i + i * S] ? P0[i + i * S] - 1 : 0);
+        orc_trans_reduce(P0, S, T);
+        for (int idx = 0; idx < SS; idx++)
+            if (T[idx] == 1) {
+                uint8_t *m = models + (size_t)n * SS;
+                memcpy(m, P0, SS);
+                m[idx] = 0;
+                set_diag(m, S, 1);
+                kind[n++] = 2;
+            }
+    }
+    if (n_raw) *n_raw = n;
+    /* unique(): keep first occurrence, R/mnems.r:222 */
+    int nu = 0;
+    for (int i = 0; i < n; i++) {
+        int dup = 0;
+        for (int j = 0; j < nu && !dup; j++)
+            if (memcmp(models + (size_t)i * SS, models + (size_t)j * SS, SS) == 0) dup = 1;
+        if (!dup) {
+            if (nu != i) { memmove(models + (size_t)nu * SS, models + (size_t)i * SS, SS); kind[nu] = kind[i]; }
+            nu++;
+        }
+    }
+    return nu;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* nem(search="greedy", runs=1, domean already applied): R/mnems.r:111-142, 203-307, 362-379           */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    double score;        /* nem$score = oldscore */
+    double max_trace;    /* max(nem$scores) */
+    int n_iter;          /* accepted moves */
+    long n_scored;       /* scoreAdj calls inside the loop (unique candidates) */
+    double min_margin;   /* smallest |best - runner-up or old| seen in a decision, relative; diagnostic */
+} orc_nem_info;
+
+void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t *adj_out, int32_t *theta_out,
+                    orc_nem_info *info)
+{
+    const int SS = S * S;
+    uint8_t better[ORC_MAXS * ORC_MAXS], tmp[ORC_MAXS * ORC_MAXS];
+    if (start) memcpy(better, start, SS); else memset(better, 0, SS);
+    for (int i = 0; i < SS; i++) better[i] = better[i] != 0;
+    set_diag(better, S, 1);                                                      /* :133, NOT closed */
+    double *P = (double *)malloc(sizeof(double) * (size_t)E * S);                 /* subweights of `better` */
+    double *Wc = (double *)malloc(sizeof(double) * (size_t)E * S);
+    double *Pbest = (double *)malloc(sizeof(double) * (size_t)E * S);
+    uint8_t *models = (uint8_t *)malloc((size_t)3 * SS * SS + SS);
+    int8_t *kind = (int8_t *)malloc((size_t)3 * SS + 1);
+    int haveP = 0;
+    double oldscore = orc_score_adj(R, E, S, better, 1, NULL, NULL);             /* :135-141 closes inside */
+    double maxtrace = oldscore;
+    long nscored = 0;
+    int niter = 0;
+    double minmargin = INFINITY;
+    for (;;) {
+        int nm = orc_neighbours(better, S, models, kind, NULL);
+        if (nm == 0) break;
+        double bests = -INFINITY, second = -INFINITY;
+        int bestidx = -1;
+        for (int m = 0; m < nm; m++) {
+            const uint8_t *cand = models + (size_t)m * SS;
+            double sc;
+            if (!haveP) {                                                        /* :439-440 */
+                score_cols(R, E, S, cand, NULL, Wc);
+            } else {                                                             /* :441-446 */
+                uint8_t chg[ORC_MAXS];
+                for (int j = 0; j < S; j++) {
+                    chg[j] = 0;
+                    for (int s = 0; s < S; s++) if (cand[s + j * S] != better[s + j * S]) { chg[j] = 1; break; }
+                }
+                memcpy(Wc, P, sizeof(double) * (size_t)E * S);
+                score_cols(R, E, S, cand, chg, Wc);
+            }
+            sc = score_total(Wc, E, S, NULL);
+            if (isnan(sc)) sc = 0.0;                                             /* :235 */
+            nscored++;
+            if (sc > bests) {                                                    /* which.max: first */
+                second = bests; bests = sc; bestidx = m;
+                memcpy(Pbest, Wc, sizeof(double) * (size_t)E * S);
+            } else if (sc > second && sc < bests) second = sc;
+        }
+        const uint8_t *best = models + (size_t)bestidx * SS;
+        int nb = 0, nc = 0;
+        for (int i = 0; i < SS; i++) { nb += better[i] == 1; nc += best[i] == 1; }
+        double scale = fabs(bests) > 1 ? fabs(bests) : 1;
+        if (bests != oldscore && fabs(bests - oldscore) / scale < minmargin) minmargin = fabs(bests - oldscore) / scale;
+        if (isfinite(second) && (bests - second) / scale < minmargin) minmargin = (bests - second) / scale;
+        if (bests > oldscore || (bests == oldscore && nb > nc)) {                /* :279-286 */
+            memcpy(tmp, best, SS); memcpy(better, tmp, SS);
+            oldscore = bests;
+            if (oldscore > maxtrace) maxtrace = oldscore;
+            memcpy(P, Pbest, sizeof(double) * (size_t)E * S);
+            haveP = 1;
+            niter++;
+        } else break;                                                            /* :287-289 */
+    }
+    /* :362-369 theta from the closed final graph, :374 reduction */
+    orc_score_adj(R, E, S, better, 1, theta_out, NULL);
+    orc_trans_reduce(better, S, adj_out);
+    if (info) { info->score = oldscore; info->max_trace = maxtrace; info->n_iter = niter; info->n_scored = nscored;
+                info->min_margin = minmargin; }
+    free(P); free(Wc); free(Pbest); free(models); free(kind);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* E-step: getProbs.  R/mnems_low.r:576-663                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+/* phi: k graphs (S*S each; any form -- closed inside, :610).  theta: k*E in 0..S or NULL (argmax path
+ * :618-619).  L_in: k x C (the `probs` argument).  Outputs: L_out k x C (bestprobs), mw_out[k], returns ll
+ * (llold of the last inner iteration, :661-662).  faithful_cost != 0 recomputes the contraction in every
+ * inner iteration as the reference does (identical values when theta is given). */
+double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *phi,
+                     const int32_t *theta, const double *L_in, const double *mw_in, int complete, double logtype,
+                     int faithful_cost, double *L_out, double *mw_out, int32_t *theta_used)
+{
+    const int SS = S * S;
+    size_t kc = (size_t)k * C;
+    double *probs = (double *)malloc(sizeof(double) * kc);
+    double *probs0 = (double *)malloc(sizeof(double) * kc);
+    double *best = (double *)malloc(sizeof(double) * kc);
+    double *post = (double *)malloc(sizeof(double) * kc);
+    double *scratch = (double *)malloc(sizeof(double) * kc);
+    uint8_t *clo = (uint8_t *)malloc((size_t)k * SS);
+    int32_t *th = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E);
+    double *Wtmp = theta ? NULL : (double *)malloc(sizeof(double) * (size_t)E * (S + 1));
+    memcpy(probs, L_in, sizeof(double) * kc);
+    memcpy(best, L_in, sizeof(double) * kc);                                      /* :581 */
+    double mw[256];
+    for (int i = 0; i < k; i++) mw[i] = mw_in ? mw_in[i] : 1.0 / k;
+    int max_count = C <= 100 ? 100 : 10;                                          /* :584-588 */
+    double llold = -INFINITY;
+    mw_update(probs, k, C, mw, complete, logtype, 1, scratch);                   /* :591-595 */
+    for (int i = 0; i < k; i++) { memcpy(clo + (size_t)i * SS, phi + (size_t)i * SS, SS);
+        for (int q = 0; q < SS; q++) clo[(size_t)i * SS + q] = clo[(size_t)i * SS + q] != 0;
+        orc_mytc(clo + (size_t)i * SS, S); }                                     /* :610 */
+    int have0 = 0;
+    for (int count = 0; count < max_count; count++) {                            /* converged = -Inf: never stops early */
+        if (!theta) orc_get_affinity(probs, k, C, mw, 0, complete, logtype, post);   /* :601-603 (probsold = probs) */
+        if (!theta || faithful_cost || !have0) {
+            for (int i = 0; i < k; i++) {
+                const uint8_t *A = clo + (size_t)i * SS;
+                int32_t *thi = th + (size_t)i * E;
+                if (!theta) {
+                    /* :619 maxCol_row( (data * gamma_i) %*% cbind(adj1, 0) ), ascending-cell double sums */
+                    memset(Wtmp, 0, sizeof(double) * (size_t)E * (S + 1));
+                    for (int c = 0; c < C; c++) {
+                        double g = post[i + (size_t)c * k];
+                        const double *d = D + (size_t)c * E;
+                        int p = pert[c] - 1;
+                        for (int j = 0; j < S; j++)
+                            if (A[p + j * S]) {
+                                double *w = Wtmp + (size_t)j * E;
+                                for (int e = 0; e < E; e++) w[e] += d[e] * g;
+                            }
+                    }
+                    orc_max_col_row(Wtmp, E, S + 1, thi);                         /* values 1..S+1 */
+                } else {
+                    for (int e = 0; e < E; e++) { int t = theta[(size_t)i * E + e]; thi[e] = t == 0 ? S + 1 : t; }  /* :621-622 */
+                }
+                /* :624,631 L[i,c] = colSums(data * t(adj1[, subtopo])) : long-double, ascending e */
+                for (int c = 0; c < C; c++) {
+                    const double *d = D + (size_t)c * E;
+                    int p = pert[c] - 1;
+                    acc_t s = 0;
+                    for (int e = 0; e < E; e++) {
+                        int t = thi[e];
+                        if (t <= S && A[p + (t - 1) * S]) s += d[e];
+                    }
+                    probs0[i + (size_t)c * k] = (double)s;
+                }
+            }
+            have0 = 1;
+        }
+        double ll0 = orc_get_ll(probs0, k, C, mw, complete, logtype);            /* :643 */
+        if (ll0 - llold > 0) memcpy(best, probs0, sizeof(double) * kc);          /* :646-648 */
+        memcpy(probs, probs0, sizeof(double) * kc);                              /* :649 */
+        mw_update(probs, k, C, mw, complete, logtype, 0, scratch);               /* :653-657 */
+        llold = ll0;                                                             /* :658 */
+    }
+    memcpy(L_out, best, sizeof(double) * kc);
+    for (int i = 0; i < k; i++) mw_out[i] = mw[i];
+    if (theta_used) for (size_t i = 0; i < (size_t)k * E; i++) theta_used[i] = th[i] == S + 1 ? 0 : th[i];
+    free(probs); free(probs0); free(best); free(post); free(scratch); free(clo); free(th); free(Wtmp);
+    return llold;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* EM for one start: mnem()::do_inits, R/mnems.r:1884-2165, init != NULL branch (explicit phi).          */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int max_trace;          /* capacity of the trace arrays */
+    int complete;           /* mnem(complete=) */
+    double logtype;         /* mnem(logtype=) */
+    int faithful_cost;      /* recompute redundant work like the reference (timing only) */
+    int max_iter_guard;     /* hard stop for runaway loops (the reference has none when increase=TRUE) */
+} orc_em_opts;
+
+typedef struct {
+    double ll;              /* limits$ll = max(lls) */
+    double best_ll;
+    int n_iter;             /* EM loop iterations executed (count) */
+    long n_scored;          /* candidate graphs scored in all greedy searches */
+    long n_greedy_iter;
+    double min_margin;
+} orc_em_info;
+
+/* outputs: adj_out k*S*S (reduced, diag 0), theta_out k*E, L_out k*C (bestprobs), mw_out k (bestmw),
+ * lls/phievo/thetaevo/mwevo traces of length n_iter. */
+void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *init_phi,
+                  const orc_em_opts *o, uint8_t *adj_out, int32_t *theta_out, double *L_out, double *mw_out,
+                  double *lls, double *phievo, double *thetaevo, double *mwevo, orc_em_info *info)
+{
+    const int SS = S * S;
+    size_t kc = (size_t)k * C;
+    double logtype = o->logtype;
+    int complete = o->complete;
+    double *probs = (double *)malloc(sizeof(double) * kc);        /* probs$probs */
+    double *probsold = (double *)malloc(sizeof(double) * kc);
+    double *newp = (double *)malloc(sizeof(double) * kc);
+    double *post = (double *)malloc(sizeof(double) * kc);
+    double *scratch = (double *)malloc(sizeof(double) * kc);
+    double *gam = (double *)malloc(sizeof(double) * C);
+    double *Rk = (double *)malloc(sizeof(double) * (size_t)E * S);
+    uint8_t *res1_adj = (uint8_t *)malloc((size_t)k * SS), *res_adj = (uint8_t *)malloc((size_t)k * SS);
+    int32_t *res1_th = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E), *res_th = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E);
+    uint8_t *bestadj = (uint8_t *)malloc((size_t)k * SS);
+    int32_t *bestth = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E);
+    int have_res1_theta = 0;
+    double mw[256], bestmw[256], mwnew[256];
+    for (int i = 0; i < k; i++) mw[i] = 1.0 / k;                                   /* R/mnems.r:1771-1773 */
+    memcpy(res1_adj, init_phi, (size_t)k * SS);                                   /* :1885-1893 */
+    memset(res1_th, 0, sizeof(int32_t) * (size_t)k * E);
+    memset(probs, 0, sizeof(double) * kc);                                        /* :1905 */
+    double probs_ll = orc_get_probs(D, E, C, pert, S, k, res1_adj, NULL, probs, mw, complete, logtype,
+                                    o->faithful_cost, newp, mwnew, NULL);         /* :1906-1911 */
+    memcpy(probs, newp, sizeof(double) * kc);
+    for (int i = 0; i < k; i++) mw[i] = mwnew[i];                                  /* :1913 */
+    mw_update(probs, k, C, mw, complete, logtype, 1, scratch);                    /* :1936-1940 */
+    double ll = -INFINITY, llold = -INFINITY, bestll = -INFINITY;                 /* :1945-1948 */
+    for (int i = 0; i < k; i++) bestmw[i] = mw[i];
+    memcpy(probsold, probs, sizeof(double) * kc);
+    double probsold_ll = probs_ll;
+    double *bestprobs = (double *)malloc(sizeof(double) * kc);
+    memcpy(bestprobs, probs, sizeof(double) * kc);
+    memcpy(bestadj, res1_adj, (size_t)k * SS);
+    memset(bestth, 0, sizeof(int32_t) * (size_t)k * E);
+    int count = 0, time0 = 1, stop = 0;
+    long nscored = 0, ngreedy = 0;
+    double minmargin = INFINITY;
+    /* :1955-1958 with converged=-Inf, increase=TRUE: (ll - llold > -Inf & |ll - llold| > 0) | time0, & !stop.
+     * `count < max_iter` binds only to the !increase arm (operator precedence). */
+    while ((((ll - llold > -INFINITY) && fabs(ll - llold) > 0) || time0) && !stop) {
+        if (!time0) {
+            if (ll - bestll > 0) {                                                /* :1960-1963 */
+                bestll = ll; memcpy(bestadj, res1_adj, (size_t)k * SS);
+                memcpy(bestth, res1_th, sizeof(int32_t) * (size_t)k * E);
+                memcpy(bestprobs, probs, sizeof(double) * kc);
+                for (int i = 0; i < k; i++) bestmw[i] = mw[i];
+            }
+            llold = ll;                                                           /* :1964-1965 */
+            memcpy(probsold, probs, sizeof(double) * kc); probsold_ll = probs_ll;
+        }
+        orc_get_affinity(probs, k, C, mw, 0, complete, logtype, post);            /* :1968-1973 */
+        double edgechange = 0, thetachange = 0;
+        for (int i = 0; i < k; i++) {                                             /* :1976-2086 */
+            for (int c = 0; c < C; c++) gam[c] = post[i + (size_t)c * k];
+            uint8_t a0[ORC_MAXS * ORC_MAXS], a1[ORC_MAXS * ORC_MAXS];
+            int32_t *t0 = (int32_t *)malloc(sizeof(int32_t) * E), *t1 = (int32_t *)malloc(sizeof(int32_t) * E);
+            orc_nem_info i0, i1;
+            orc_do_mean(D, E, C, pert, S, gam, Rk);                               /* nem :101-107 */
+            orc_nem_greedy(Rk, E, S, NULL, a0, t0, &i0);                          /* j == 1: start0*0 :2042 */
+            if (o->faithful_cost) orc_do_mean(D, E, C, pert, S, gam, Rk);
+            orc_nem_greedy(Rk, E, S, res1_adj + (size_t)i * SS, a1, t1, &i1);     /* j == 2: start0 :2040 */
+            nscored += i0.n_scored + i1.n_scored; ngreedy += i0.n_iter + i1.n_iter;
+            if (i0.min_margin < minmargin) minmargin = i0.min_margin;
+            if (i1.min_margin < minmargin) minmargin = i1.min_margin;
+            int pick1 = i1.max_trace > i0.max_trace;                              /* which.max: tie -> j == 1 :2072-2073 */
+            memcpy(res_adj + (size_t)i * SS, pick1 ? a1 : a0, SS);
+            memcpy(res_th + (size_t)i * E, pick1 ? t1 : t0, sizeof(int32_t) * E);
+            for (int q = 0; q < SS; q++)                                          /* :2080-2081 */
+                edgechange += abs((int)res_adj[(size_t)i * SS + q] - (int)res1_adj[(size_t)i * SS + q]);
+            if (have_res1_theta)                                                  /* :2082-2083 (NULL != x sums to 0) */
+                for (int e = 0; e < E; e++) thetachange += res_th[(size_t)i * E + e] != res1_th[(size_t)i * E + e];
+            free(t0); free(t1);
+        }
+        memcpy(res1_adj, res_adj, (size_t)k * SS);                                /* :2092 */
+        memcpy(res1_th, res_th, sizeof(int32_t) * (size_t)k * E);
+        have_res1_theta = 1;
+        /* E-step :2095-2108 */
+        double newll = orc_get_probs(D, E, C, pert, S, k, res1_adj, res1_th, probsold, mw, complete, logtype,
+                                     o->faithful_cost, newp, mwnew, NULL);
+        if (newll > probsold_ll) { memcpy(probs, newp, sizeof(double) * kc); probs_ll = newll; }
+        else { memcpy(probs, probsold, sizeof(double) * kc); probs_ll = probsold_ll; }
+        ll = probs_ll;                                                            /* :2111, evopen = 0 */
+        double mwold[256];
+        for (int i = 0; i < k; i++) mwold[i] = mw[i];
+        mw_update(probs, k, C, mw, complete, logtype, 0, scratch);                /* :2113-2121 */
+        acc_t dm = 0;
+        for (int i = 0; i < k; i++) dm += fabs(mw[i] - mwold[i]);
+        if (count < o->max_trace) { lls[count] = ll; phievo[count] = edgechange; thetaevo[count] = thetachange;
+                                    mwevo[count] = (double)dm; }
+        count++;
+        if (edgechange == 0 && thetachange == 0 && !time0) stop = 1;              /* :2138-2141 */
+        time0 = 0;
+        if (o->max_iter_guard > 0 && count >= o->max_iter_guard) break;
+    }
+    if (ll - bestll > 0) {                                                        /* :2144-2147 */
+        bestll = ll; memcpy(bestadj, res1_adj, (size_t)k * SS);
+        memcpy(bestth, res1_th, sizeof(int32_t) * (size_t)k * E);
+        memcpy(bestprobs, probs, sizeof(double) * kc);
+        for (int i = 0; i < k; i++) bestmw[i] = mw[i];
+    }
+    memcpy(adj_out, bestadj, (size_t)k * SS);
+    memcpy(theta_out, bestth, sizeof(int32_t) * (size_t)k * E);
+    memcpy(L_out, bestprobs, sizeof(double) * kc);
+    for (int i = 0; i < k; i++) mw_out[i] = bestmw[i];
+    double mx = -INFINITY;
+    int nt = count < o->max_trace ? count : o->max_trace;
+    for (int i = 0; i < nt; i++) if (lls[i] > mx) mx = lls[i];
+    info->ll = mx;                                                                /* limits$ll <- max(lls) :2157 */
+    info->best_ll = bestll; info->n_iter = count; info->n_scored = nscored; info->n_greedy_iter = ngreedy;
+    info->min_margin = minmargin;
+    free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk);
+    free(res1_adj); free(res_adj); free(res1_th); free(res_th); free(bestadj); free(bestth); free(bestprobs);
+}
+
+/* All starts (lapply / sfLapply over do_inits, R/mnems.r:2166-2170) and the winner (:2222-2230: `<=` so the
+ * LAST maximal start wins).  Per-start outputs are laid out start-major.  nthreads > 1 runs starts in
+ * parallel like snowfall `parallel = n` (results are independent of the thread count).
+ * Returns the 0-based index of the winning start. */
+int orc_mnem_em(const double *D, int E, int C, const int32_t *pert, int S, int k, int starts,
+                const uint8_t *init_phi, const orc_em_opts *o, int nthreads, uint8_t *adj_out, int32_t *theta_out,
+                double *L_out, double *mw_out, double *lls, double *phievo, double *thetaevo, double *mwevo,
+                orc_em_info *infos)
+{
+    const size_t SS = (size_t)S * S;
+    int s;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#endif
+    for (s = 0; s < starts; s++)
+        orc_em_start(D, E, C, pert, S, k, init_phi + (size_t)s * k * SS, o, adj_out + (size_t)s * k * SS,
+                     theta_out + (size_t)s * k * E, L_out + (size_t)s * k * C, mw_out + (size_t)s * k,
+                     lls + (size_t)s * o->max_trace, phievo + (size_t)s * o->max_trace,
+                     thetaevo + (size_t)s * o->max_trace, mwevo + (size_t)s * o->max_trace, infos + s);
+    int best = 0;
+    for (s = 1; s < starts; s++) if (infos[best].ll <= infos[s].ll) best = s;
+    return best;
+}
+
+/* Final mixture weights of the returned object: lambda0, R/mnems.r:2298-2303. */
+void orc_final_mw(const double *L, int k, int C, const double *mw_best, int complete, double logtype, double *out)
+{
+    for (int i = 0; i < k; i++) out[i] = mw_best[i];
+    if (k == 1) { out[0] = 1.0; return; }
+    double *scratch = (double *)malloc(sizeof(double) * (size_t)k * C);
+    mw_update(L, k, C, out, complete, logtype, 0, scratch);
+    free(scratch);
+}
+
+int orc_acc_bits(void) { return (int)(sizeof(acc_t) * 8); }
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
