@@ -19,7 +19,7 @@ c_i32p = C.POINTER(C.c_int32)
 
 class NemInfo(C.Structure):
     _fields_ = [("score", C.c_double), ("max_trace", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
-                ("min_margin", C.c_double)]
+                ("min_margin", C.c_double), ("n_raw", C.c_long)]
 
 
 class EmOpts(C.Structure):
@@ -29,7 +29,7 @@ class EmOpts(C.Structure):
 
 class EmInfo(C.Structure):
     _fields_ = [("ll", C.c_double), ("best_ll", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
-                ("n_greedy_iter", C.c_long), ("min_margin", C.c_double)]
+                ("n_greedy_iter", C.c_long), ("min_margin", C.c_double), ("n_raw", C.c_long)]
 
 
 def build():
@@ -207,7 +207,7 @@ def nem_greedy(R, start=None, acc="ld"):
     info = NemInfo()
     lib(acc).orc_nem_greedy(_d(R), E, S, _u8(sb) if sb is not None else None, _u8(adj), _i32(theta), C.byref(info))
     return dict(adj=_ungraphs(adj, 1, S)[0], theta=theta, score=info.score, max_trace=info.max_trace,
-                n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin)
+                n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin, n_raw=info.n_raw)
 
 
 # ---- E-step ----------------------------------------------------------------------------------------------
@@ -254,7 +254,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     res = dict(best=best, adj=adj, theta=theta, probs=np.transpose(L, (0, 2, 1)).copy(), mw=mw,
                ll=np.array([i.ll for i in infos]), n_iter=n_iter,
                n_scored=np.array([i.n_scored for i in infos]), n_greedy_iter=np.array([i.n_greedy_iter for i in infos]),
-               min_margin=np.array([i.min_margin for i in infos]),
+               min_margin=np.array([i.min_margin for i in infos]), n_raw=np.array([i.n_raw for i in infos]),
                lls=[tr[0][s, :n_iter[s]].copy() for s in range(starts)],
                phievo=[tr[1][s, :n_iter[s]].copy() for s in range(starts)],
                thetaevo=[tr[2][s, :n_iter[s]].copy() for s in range(starts)],

@@ -395,6 +395,7 @@ typedef struct {
     int n_iter;          /* accepted moves */
     long n_scored;       /* scoreAdj calls inside the loop (unique candidates) */
     double min_margin;   /* smallest |best - runner-up or old| seen in a decision, relative; diagnostic */
+    long n_raw;          /* candidates generated before unique() */
 } orc_nem_info;
 
 void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t *adj_out, int32_t *theta_out,
@@ -413,11 +414,13 @@ void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t
     int haveP = 0;
     double oldscore = orc_score_adj(R, E, S, better, 1, NULL, NULL);             /* :135-141 closes inside */
     double maxtrace = oldscore;
-    long nscored = 0;
+    long nscored = 0, nraw = 0;
     int niter = 0;
     double minmargin = INFINITY;
     for (;;) {
-        int nm = orc_neighbours(better, S, models, kind, NULL);
+        int nr1 = 0;
+        int nm = orc_neighbours(better, S, models, kind, &nr1);
+        nraw += nr1;
         if (nm == 0) break;
         double bests = -INFINITY, second = -INFINITY;
         int bestidx = -1;
@@ -462,7 +465,7 @@ void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t
     orc_score_adj(R, E, S, better, 1, theta_out, NULL);
     orc_trans_reduce(better, S, adj_out);
     if (info) { info->score = oldscore; info->max_trace = maxtrace; info->n_iter = niter; info->n_scored = nscored;
-                info->min_margin = minmargin; }
+                info->min_margin = minmargin; info->n_raw = nraw; }
     free(P); free(Wc); free(Pbest); free(models); free(kind);
 }
 
@@ -566,6 +569,7 @@ typedef struct {
     long n_scored;          /* candidate graphs scored in all greedy searches */
     long n_greedy_iter;
     double min_margin;
+    long n_raw;             /* candidates generated before unique() */
 } orc_em_info;
 
 /* outputs: adj_out k*S*S (reduced, diag 0), theta_out k*E, L_out k*C (bestprobs), mw_out k (bestmw),
@@ -609,7 +613,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     memcpy(bestadj, res1_adj, (size_t)k * SS);
     memset(bestth, 0, sizeof(int32_t) * (size_t)k * E);
     int count = 0, time0 = 1, stop = 0;
-    long nscored = 0, ngreedy = 0;
+    long nscored = 0, ngreedy = 0, nraw = 0;
     double minmargin = INFINITY;
     /* :1955-1958 with converged=-Inf, increase=TRUE: (ll - llold > -Inf & |ll - llold| > 0) | time0, & !stop.
      * `count < max_iter` binds only to the !increase arm (operator precedence). */
@@ -635,7 +639,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
             orc_nem_greedy(Rk, E, S, NULL, a0, t0, &i0);                          /* j == 1: start0*0 :2042 */
             if (o->faithful_cost) orc_do_mean(D, E, C, pert, S, gam, Rk);
             orc_nem_greedy(Rk, E, S, res1_adj + (size_t)i * SS, a1, t1, &i1);     /* j == 2: start0 :2040 */
-            nscored += i0.n_scored + i1.n_scored; ngreedy += i0.n_iter + i1.n_iter;
+            nscored += i0.n_scored + i1.n_scored; ngreedy += i0.n_iter + i1.n_iter; nraw += i0.n_raw + i1.n_raw;
             if (i0.min_margin < minmargin) minmargin = i0.min_margin;
             if (i1.min_margin < minmargin) minmargin = i1.min_margin;
             int pick1 = i1.max_trace > i0.max_trace;                              /* which.max: tie -> j == 1 :2072-2073 */
@@ -683,7 +687,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     for (int i = 0; i < nt; i++) if (lls[i] > mx) mx = lls[i];
     info->ll = mx;                                                                /* limits$ll <- max(lls) :2157 */
     info->best_ll = bestll; info->n_iter = count; info->n_scored = nscored; info->n_greedy_iter = ngreedy;
-    info->min_margin = minmargin;
+    info->min_margin = minmargin; info->n_raw = nraw;
     free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk);
     free(res1_adj); free(res_adj); free(res1_th); free(res_th); free(bestadj); free(bestth); free(bestprobs);
 }

@@ -1,0 +1,75 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol include/mnemcu.h declares,
+and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mnem_b200 as mb
+from mnem_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mnemcu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mnemcu_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    decl = _declared()
+    assert len(decl) >= 25
+    assert sorted(_lib.SIGNATURES) == decl, set(decl) ^ set(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in _declared():
+        assert hasattr(lib, name), name
+    assert mb.load_library().mnemcu_version() >= 100
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under mnem_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "mnem_b200")
+    for dp_, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp_, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "mnem_oracle" not in txt, f
+
+
+@pytest.mark.skipif(mb.api.load_library() is None, reason="library missing")
+def test_compute_fails_loudly_without_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(mb.MnemcuError):
+        mb.getLL(np.zeros((2, 8)))
+    with pytest.raises(mb.MnemcuError):
+        mb.Context(np.zeros((4, 8)), np.array([1, 2] * 4))
+    with pytest.raises(mb.MnemcuError):
+        mb.transitive_closure(np.eye(3))
+
+
+def test_argument_validation_is_reported_not_crashed():
+    lib = mb.load_library()
+    rc = lib.mnemcu_trans_close_w(None, 3, 1)
+    assert rc == 1 and b"NULL" in lib.mnemcu_last_error()
+    x = np.zeros(40 * 40, dtype=np.uint8)
+    rc = lib.mnemcu_trans_close_w(_lib.u8p(x), 40, 1)          # S > 32 is outside this build
+    assert rc == 1
+
+
+def test_mod_data_natural_order():
+    pert, S, labs = mb.mod_data(["g10", "g2", "g1", "g2", "g10"])
+    assert labs == ["g1", "g2", "g10"] and S == 3
+    assert pert.tolist() == [3, 2, 1, 2, 3]
+    with pytest.raises(NotImplementedError):
+        mb.mod_data(["1_2", "1"])

@@ -1,0 +1,340 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (north star): graphs, theta, closures and every other integer output bit-exact; log-likelihoods,
+responsibilities, mixture weights and scores within 1e-9 relative (tolerances written at each assert; most
+comparisons are far tighter because both sides use fixed summation orders).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import mnem_b200 as mb
+import oracle as orc
+from mnem_b200 import simdata
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "app_rda_golden.npz"))
+KEYS = sorted(k[:-6] for k in G.files if k.endswith("_probs"))
+
+
+def rand_graph(rng, S, p=0.25, dag=False):
+    a = (rng.random((S, S)) < p).astype(np.uint8)
+    if dag:
+        a = np.triu(a, 1)
+    np.fill_diagonal(a, 0)
+    return a
+
+
+def close(a, b, rtol=RTOL, atol=0.0):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+# ---- src/mm.cpp -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [1, 2, 3, 7, 13, 24, 31, 32])
+def test_mm_cpp_graph_routines(S):
+    rng = np.random.default_rng(S)
+    gs = np.stack([rand_graph(rng, S, rng.uniform(0.02, 0.5), dag=i % 2 == 0) for i in range(24)])
+    got = mb.transClose_W(gs)
+    for g, o in zip(gs, got):
+        assert (o == orc.trans_close_w(g)).all()
+    got = mb.transitive_closure(gs)
+    red = mb.transitive_reduction(gs)
+    for g, o, r in zip(gs, got, red):
+        assert (o == orc.mytc(g)).all()
+        assert (r == orc.transitive_reduction(g)).all()
+    u = rng.integers(1, S + 1, len(gs))
+    v = rng.integers(1, S + 1, len(gs))
+    ins = mb.transClose_Ins(gs, u, v)
+    dele = mb.transClose_Del(gs, u, v)
+    for i, g in enumerate(gs):
+        assert (ins[i] == orc.trans_close_ins(g, u[i], v[i])).all()
+        assert (dele[i] == orc.trans_close_del(g, u[i], v[i])).all()
+
+
+def test_closure_roxygen_example():
+    g = np.array([0, 0, 0, 1, 0, 0, 0, 1, 0], dtype=float).reshape(3, 3, order="F")     # R/mnems.r:547
+    assert (mb.transitive_closure(g) == np.triu(np.ones((3, 3)))).all()
+    assert (mb.transitive_closure(g, 1, 2) == orc.mytc(g, 1, 2)).all()
+
+
+def test_maxcol_and_matmul():
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(257, 9))
+    x[5] = x[5, 0]                       # ties -> first
+    x[6, :] = -np.inf
+    assert (mb.maxCol_row(x) == orc.max_col_row(x)).all()
+    A, B = rng.normal(size=(131, 17)), rng.normal(size=(17, 5))
+    assert np.array_equal(mb.eigenMapMatMult(A, B), orc.matmul(A, B))   # same ascending mul/add order: bit-exact
+
+
+@pytest.mark.parametrize("S", [2, 3, 5, 9, 16, 30])
+def test_neighbours(S):
+    rng = np.random.default_rng(300 + S)
+    for t in range(8):
+        P = rand_graph(rng, S, rng.uniform(0.03, 0.4), dag=t % 2 == 0)
+        if t % 3 == 0:
+            P = orc.mytc(P)
+        np.fill_diagonal(P, 1)
+        got, kind = mb.neighbours(P)
+        want, wkind, nraw = orc.neighbours(P)
+        assert len(got) == nraw
+        uniq, ukind = [], []
+        for m, kd in zip(got, kind):                        # unique(): keep first, R/mnems.r:222
+            if not any((m == q).all() for q in uniq):
+                uniq.append(m)
+                ukind.append(kd)
+        assert len(uniq) == len(want)
+        assert all((a == b).all() for a, b in zip(uniq, want))
+        assert list(ukind) == list(wkind)
+
+
+# ---- responsibilities / likelihood ------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", KEYS)
+def test_getll_app_rda_known_answers(key):
+    """The reference's own fitted objects: ll must equal getLL(probs, mw) (data/app.rda)."""
+    probs, mw, ll = G[key + "_probs"], G[key + "_mw"], G[key + "_ll"]
+    got = mb.getLL(probs, mw=mw)
+    assert abs(got - ll.max()) <= 1e-12 * abs(ll.max())
+    g = mb.getAffinity(probs, mw=mw)
+    close(g, orc.get_affinity(probs, mw), rtol=1e-12)
+    if probs.shape[0] > 1:                                   # inst/unitTests/test_hardClustering.R
+        hard = mb.getAffinity(probs, affinity=1, mw=mw)
+        assert (hard == orc.get_affinity(probs, mw, affinity=1)).all()
+        assert (hard == (g == g.max(0, keepdims=True))).all()
+
+
+@pytest.mark.parametrize("k,complete,logtype", [(1, False, 2), (2, False, 2), (3, True, 2), (5, True, 2), (4, False, np.e),
+                                                (3, True, 10)])
+def test_affinity_and_ll_random(k, complete, logtype):
+    rng = np.random.default_rng(k)
+    L = rng.normal(size=(k, 3001)) * 40
+    mw = rng.random(k)
+    mw /= mw.sum()
+    close(mb.getAffinity(L, mw=mw, complete=complete, logtype=logtype),
+          orc.get_affinity(L, mw, complete=complete, logtype=logtype), rtol=1e-11, atol=1e-300)
+    got, want = mb.getLL(L, mw=mw, complete=complete, logtype=logtype), orc.get_ll(L, mw, complete=complete, logtype=logtype)
+    assert abs(got - want) <= 1e-11 * abs(want)
+    close(mb.getAffinity(-np.abs(L), complete=complete), orc.get_affinity(-np.abs(L), None, complete=complete), rtol=1e-11,
+          atol=1e-300)
+
+
+def test_overflow_semantics_q9():
+    """complete = FALSE: 2^L overflows for L >= 1024 -> ll = Inf, gamma NaN -> 0."""
+    L = np.array([[1100.0, 3.0, -2000.0], [1100.0, 1.0, -2100.0]])
+    assert mb.getLL(L) == orc.get_ll(L) == np.inf
+    assert np.array_equal(mb.getAffinity(L), orc.get_affinity(L))
+    close(mb.getAffinity(L, complete=True), orc.get_affinity(L, complete=True), rtol=1e-12)
+
+
+# ---- M-step statistics, scoring, greedy search -------------------------------------------------------------------
+@pytest.mark.parametrize("S,E,Cn", [(3, 1, 7), (5, 10, 1000), (10, 101, 5003), (30, 257, 4000)])
+def test_do_mean(S, E, Cn):
+    rng = np.random.default_rng(S * E)
+    D = rng.normal(size=(E, Cn))
+    pert = rng.integers(1, S + 1, Cn).astype(np.int32)
+    pert[:S] = np.arange(1, S + 1)
+    w = rng.random((7, Cn))
+    w[rng.random((7, Cn)) < 0.05] = 0.0
+    with mb.Context(D, pert) as cx:
+        R = mb.doMean(cx, w)
+        R0 = mb.doMean(cx)
+    for j in range(7):
+        close(R[j], orc.do_mean(D, pert, S, w[j]), rtol=1e-11, atol=1e-11)
+    close(R0, orc.do_mean(D, pert, S), rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize("S,E", [(2, 3), (5, 10), (10, 100), (20, 333), (30, 1000), (32, 129)])
+def test_score_adj(S, E):
+    rng = np.random.default_rng(S + E)
+    R = rng.normal(size=(E, S)) * 3
+    adjs = np.stack([rand_graph(rng, S, rng.uniform(0.02, 0.5)) for _ in range(40)])
+    for tc in (True, False):
+        got = mb.scoreAdj(R, adjs, trans_close=tc)
+        for i, a in enumerate(adjs):
+            sc, th, W = orc.score_adj(R, a, trans_close=tc)
+            assert np.array_equal(got["subweights"][i], W)          # same ascending S-gene sums: bit-exact
+            assert np.array_equal(got["subtopo"][i], th)
+            assert abs(got["score"][i] - sc) <= 1e-12 * abs(sc) + 1e-300
+
+
+def planted_R(rng, S, E, snr=4.0):
+    truth = orc.mytc(rand_graph(rng, S, 0.3, dag=True))
+    truth = truth[np.ix_(rng.permutation(S), rng.permutation(S))]
+    theta = rng.integers(1, S + 1, E)
+    return np.where(truth[:, theta - 1].T > 0, 1.0, -1.0) * snr + rng.normal(size=(E, S)) * 3
+
+
+@pytest.mark.parametrize("S,E,n", [(2, 5, 4), (3, 10, 6), (5, 20, 8), (8, 60, 6), (10, 100, 6), (16, 130, 4), (20, 300, 2)])
+def test_nem_greedy(S, E, n):
+    rng = np.random.default_rng(1000 + S)
+    R = np.stack([planted_R(rng, S, E) for _ in range(n)])
+    starts = np.stack([orc.transitive_reduction(rand_graph(rng, S, 0.15, dag=i % 2 == 0)) if i % 3 else np.zeros((S, S))
+                       for i in range(n)])
+    got = mb.nem_greedy(R, starts)
+    got0 = mb.nem_greedy(R, None)
+    for i in range(n):
+        for g, st in ((got, starts[i]), (got0, None)):
+            want = orc.nem_greedy(R[i], st)
+            assert want["min_margin"] > 1e-11, "test case has a near-tie; pick another seed"
+            assert np.array_equal(g["adj"][i], want["adj"])
+            assert np.array_equal(g["subtopo"][i], want["theta"])
+            assert g["n_iter"][i] == want["n_iter"]
+            assert g["n_scored"][i] == want["n_raw"]
+            assert abs(g["score"][i] - want["score"]) <= 1e-12 * abs(want["score"])
+            assert abs(g["max_trace"][i] - want["max_trace"]) <= 1e-12 * abs(want["max_trace"])
+
+
+def test_nem_greedy_structural_ties():
+    """Exact score ties (duplicate E-gene rows, S-genes without effects): first maximum / sparser graph must win
+    exactly as in R/mnems.r:236, 279-283."""
+    rng = np.random.default_rng(77)
+    S, E = 6, 24
+    R = planted_R(rng, S, E)
+    R[:, 4] = R[:, 3]                   # two indistinguishable S-genes
+    R[:, 5] = -1.0                      # an S-gene no E-gene likes
+    R = np.round(R * 4) / 4             # coarse values: many exact ties
+    want = orc.nem_greedy(R, None)
+    got = mb.nem_greedy(R, None)
+    assert np.array_equal(got["adj"], want["adj"]) and np.array_equal(got["subtopo"], want["theta"])
+    assert got["n_iter"] == want["n_iter"] and abs(got["score"] - want["score"]) <= 1e-12 * abs(want["score"])
+
+
+# ---- E-step ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,E,Cn,k,complete", [(3, 4, 50, 2, False), (5, 10, 1000, 2, False), (7, 33, 2100, 3, True),
+                                               (10, 100, 3001, 4, False), (30, 300, 5000, 5, True), (6, 20, 777, 1, False)])
+def test_get_probs_theta_given(S, E, Cn, k, complete):
+    rng = np.random.default_rng(S * k)
+    D = rng.normal(size=(E, Cn))
+    pert = rng.integers(1, S + 1, Cn).astype(np.int32)
+    res = [dict(adj=orc.transitive_reduction(rand_graph(rng, S, 0.3)), subtopo=rng.integers(0, S + 1, E).astype(np.int32))
+           for _ in range(k)]
+    L_in = rng.normal(size=(k, Cn))
+    mw = rng.random(k)
+    mw /= mw.sum()
+    got = mb.getProbs(L_in, k, D, res, pert=pert, mw=mw, complete=complete)
+    want = orc.get_probs(D, pert, S, np.stack([r["adj"] for r in res]), np.stack([r["subtopo"] for r in res]), L_in, mw,
+                         complete=complete)
+    close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
+    close(got["mw"], want["mw"], rtol=1e-10)
+    assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
+
+
+@pytest.mark.parametrize("S,E,Cn,k", [(3, 6, 90, 2), (5, 10, 1000, 2), (8, 40, 2500, 3), (20, 120, 4000, 5)])
+def test_get_probs_theta_free(S, E, Cn, k):
+    """First E-step of a start: theta = argmax with the null column last (R/mnems_low.r:617-619)."""
+    sim = simdata.make_config(dict(S=S, Egenes=E // S, C=Cn, mw=[1.0 / k] * k, k=k, starts=1, uninform=E % S), seed=S)
+    D = simdata.host_data(sim) + np.random.default_rng(S).normal(size=(sim["E"], sim["C"])) * 0.25
+    phi = simdata.init_phi(S, k, 1, seed=5)[0]
+    res = [dict(adj=p) for p in phi]
+    L0 = np.zeros((k, sim["C"]))
+    got = mb.getProbs(L0, k, D, res, pert=sim["pert"])
+    want = orc.get_probs(D, sim["pert"], S, phi, None, L0, None)
+    assert np.array_equal(got["theta_used"], want["theta_used"])
+    close(got["probs"], want["probs"], rtol=1e-10, atol=1e-10)
+    close(got["mw"], want["mw"], rtol=RTOL)
+    assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
+
+
+# ---- the EM loop -------------------------------------------------------------------------------------------------
+def check_em(sim, D, init, complete, batch=0):
+    ref = orc.mnem_em(D, sim["pert"], sim["S"], init, complete=complete, nthreads=8)
+    res = mb.mnem(D, sim["pert"], phi=init, complete=complete, batch=batch)
+    starts = init.shape[0]
+    assert ref["min_margin"].min() > 1e-11, "a greedy decision in this case is a near-tie; pick another seed"
+    for s in range(starts):
+        lim = res["limits"][s]
+        assert np.array_equal(lim["adj"], ref["adj"][s]), "phi of start %d" % s
+        assert np.array_equal(lim["theta"], ref["theta"][s]), "theta of start %d" % s
+        assert res["n_iter"][s] == ref["n_iter"][s]
+        assert abs(lim["ll"] - ref["ll"][s]) <= RTOL * abs(ref["ll"][s])
+        close(lim["probs"], ref["probs"][s], rtol=RTOL, atol=1e-9)
+        close(lim["mw"], ref["mw"][s], rtol=RTOL)
+        close(lim["lls"], ref["lls"][s], rtol=RTOL)
+        assert np.array_equal(lim["phievo"], ref["phievo"][s]) and np.array_equal(lim["thetaevo"], ref["thetaevo"][s])
+        close(lim["mwevo"], ref["mwevo"][s], rtol=1e-6, atol=1e-12)
+    # winner: last maximal ll (R/mnems.r:2226).  Starts that reach the same optimum differ in the last bits of ll
+    # (SURVEY Q12), so the GPU's winner must be one of the oracle's maximal starts up to 1e-9.
+    top = ref["ll"].max()
+    assert abs(ref["ll"][res["best_start"]] - top) <= RTOL * abs(top)
+    assert res["stats"]["em_iters"] == ref["n_iter"].sum()
+    assert res["stats"]["cand_scored"] == ref["n_raw"].sum()
+    lam = orc.final_mw(ref["probs"][res["best_start"]], ref["mw"][res["best_start"]], complete=complete)
+    close(res["mw"], lam, rtol=RTOL)
+    return res, ref
+
+
+def test_em_config1_readme_toy():
+    sim = simdata.make_config(1)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(sim["S"], sim["k"], sim["starts"], seed=1)
+    check_em(sim, D, init, complete=False)
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_em_small_gaussian(batch):
+    sim = simdata.make_config(dict(S=6, Egenes=5, C=1500, mw=[0.3, 0.3, 0.4], k=3, starts=5, uninform=2), seed=12)
+    D = simdata.host_data(sim) + np.random.default_rng(3).normal(size=(sim["E"], sim["C"])) * 0.5
+    init = simdata.init_phi(sim["S"], 3, 5, seed=2)
+    check_em(sim, D, init, complete=False, batch=batch)
+
+
+def test_em_config2_shape_complete():
+    """BASELINE config 2 shape (S=10, E=100, ~10k cells, k=3), 6 starts, complete = TRUE."""
+    sim = simdata.make_config(2)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(sim["S"], 3, 6, seed=4)
+    check_em(sim, D, init, complete=True)
+
+
+def test_em_few_cells_100_inner_iterations():
+    """C <= 100 switches getProbs to 100 inner iterations (R/mnems_low.r:584-588)."""
+    sim = simdata.make_config(dict(S=3, Egenes=4, C=90, mw=[0.5, 0.5], k=2, starts=3, uninform=0), seed=5)
+    D = simdata.host_data(sim)
+    assert sim["C"] <= 100
+    init = simdata.init_phi(3, 2, 3, seed=6)
+    check_em(sim, D, init, complete=False)
+
+
+def test_mnem_k1_branch():
+    sim = simdata.make_config(dict(S=5, Egenes=6, C=800, mw=[1.0], k=1, starts=1, uninform=0), seed=8)
+    D = simdata.host_data(sim)
+    start = simdata.init_phi(5, 1, 1, seed=1)[0, 0]
+    res = mb.mnem(D, sim["pert"], phi=start[None, None])
+    R = orc.do_mean(D, sim["pert"], 5)
+    fit = orc.nem_greedy(R, start)
+    pr = orc.get_probs(D, sim["pert"], 5, fit["adj"][None], fit["theta"][None], np.zeros((1, sim["C"])), np.ones(1))
+    assert np.array_equal(res["comp"][0]["phi"], fit["adj"]) and np.array_equal(res["comp"][0]["theta"], fit["theta"])
+    assert abs(res["ll"] - pr["ll"]) <= RTOL * abs(pr["ll"])
+
+
+# ---- data context ------------------------------------------------------------------------------------------------
+def test_device_generator_matches_host_generator():
+    sim = simdata.make_config(dict(S=7, Egenes=9, C=3000, mw=[0.4, 0.6], k=2, starts=1, uninform=5), seed=33)
+    D = simdata.host_data(sim)
+    with mb.Context.synthetic(sim) as cx:
+        assert np.array_equal(cx.read_data(), D)
+        assert np.array_equal(cx.read_data(1234, 77), D[:, 1234:1311])
+        R = mb.doMean(cx)
+    close(R, orc.do_mean(D, sim["pert"], sim["S"]), rtol=1e-11, atol=1e-11)
+    with mb.Context(D, sim["pert"]) as cx:
+        assert np.array_equal(cx.read_data(), D)
+
+
+def test_ragged_segments_and_missing_padding():
+    """Segments of very different sizes (1 cell, 63, 64, 65, 1000 cells) exercise the 64-cell padding."""
+    rng = np.random.default_rng(9)
+    sizes = [1, 63, 64, 65, 1000, 2]
+    pert = np.concatenate([np.full(n, i + 1) for i, n in enumerate(sizes)]).astype(np.int32)
+    pert = pert[rng.permutation(len(pert))]
+    S, E, k = len(sizes), 37, 2
+    D = rng.normal(size=(E, len(pert)))
+    res = [dict(adj=rand_graph(rng, S, 0.3), subtopo=rng.integers(0, S + 1, E).astype(np.int32)) for _ in range(k)]
+    L_in = np.zeros((k, len(pert)))
+    got = mb.getProbs(L_in, k, D, res, pert=pert)
+    want = orc.get_probs(D, pert, S, np.stack([r["adj"] for r in res]), np.stack([r["subtopo"] for r in res]), L_in, None)
+    close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
+    assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
+    w = rng.random(len(pert))
+    close(mb.doMean(D, w, pert), orc.do_mean(D, pert, S, w), rtol=1e-11, atol=1e-11)
