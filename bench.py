@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- the EM hot path of M&NEM on B200: EM iterations/s, candidate-graph scores/s, E-step HBM GB/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 5] [--starts S] [--impl ours|reference]
+  N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one complete EM phase of mnem(D, phi = init): every EM start of the config (sharded over the ranks,
+start s on rank s mod N; D replicated) runs do_inits to convergence (R/mnems.r:1884-2165).  `value` = EM loop
+iterations summed over all starts and ranks / device time of the step (CUDA events inside the library, max over
+ranks), with D already resident in HBM.  `e2e` times the same step through the C ABI from HOST buffers: the H2D copy
+of D (pinned memory), the layout pass, the EM phase and the D2H copy of the results are all inside the timed region.
+The default workload is BASELINE.json's scaling config (30 S-genes x 2000 E-genes x 1M cells, k = 5, 100 starts).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=5)
+    ap.add_argument("--starts", type=int, default=0, help="override the config's number of EM starts")
+    ap.add_argument("--cells", type=int, default=0, help="override the config's number of cells")
+    ap.add_argument("--batch", type=int, default=0, help="EM starts per pass over D (0: k*batch <= 20)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-cells", type=int, default=0, help="cells in the CPU-baseline sample (0: auto)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+def make_workload(args):
+    from mnem_b200 import simdata
+    cfg = dict(simdata.CONFIGS[args.config])
+    if args.cells:
+        cfg["C"] = args.cells
+    if args.starts:
+        cfg["starts"] = args.starts
+    sim = simdata.make_config(cfg, seed=1000 + args.config)
+    init = simdata.init_phi(sim["S"], sim["k"], sim["starts"], seed=2000 + args.config)
+    name = "cfg%d: simData-style S=%d E=%d C=%d k=%d starts=%d complete=%s" % (
+        args.config, sim["S"], sim["E"], sim["C"], sim["k"], sim["starts"], sim["complete"])
+    return sim, init, name
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (R cannot be installed in this image)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_sample(sim, init, n_threads, cells):
+    """EM iterations/s of the CPU restatement on a bounded sample: the first `cells` cells of the same data, one EM
+    start per thread, INIT phase + exactly one EM loop iteration each (max_iter_guard = 1), with the reference's
+    redundant recomputation switched on (faithful_cost)."""
+    import oracle as orc
+    from mnem_b200 import simdata
+    cells = min(cells, sim["C"])
+    D = simdata.host_data_native(sim, 0, cells, nthreads=max(1, n_threads))
+    pert = sim["pert"][:cells]
+    ph = init[:n_threads]
+    t0 = time.time()
+    r = orc.mnem_em(D, pert, sim["S"], ph, complete=sim["complete"], nthreads=n_threads, faithful_cost=True,
+                    max_iter_guard=1)
+    dt = time.time() - t0
+    return dict(value=float(r["n_iter"].sum() / dt), seconds=dt, em_iters=int(r["n_iter"].sum()),
+                cand_scored=int(r["n_scored"].sum()), cells=cells, starts=len(ph))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sim, init, name = make_workload(args)
+    import oracle as orc
+    nthr = min(os.cpu_count() or 1, sim["starts"], orc.lib().orc_max_threads())
+    cells = args.cpu_cells or max(2000, sim["C"] // 64)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_sample(sim, init, nthr, cells)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([x["value"] for x in vals]))
+    sample = ("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R): %d starts in parallel, first %d of %d cells, "
+              "INIT + 1 EM iteration each, redundant passes kept" % (vals[0]["starts"], vals[0]["cells"], sim["C"]))
+    line = {"impl": "reference", "metric": "em_iterations_per_s", "value": v, "unit": "EM iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(np.mean([x["seconds"] for x in vals])), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "EM iterations/s", "cores": nthr, "kind": "port", "sample": sample},
+            "cand_scores_per_s": float(np.mean([x["cand_scored"] / x["seconds"] for x in vals])),
+            "e2e": {"value": v, "unit": "EM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mnem_b200 as mb
+    from mnem_b200 import dist as mdist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sim, init, name = make_workload(args)
+    my = mdist.shard_starts(sim["starts"], rank, world)
+    my_init = init[my]
+    k, E, Cn, S = sim["k"], sim["E"], sim["C"], sim["S"]
+    launches0 = mb.launch_count()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(xs):
+        t = torch.tensor(xs, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    # ---- value: D resident in HBM ----
+    cx = mb.Context.synthetic(sim, device=local)
+    recs = []
+    sampler = ClockSampler(local)
+    launches_timed = 0
+    for i in range(args.warmup + args.steps):
+        if i == args.warmup:
+            sampler.start()
+            launches_timed = mb.launch_count()
+        barrier()
+        t0 = time.time()
+        r = mb.em_run(cx, my_init, complete=sim["complete"], batch=args.batch, want_probs=False) if len(my) else None
+        torch.cuda.synchronize()
+        wall = time.time() - t0
+        barrier()
+        st = r["stats"] if r else dict(ms_total=0.0, em_iters=0, cand_scored=0, ms_estep=0.0, passes_estep=0,
+                                       estep_bytes=0.0, ms_search=0.0, ms_mstats=0.0, passes_mstats=0, ms_mixture=0.0,
+                                       greedy_iters=0)
+        ms = reduce_max(st["ms_total"])
+        tot = reduce_sum([st["em_iters"], st["cand_scored"], st["greedy_iters"]])
+        if i >= args.warmup:
+            recs.append(dict(ms=ms, wall=reduce_max(wall), em_iters=tot[0], cand=tot[1], st=st))
+        winner, lls = mdist.gather_winner(my, r["ll"] if r else [], sim["starts"], device=dev)
+    clocks = sampler.stop()
+    launches_timed = mb.launch_count() - launches_timed
+    ms_step = float(np.mean([x["ms"] for x in recs]))
+    em_iters = float(np.mean([x["em_iters"] for x in recs]))
+    value = em_iters / (ms_step * 1e-3)
+    st = recs[-1]["st"]
+    peak, peak_kind = peaks()
+    t_estep = st["ms_estep"] / max(1, st["passes_estep"]) * 1e-3
+    bytes_launch = st["estep_bytes"] / max(1, st["passes_estep"])
+    achieved = bytes_launch / t_estep / 1e9 if t_estep > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "estep_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "estep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+                "traffic": traffic, "algorithmic_bytes_per_launch": bytes_launch, "ms_per_launch": t_estep * 1e3,
+                "launches_per_step": st["passes_estep"],
+                "pairs_per_launch": (bytes_launch - 8.0 * E * Cn) / (8.0 * Cn),
+                "share_of_step": st["ms_estep"] / max(st["ms_total"], 1e-9)}
+    breakdown = {"ms_estep": st["ms_estep"], "ms_mstats": st["ms_mstats"], "ms_search": st["ms_search"],
+                 "ms_mixture": st["ms_mixture"], "ms_total": st["ms_total"], "passes_estep": st["passes_estep"],
+                 "passes_mstats": st["passes_mstats"]}
+    cand_rate = float(np.mean([x["cand"] for x in recs])) / (ms_step * 1e-3)
+    cand_rate_search = float(np.sum(reduce_sum([st["cand_scored"]]))) / max(1e-9, reduce_max(st["ms_search"]) * 1e-3)
+    cx.close()
+
+    # ---- e2e: host buffers in, host buffers out ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            import psutil
+            need = 8.0 * E * Cn
+            if psutil.virtual_memory().available < 2.5 * need * max(1, world):
+                raise MemoryError("not enough host memory for a pinned copy of D on every rank")
+            host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)       # column-major E x C
+            Dh = host.numpy().T
+            with mb.Context.synthetic(sim, device=local) as c0:
+                mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(host.numpy())))
+            times, iters = [], []
+            for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
+                barrier()
+                t0 = time.time()
+                with mb.Context(Dh, sim["pert"], device=local) as cxe:
+                    r = mb.em_run(cxe, my_init, complete=sim["complete"], batch=args.batch, want_probs=False) if len(my) else None
+                torch.cuda.synchronize()
+                dt = reduce_max(time.time() - t0)
+                barrier()
+                if i >= 1:
+                    times.append(dt)
+                    iters.append(reduce_sum([r["stats"]["em_iters"] if r else 0])[0])
+            d2h = len(my) * (k * S * S + 4 * k * E + 8 * k + 8 + 4 + 4 * 8 * 256)
+            e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
+                   "h2d_bytes_per_step": int(8 * E * Cn + 4 * Cn + len(my) * k * S * S), "d2h_bytes_per_step": int(d2h),
+                   "seconds_per_step": float(np.mean(times)), "steps": len(times)}
+            del host
+        except Exception as ex:                                                    # noqa: BLE001
+            e2e = {"value": None, "unit": "EM iterations/s", "error": repr(ex)[:200]}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cells = args.cpu_cells or max(2000, Cn // 64)
+        c = cpu_sample(sim, init, 1, cells)
+        cpu = {"value": c["value"], "unit": "EM iterations/s", "cores": 1, "kind": "port",
+               "sample": "oracle port (C restatement, not R): 1 start, first %d of %d cells, INIT + 1 EM iteration, "
+                         "redundant passes kept; %.1f s" % (c["cells"], Cn, c["seconds"]),
+               "cand_scores_per_s": c["cand_scored"] / c["seconds"]}
+    if rank == 0:
+        line = {"metric": "em_iterations_per_s", "value": value, "unit": "EM iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": name, "starts_per_rank": len(my), "batch": args.batch or max(1, 20 // k),
+                           "l2": "inputs larger than L2 (D = %.1f GB per layout)" % (8e-9 * E * Cn),
+                           "candidate_count": "graphs generated and scored, before unique()"},
+                "em_iters_per_step": em_iters, "cand_scores_per_s": cand_rate,
+                "cand_scores_per_s_in_search": cand_rate_search, "estep_gbs": achieved,
+                "roofline": roofline, "breakdown_last_step_rank0": breakdown, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches_timed), "clocks": clocks, "winner_start": int(winner),
+                "wall_ms_per_step": 1e3 * float(np.mean([x["wall"] for x in recs]))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

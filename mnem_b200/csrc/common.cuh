@@ -81,6 +81,11 @@ struct DevBuf {
     }
 };
 
+// An empty volatile asm inside a conditional block keeps the compiler from if-converting `if (bit) acc += x` into
+// an unconditional FP64 add plus two 32-bit selects; ptxas then emits a predicated DADD (one issue slot, and no
+// FP64-pipe work when the bit is clear).
+#define MN_KEEP_BRANCH() asm volatile("")
+
 constexpr int kBlkCells = 64;      // cells per streamed block (one warp, two cells per lane)
 constexpr unsigned kFull = 0xffffffffu;
 

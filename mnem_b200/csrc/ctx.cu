@@ -171,10 +171,12 @@ static int ctx_layout(mnemcu_ctx *cx, int E, int C, const int32_t *pert, int S, 
     MN_CU(cudaMemcpy(cx->pos, cx->h_pos.data(), sizeof(int32_t) * C, cudaMemcpyHostToDevice));
     MN_CU(cudaMemcpy(cx->orig, cx->h_orig.data(), sizeof(int32_t) * cx->h_orig.size(), cudaMemcpyHostToDevice));
     MN_CU(cudaMemcpy(cx->blk_seg, cx->h_blk_seg.data(), sizeof(int32_t) * cx->h_blk_seg.size(), cudaMemcpyHostToDevice));
-    const size_t ncol = (size_t)cx->Cp * cx->Epad, nblkE = (size_t)cx->nblk * E * kBlkCells;
+    const size_t ncol = (size_t)cx->Cp * cx->Epad;
+    const size_t nblkE = ((size_t)cx->nblk * E + 256) * kBlkCells;   // 256 E-genes of slack: the E-step reads whole groups of 32 per warp
     cudaError_t e1 = cudaMalloc((void **)&cx->Dcol, sizeof(double) * std::max<size_t>(1, ncol));
     if (e1 != cudaSuccess) return set_err(MNEMCU_ERR_NOMEM, "cudaMalloc Dcol (%zu bytes): %s", ncol * 8, cudaGetErrorString(e1));
     e1 = cudaMalloc((void **)&cx->Dblk, sizeof(double) * std::max<size_t>(1, nblkE));
+    if (e1 == cudaSuccess) e1 = cudaMemset(cx->Dblk + (size_t)cx->nblk * E * kBlkCells, 0, sizeof(double) * 256 * kBlkCells);
     if (e1 != cudaSuccess) return set_err(MNEMCU_ERR_NOMEM, "cudaMalloc Dblk (%zu bytes): %s", nblkE * 8, cudaGetErrorString(e1));
     return 0;
 }

@@ -131,7 +131,7 @@ __device__ __forceinline__ double col_sum(const double (&r)[SP], uint32_t m)
     double w = 0.0;
 #pragma unroll
     for (int s = 0; s < SP; ++s)
-        if ((m >> s) & 1u) w += r[s];
+        if ((m >> s) & 1u) { MN_KEEP_BRANCH(); w += r[s]; }
     return w;
 }
 

@@ -18,70 +18,71 @@ namespace mn {
 // ([Cp] doubles) because the EM slots rotate their k x C buffers independently.  No cross-lane reduction is needed: each lane
 // accumulates its own cells in ascending E-gene order, exactly the order of colSums() in the reference.
 //
-// grid = (nblk, groups of MT pairs), block = 32 * esplit threads; warp w covers E-genes [w*eper, (w+1)*eper).
+// grid = nblk, block = 32 * groups * esplit threads: warp (g, w) serves pairs [g*MT, (g+1)*MT) over the E-genes
+// [w*eper, (w+1)*eper).  The `groups` warps that share a cell block sit in the same CTA, so only the first of them
+// pulls a line from HBM; the others hit L1/L2.
+//
+// The masked add is written as a real branch (MN_KEEP_BRANCH) so that ptxas emits predicated DADDs fed by R2P
+// (1 issue slot per pair and cell); left alone it if-converts to DADD + 2 FSEL, three issue slots per add.
 // ---------------------------------------------------------------------------------------------------------
 template <int MT>
 __global__ void __launch_bounds__(256) estep_kernel(const double *__restrict__ Dblk, int E,
                                                     const uint32_t *__restrict__ maskT,
                                                     const int32_t *__restrict__ blk_seg, int M, int eper,
-                                                    PairPtrs out)
+                                                    int groups, PairPtrs out)
 {
-    extern __shared__ double2 s_part[];   // [esplit-1][MT][32] partial sums of warps 1..
+    extern __shared__ double2 s_part[];   // [groups][esplit-1][MT][32] partial sums of warps 1..
     const int blk = blockIdx.x;
-    const int m0 = blockIdx.y * MT;
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nwarp = blockDim.x >> 5;
-    const int seg = blk_seg[blk];
+    const int grp = (threadIdx.x >> 5) % groups;
+    const int warp = (threadIdx.x >> 5) / groups;          // E-gene range index
+    const int nwarp = (blockDim.x >> 5) / groups;
+    const int m0 = grp * MT;
     const int ebeg = warp * eper;
     const int eend = min(E, ebeg + eper);
     const double2 *base = reinterpret_cast<const double2 *>(Dblk + (size_t)blk * E * kBlkCells) + lane;
-    const uint32_t *mk = maskT + (size_t)seg * E;
+    const uint32_t *mk = maskT + (size_t)blk_seg[blk] * E;
 
-    double2 acc[MT];
+    // scalar accumulators (not double2): ptxas then adds in place under the predicate instead of via a temporary
+    double ax[MT], ay[MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = make_double2(0.0, 0.0);
+    for (int m = 0; m < MT; ++m) { ax[m] = 0.0; ay[m] = 0.0; }
 
-    for (int e0 = ebeg; e0 < eend; e0 += 32) {
-        uint32_t wv = (e0 + lane < eend) ? (__ldg(mk + e0 + lane) >> m0) : 0u;
-        const int n = min(32, eend - e0);
-        if (n == 32) {
+    // E-genes are taken 32 at a time and EVERY warp runs the same number of groups (eper / 32): with a uniform trip
+    // count the compiler knows the __shfl_sync below is convergent and emits one copy of the loop.  A range may run
+    // past eend / E; those reads stay inside the allocation (256 E-genes of slack) and their mask words are zero.
+    const int nit = eper >> 5;
+    for (int it = 0; it < nit; ++it) {
+        const int e0 = ebeg + (it << 5);
+        const uint32_t wv = (e0 + lane < eend) ? (__ldg(mk + e0 + lane) >> m0) : 0u;
 #pragma unroll
-            for (int jb = 0; jb < 32; jb += 8) {
-                double2 d[8];
+        for (int jb = 0; jb < 32; jb += 8) {
+            double2 d[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) d[j] = ld_stream2(base + (size_t)(e0 + jb + j) * 32);
+            for (int j = 0; j < 8; ++j) d[j] = ld_stream2(base + (size_t)(e0 + jb + j) * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t w = __shfl_sync(kFull, wv, jb + j);
-#pragma unroll
-                    for (int m = 0; m < MT; ++m)
-                        if ((w >> m) & 1u) { acc[m].x += d[j].x; acc[m].y += d[j].y; }
-                }
-            }
-        } else {
-            for (int j = 0; j < n; ++j) {
-                const double2 d = ld_stream2(base + (size_t)(e0 + j) * 32);
-                const uint32_t w = __shfl_sync(kFull, wv, j);
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t w = __shfl_sync(kFull, wv, jb + j);
 #pragma unroll
                 for (int m = 0; m < MT; ++m)
-                    if ((w >> m) & 1u) { acc[m].x += d.x; acc[m].y += d.y; }
+                    if ((w >> m) & 1u) { MN_KEEP_BRANCH(); ax[m] += d[j].x; ay[m] += d[j].y; }
             }
         }
     }
     if (nwarp > 1) {   // combine the E-gene ranges in ascending order (fixed shape => deterministic)
         if (warp > 0) {
 #pragma unroll
-            for (int m = 0; m < MT; ++m) s_part[((warp - 1) * MT + m) * 32 + lane] = acc[m];
+            for (int m = 0; m < MT; ++m)
+                s_part[((grp * (nwarp - 1) + warp - 1) * MT + m) * 32 + lane] = make_double2(ax[m], ay[m]);
         }
         __syncthreads();
         if (warp == 0) {
             for (int w = 1; w < nwarp; ++w)
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
-                    const double2 p = s_part[((w - 1) * MT + m) * 32 + lane];
-                    acc[m].x += p.x;
-                    acc[m].y += p.y;
+                    const double2 p = s_part[((grp * (nwarp - 1) + w - 1) * MT + m) * 32 + lane];
+                    ax[m] += p.x;
+                    ay[m] += p.y;
                 }
         }
     }
@@ -89,8 +90,8 @@ __global__ void __launch_bounds__(256) estep_kernel(const double *__restrict__ D
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
             if (m0 + m < M) {   // warp-uniform
-                reinterpret_cast<double2 *>(out.L[m0 + m] + (size_t)blk * kBlkCells)[lane] = acc[m];
-                const bool pos = acc[m].x > 0.0 || acc[m].y > 0.0;
+                reinterpret_cast<double2 *>(out.L[m0 + m] + (size_t)blk * kBlkCells)[lane] = make_double2(ax[m], ay[m]);
+                const bool pos = ax[m] > 0.0 || ay[m] > 0.0;
                 const unsigned any = __ballot_sync(kFull, pos);
                 if (any && lane == 0) atomicOr(out.flag[m0 + m], 1);   // any(L > 0), R/mnems.r:1422
             }
@@ -104,34 +105,29 @@ static int launch_estep_t(const mnemcu_ctx *cx, const uint32_t *maskT, int M, co
 {
     const int groups = (M + MT - 1) / MT;
     const int eper = ((cx->E + esplit - 1) / esplit + 31) / 32 * 32;
-    dim3 grid(cx->nblk, groups);
-    size_t smem = esplit > 1 ? (size_t)(esplit - 1) * MT * 32 * sizeof(double2) : 0;
-    MN_LAUNCH(estep_kernel<MT>, grid, 32 * esplit, smem, st, cx->Dblk, cx->E, maskT, cx->blk_seg, M, eper, out);
+    size_t smem = esplit > 1 ? (size_t)groups * (esplit - 1) * MT * 32 * sizeof(double2) : 0;
+    MN_LAUNCH(estep_kernel<MT>, cx->nblk, 32 * groups * esplit, smem, st, cx->Dblk, cx->E, maskT, cx->blk_seg, M, eper,
+              groups, out);
     return 0;
 }
 
 int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairPtrs &out, cudaStream_t st)
 {
     MN_ARG(M >= 1 && M <= 32, "E-step serves 1..32 (start, component) pairs per launch");
-    // Pairs per warp: at most 10 (20 FP64 accumulators per lane); split evenly above that.  The second group
-    // re-reads the block from L1/L2, not from HBM.
-    const int groups = (M + 9) / 10;
+    // Pairs per warp: up to 20 (40 FP64 accumulators per lane, 125 registers); above that two warps of the same CTA
+    // split the pairs and the second one re-reads the block from L1/L2, not from HBM.
+    const int groups = (M + 19) / 20;
     const int MT = (M + groups - 1) / groups;
     // Few blocks (small C): split the E-gene range over up to 8 warps so that every SM still has loads in flight.
     int esplit = 1;
     const long warps = (long)cx->nblk * groups;
-    while (esplit < 8 && warps * esplit < 16L * cx->sm_count && cx->E / (esplit * 2) >= 64) esplit *= 2;
+    while (esplit * groups < 8 && warps * esplit < 16L * cx->sm_count && cx->E / (esplit * 2) >= 64) esplit *= 2;
     switch (MT) {
-        case 1: return launch_estep_t<1>(cx, maskT, M, out, esplit, st);
-        case 2: return launch_estep_t<2>(cx, maskT, M, out, esplit, st);
-        case 3: return launch_estep_t<3>(cx, maskT, M, out, esplit, st);
-        case 4: return launch_estep_t<4>(cx, maskT, M, out, esplit, st);
-        case 5: return launch_estep_t<5>(cx, maskT, M, out, esplit, st);
-        case 6: return launch_estep_t<6>(cx, maskT, M, out, esplit, st);
-        case 7: return launch_estep_t<7>(cx, maskT, M, out, esplit, st);
-        case 8: return launch_estep_t<8>(cx, maskT, M, out, esplit, st);
-        case 9: return launch_estep_t<9>(cx, maskT, M, out, esplit, st);
-        default: return launch_estep_t<10>(cx, maskT, M, out, esplit, st);
+#define MN_CASE(v) case v: return launch_estep_t<v>(cx, maskT, M, out, esplit, st);
+        MN_CASE(1) MN_CASE(2) MN_CASE(3) MN_CASE(4) MN_CASE(5) MN_CASE(6) MN_CASE(7) MN_CASE(8) MN_CASE(9) MN_CASE(10)
+        MN_CASE(11) MN_CASE(12) MN_CASE(13) MN_CASE(14) MN_CASE(15) MN_CASE(16) MN_CASE(17) MN_CASE(18) MN_CASE(19)
+#undef MN_CASE
+        default: return launch_estep_t<20>(cx, maskT, M, out, esplit, st);
     }
 }
 
@@ -166,67 +162,92 @@ int launch_build_masks(const mnemcu_ctx *cx, const uint32_t *clo, const int32_t 
 //
 // grid = (E-gene tiles, chunks, groups of MT pairs), block = tpb threads.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSub = 64;   // cells whose weights are staged in shared memory at a time
+constexpr int kSub = 64;   // cells whose weights are staged in shared memory at a time (chunks are multiples of 64 cells)
 
-template <int MT>
-__global__ void __launch_bounds__(256) mstats_kernel(const double *__restrict__ Dcol, int Epad,
-                                                     const double *__restrict__ gam, int M, int Cp,
-                                                     const int32_t *__restrict__ chunk_cp0,
-                                                     const int32_t *__restrict__ chunk_n, double *__restrict__ partial)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
-    __shared__ double s_g[kSub][MT];
-    const int chunk = blockIdx.y;
-    const int m0 = blockIdx.z * MT;
-    const int e = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// grid = (groups of MT pairs, E-gene tiles, chunks), block = tpb threads.  Two software pipelines keep HBM busy:
+// the weights of the NEXT 64 cells are fetched with cp.async while the current 64 are consumed, and the D values
+// of the next 4 cells are in flight (registers) while the current 4 are multiplied.
+template <int MT>
+__global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict__ Dcol, int Epad,
+                                                        const double *__restrict__ gam, int M, int Cp,
+                                                        const int32_t *__restrict__ chunk_cp0,
+                                                        const int32_t *__restrict__ chunk_n, double *__restrict__ partial)
+{
+    constexpr int MTP = (MT + 1) & ~1;                 // even row length: weights are fetched as double2
+    __shared__ __align__(16) double s_g[2][kSub][MTP];
+    const int chunk = blockIdx.z;
+    const int m0 = blockIdx.x * MT;                     // groups vary fastest: the CTAs that re-read a tile run together
+    const int e = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
     const bool live = e < Epad;
     const int cp0 = chunk_cp0[chunk];
-    const int n = chunk_n[chunk];
-    double2 acc[MT];
+    const int n = chunk_n[chunk];                       // multiple of 64
+    double ax[MT], ay[MT];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) acc[m] = make_double2(0.0, 0.0);
-    for (int c0 = 0; c0 < n; c0 += kSub) {
-        const int nc = min(kSub, n - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < kSub * MT; i += blockDim.x) {
-            const int m = i / kSub, c = i - m * kSub;     // consecutive threads read consecutive cells
-            double g = 0.0;
-            if (c < nc && m0 + m < M) g = gam ? gam[(size_t)(m0 + m) * Cp + cp0 + c0 + c] : 1.0;
-            s_g[c][m] = g;
+    for (int m = 0; m < MT; ++m) { ax[m] = 0.0; ay[m] = 0.0; }
+
+    auto stage = [&](int buf, int c0) {
+        for (int i = threadIdx.x; i < kSub * MTP; i += blockDim.x) {
+            const int m = i / kSub, c = i - m * kSub;   // consecutive threads fetch consecutive cells
+            double *dst = &s_g[buf][c][m];
+            if (m < MT && m0 + m < M) {
+                if (gam) cp_async8(dst, gam + (size_t)(m0 + m) * Cp + cp0 + c0 + c);
+                else *dst = 1.0;
+            } else {
+                *dst = 0.0;
+            }
         }
+        cp_async_commit();
+    };
+
+    const double2 *p = reinterpret_cast<const double2 *>(Dcol + (size_t)cp0 * Epad + (live ? e : 0));
+    const size_t stride = (size_t)Epad / 2;
+    double2 dn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dn[j] = ld_stream2(p + (size_t)j * stride);
+    stage(0, 0);
+    int buf = 0;
+    for (int c0 = 0; c0 < n; c0 += kSub, buf ^= 1) {
+        if (c0 + kSub < n) { stage(buf ^ 1, c0 + kSub); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
-        if (live) {
-            const double2 *p = reinterpret_cast<const double2 *>(Dcol + (size_t)(cp0 + c0) * Epad + e);
-            const size_t stride = (size_t)Epad / 2;
-            int c = 0;
-            for (; c + 4 <= nc; c += 4) {
-                double2 d[4];
+#pragma unroll 2
+        for (int cl = 0; cl < kSub; cl += 4) {
+            double2 d[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = ld_stream2(p + (size_t)(c + j) * stride);
+            for (int j = 0; j < 4; ++j) d[j] = dn[j];
+            const int cn = c0 + cl + 4;
+            if (cn < n) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 4; ++j) dn[j] = ld_stream2(p + (size_t)(cn + j) * stride);
+            }
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const double g = s_g[c + j][m];
-                        acc[m].x = fma(d[j].x, g, acc[m].x);
-                        acc[m].y = fma(d[j].y, g, acc[m].y);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int m = 0; m < MT; m += 2) {
+                    const double2 g = *reinterpret_cast<const double2 *>(&s_g[buf][cl + j][m]);   // broadcast LDS.128
+                    ax[m] = fma(d[j].x, g.x, ax[m]);
+                    ay[m] = fma(d[j].y, g.x, ay[m]);
+                    if (m + 1 < MT) {
+                        ax[m + 1] = fma(d[j].x, g.y, ax[m + 1]);
+                        ay[m + 1] = fma(d[j].y, g.y, ay[m + 1]);
                     }
-            }
-            for (; c < nc; ++c) {
-                const double2 d = ld_stream2(p + (size_t)c * stride);
-#pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const double g = s_g[c][m];
-                    acc[m].x = fma(d.x, g, acc[m].x);
-                    acc[m].y = fma(d.y, g, acc[m].y);
                 }
-            }
         }
+        __syncthreads();
     }
     if (live) {
 #pragma unroll
         for (int m = 0; m < MT; ++m)
             if (m0 + m < M)
-                *reinterpret_cast<double2 *>(partial + ((size_t)chunk * M + m0 + m) * Epad + e) = acc[m];
+                *reinterpret_cast<double2 *>(partial + ((size_t)chunk * M + m0 + m) * Epad + e) = make_double2(ax[m], ay[m]);
     }
 }
 
@@ -250,7 +271,7 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, doubl
     const int pairs = cx->Epad / 2;
     int tpb = 256;
     while (tpb > 32 && tpb / 2 >= pairs) tpb /= 2;
-    dim3 grid((pairs + tpb - 1) / tpb, cx->nchunk, (M + MT - 1) / MT);
+    dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
     MN_LAUNCH(mstats_kernel<MT>, grid, tpb, 0, st, cx->Dcol, cx->Epad, gam, M, cx->Cp, cx->chunk_cp0, cx->chunk_n,
               partial);
     return 0;
@@ -259,20 +280,15 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, doubl
 int launch_mstats(const mnemcu_ctx *cx, const double *gam, int M, double *partial, double *R, cudaStream_t st)
 {
     MN_ARG(M >= 1 && M <= 32, "M-step statistics serve 1..32 pairs per launch");
-    const int groups = (M + 9) / 10;
+    const int groups = (M + 19) / 20;
     const int MT = (M + groups - 1) / groups;
     int rc;
     switch (MT) {
-        case 1: rc = launch_mstats_t<1>(cx, gam, M, partial, st); break;
-        case 2: rc = launch_mstats_t<2>(cx, gam, M, partial, st); break;
-        case 3: rc = launch_mstats_t<3>(cx, gam, M, partial, st); break;
-        case 4: rc = launch_mstats_t<4>(cx, gam, M, partial, st); break;
-        case 5: rc = launch_mstats_t<5>(cx, gam, M, partial, st); break;
-        case 6: rc = launch_mstats_t<6>(cx, gam, M, partial, st); break;
-        case 7: rc = launch_mstats_t<7>(cx, gam, M, partial, st); break;
-        case 8: rc = launch_mstats_t<8>(cx, gam, M, partial, st); break;
-        case 9: rc = launch_mstats_t<9>(cx, gam, M, partial, st); break;
-        default: rc = launch_mstats_t<10>(cx, gam, M, partial, st); break;
+#define MN_CASE(v) case v: rc = launch_mstats_t<v>(cx, gam, M, partial, st); break;
+        MN_CASE(1) MN_CASE(2) MN_CASE(3) MN_CASE(4) MN_CASE(5) MN_CASE(6) MN_CASE(7) MN_CASE(8) MN_CASE(9) MN_CASE(10)
+        MN_CASE(11) MN_CASE(12) MN_CASE(13) MN_CASE(14) MN_CASE(15) MN_CASE(16) MN_CASE(17) MN_CASE(18) MN_CASE(19)
+#undef MN_CASE
+        default: rc = launch_mstats_t<20>(cx, gam, M, partial, st); break;
     }
     if (rc) return rc;
     dim3 grid((cx->E + 127) / 128, cx->S, M);

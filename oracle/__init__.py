@@ -24,12 +24,13 @@ class NemInfo(C.Structure):
 
 class EmOpts(C.Structure):
     _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
-                ("max_iter_guard", C.c_int)]
+                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int)]
 
 
 class EmInfo(C.Structure):
     _fields_ = [("ll", C.c_double), ("best_ll", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
-                ("n_greedy_iter", C.c_long), ("min_margin", C.c_double), ("n_raw", C.c_long)]
+                ("n_greedy_iter", C.c_long), ("min_margin", C.c_double), ("n_raw", C.c_long),
+                ("min_accept_margin", C.c_double)]
 
 
 def build():
@@ -232,7 +233,7 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 
 # ---- EM --------------------------------------------------------------------------------------------------
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
-            max_iter_guard=0, acc="ld"):
+            max_iter_guard=0, noise_mode=0, acc="ld"):
     """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
     D = _f(D)
     E, Cn = D.shape
@@ -246,7 +247,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     mw = np.zeros((starts, k))
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     infos = (EmInfo * starts)()
-    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard)
+    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode))
     best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
                                 _i32(theta), _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
     adj = _ungraphs(adj, starts * k, S).reshape(starts, k, S, S)
@@ -255,6 +256,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
                ll=np.array([i.ll for i in infos]), n_iter=n_iter,
                n_scored=np.array([i.n_scored for i in infos]), n_greedy_iter=np.array([i.n_greedy_iter for i in infos]),
                min_margin=np.array([i.min_margin for i in infos]), n_raw=np.array([i.n_raw for i in infos]),
+               min_accept_margin=np.array([i.min_accept_margin for i in infos]),
                lls=[tr[0][s, :n_iter[s]].copy() for s in range(starts)],
                phievo=[tr[1][s, :n_iter[s]].copy() for s in range(starts)],
                thetaevo=[tr[2][s, :n_iter[s]].copy() for s in range(starts)],
