@@ -20,107 +20,187 @@ namespace mn {
 constexpr int kCT = 32;        // candidates per score CTA
 constexpr int kRows = 128;     // E-gene rows per score CTA (= threads)
 
+constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionary (power of two)
+constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
+constexpr int kDictThreads = 512;
+
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
+    int dcap = 0, G = 1;              // dictionary capacity (entries), row groups per search
+    size_t dict_smem = 0;
     DevBuf<const double *> Rptr;
-    DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols;
-    DevBuf<int32_t> ncand, active, niter, n_active, theta;
+    DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks;
+    DevBuf<uint16_t> cand_id, base_id;
+    DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, overflow;
     DevBuf<double> partial, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored;
-    int32_t *h_n_active = nullptr;   // pinned
+    int32_t *h_n_active = nullptr;   // pinned: [0] searches still active, [1] dictionary overflow flag
 };
 
-// ---- candidate generation --------------------------------------------------------------------------------
+// ---- candidate generation + mask dictionary ----------------------------------------------------------------
 // mode 0: the single "candidate" closure(better) used for the initial score (R/mnems.r:135-141)
 // mode 1: all single-edge neighbours of `better`
-__global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int mode, const uint32_t *__restrict__ Prow,
+//
+// Dictionary.  Every candidate differs from the current graph in a few columns, and the same new column mask
+// recurs in many candidates (an insertion u -> v turns column j into col_j | col_u for every j below v, whatever v
+// is).  While the candidates are generated, each changed column mask is entered into a shared-memory hash set;
+// afterwards the occupied slots get dense ids and every candidate keeps, per changed column, the id of its mask.
+// The scoring kernel then sums each distinct mask once per E-gene row instead of once per candidate.  Ids follow
+// hash order; they only index a table, so no result depends on them.
+// For insertions the "changed" set written to cand_J is the whole row of v (the columns the one-step closure may
+// touch): candidates that share v then share the set, and the scoring kernel reuses their unchanged-column maximum.
+__global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int mode, const uint32_t *__restrict__ Prow,
                                                   const int32_t *__restrict__ active, uint32_t *__restrict__ Pcol,
                                                   uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
-                                                  int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind)
+                                                  int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind,
+                                                  uint32_t *__restrict__ dict_masks, int32_t *__restrict__ nd,
+                                                  uint16_t *__restrict__ cand_id, uint16_t *__restrict__ base_id,
+                                                  int32_t *__restrict__ overflow)
 {
-    const int q = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    __shared__ uint32_t keys[kDictHash];
+    __shared__ uint16_t ids[kDictHash];
+    __shared__ int s_warp[8];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     if (!active[q]) {
-        if (threadIdx.x == 0) ncand[q] = 0;
+        if (tid == 0) { ncand[q] = 0; if (nd) nd[q] = 0; }
         return;
     }
+    const bool dict = dict_masks != nullptr;
+    if (dict)
+        for (int i = tid; i < kDictHash; i += 256) keys[i] = 0u;
+    __syncthreads();
+    auto insert = [&](uint32_t m) -> int {          // returns the hash slot of m
+        int h = (int)((m * 2654435761u) >> 21);
+        while (true) {
+            const uint32_t prev = atomicCAS(&keys[h], 0u, m);
+            if (prev == 0u || prev == m) return h;
+            h = (h + 1) & (kDictHash - 1);
+        }
+    };
     const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
     const uint32_t row = lane < S ? (Prow[q * 32 + lane] | (1u << lane)) & smask : 0u;
     const uint32_t col = warp_transpose(row, lane, S);
     uint32_t *cc = cand_cols + (size_t)q * maxc * 32;
     uint32_t *cj = cand_J + (size_t)q * maxc;
-    if (warp == 0) Pcol[q * 32 + lane] = col;
+    uint16_t *ci = dict ? cand_id + (size_t)q * maxc * 32 : nullptr;
+    int total = 0;
+    if (warp == 0) {
+        Pcol[q * 32 + lane] = col;
+        if (dict && lane < S) base_id[q * 32 + lane] = (uint16_t)insert(col);
+    }
     if (mode == 0) {
         if (warp == 0) {
             const uint32_t clo = warp_closure(row, S);
             const uint32_t ccol = warp_transpose(clo, lane, S);
             cc[lane] = ccol;
+            if (dict && lane < S) ci[lane] = (uint16_t)insert(ccol);
             if (lane == 0) { cj[0] = smask; ncand[q] = 1; }
         }
-        return;
-    }
-    const uint32_t T = warp_reduce_graph(row, lane, S);          // rows of transitive.reduction(better)
-    const uint32_t Tcol = warp_transpose(T, lane, S);
-    // lane v owns column v: rows u that yield a candidate, per kind
-    uint32_t km[3];
-    km[0] = lane < S ? (~col & smask) : 0u;                       // which(Phi == 0)            get.ins.fast :1049
-    km[1] = lane < S ? ((Tcol ^ T) & smask) : 0u;                 // Phitr + t(Phitr) == 1      get.rev.tc  :1027
-    km[2] = lane < S ? (Tcol & smask) : 0u;                       // which(Phi2 == 1)           get.del.tc  :1073
-    int off[3], base = 0;
+        total = 1;
+    } else {
+        const uint32_t T = warp_reduce_graph(row, lane, S);          // rows of transitive.reduction(better)
+        const uint32_t Tcol = warp_transpose(T, lane, S);
+        // lane v owns column v: rows u that yield a candidate, per kind
+        uint32_t km[3];
+        km[0] = lane < S ? (~col & smask) : 0u;                       // which(Phi == 0)            get.ins.fast :1049
+        km[1] = lane < S ? ((Tcol ^ T) & smask) : 0u;                 // Phitr + t(Phitr) == 1      get.rev.tc  :1027
+        km[2] = lane < S ? (Tcol & smask) : 0u;                       // which(Phi2 == 1)           get.del.tc  :1073
+        int off[3], base = 0;
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-        const int cnt = __popc(km[kd]);
-        int incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += t;
+        for (int kd = 0; kd < 3; ++kd) {
+            const int cnt = __popc(km[kd]);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += t;
+            }
+            off[kd] = base + incl - cnt;
+            base += __shfl_sync(kFull, incl, 31);
         }
-        off[kd] = base + incl - cnt;
-        base += __shfl_sync(kFull, incl, 31);
-    }
-    if (threadIdx.x == 0) ncand[q] = base;
-    for (int item = warp; item < 3 * S; item += nwarp) {
-        const int kd = item / S, v = item - kd * S;
-        uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
-        int idx = __shfl_sync(kFull, kd == 0 ? off[0] : (kd == 1 ? off[1] : off[2]), v);
-        while (m) {
-            const int u = __ffs(m) - 1;
-            m &= m - 1;
-            uint32_t nc;
-            if (kd == 0) {
-                // Phinew[u,v] = 1; transClose_Ins(u,v): x[i,j] |= x[i,u] && x[v,j]
-                const uint32_t b = col | (lane == v ? (1u << u) : 0u);
-                const uint32_t cu = __shfl_sync(kFull, col, u);
-                nc = ((b >> v) & 1u) ? (b | cu) : b;
-            } else if (kd == 1) {
-                // flip (u,v) and (v,u) in better (row u, column v), then mytc(Phinew, uv): Ins if the edge is there, else Del
-                const int r = u, c = v;
-                const uint32_t f = col ^ (lane == c ? (1u << r) : 0u) ^ (lane == r ? (1u << c) : 0u);
-                const uint32_t fc = __shfl_sync(kFull, f, c);
-                int uu, vv;
-                if ((fc >> r) & 1u) { uu = r; vv = c; } else { uu = c; vv = r; }
-                const uint32_t fv = __shfl_sync(kFull, f, vv);
-                const uint32_t fu = __shfl_sync(kFull, f, uu);
-                if ((fv >> uu) & 1u) {
-                    nc = ((f >> vv) & 1u) ? (f | fu) : f;
+        total = base;
+        if (tid == 0) ncand[q] = base;
+        for (int item = warp; item < 3 * S; item += nwarp) {
+            const int kd = item / S, v = item - kd * S;
+            uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
+            int idx = __shfl_sync(kFull, kd == 0 ? off[0] : (kd == 1 ? off[1] : off[2]), v);
+            const uint32_t rowv = __shfl_sync(kFull, row, v);
+            while (m) {
+                const int u = __ffs(m) - 1;
+                m &= m - 1;
+                uint32_t nc;
+                if (kd == 0) {
+                    // Phinew[u,v] = 1; transClose_Ins(u,v): x[i,j] |= x[i,u] && x[v,j]
+                    const uint32_t b = col | (lane == v ? (1u << u) : 0u);
+                    const uint32_t cu = __shfl_sync(kFull, col, u);
+                    nc = ((b >> v) & 1u) ? (b | cu) : b;
+                } else if (kd == 1) {
+                    // flip (u,v) and (v,u) in better (row u, column v), then mytc(Phinew, uv): Ins if the edge is there, else Del
+                    const int r = u, c = v;
+                    const uint32_t f = col ^ (lane == c ? (1u << r) : 0u) ^ (lane == r ? (1u << c) : 0u);
+                    const uint32_t fc = __shfl_sync(kFull, f, c);
+                    int uu, vv;
+                    if ((fc >> r) & 1u) { uu = r; vv = c; } else { uu = c; vv = r; }
+                    const uint32_t fv = __shfl_sync(kFull, f, vv);
+                    const uint32_t fu = __shfl_sync(kFull, f, uu);
+                    if ((fv >> uu) & 1u) {
+                        nc = ((f >> vv) & 1u) ? (f | fu) : f;
+                    } else {
+                        // transClose_Del: x[uu,vv] = exists k: x[uu,k] && x[k,vv]   (src/mm.cpp:32-48)
+                        const unsigned any = __ballot_sync(kFull, lane < S && ((f >> uu) & 1u) && ((fv >> lane) & 1u));
+                        nc = f | ((lane == vv && any) ? (1u << uu) : 0u);
+                    }
                 } else {
-                    // transClose_Del: x[uu,vv] = exists k: x[uu,k] && x[k,vv]   (src/mm.cpp:32-48)
-                    const unsigned any = __ballot_sync(kFull, lane < S && ((f >> uu) & 1u) && ((fv >> lane) & 1u));
-                    nc = f | ((lane == vv && any) ? (1u << uu) : 0u);
+                    nc = col & ~(lane == v ? (1u << u) : 0u);
                 }
-            } else {
-                nc = col & ~(lane == v ? (1u << u) : 0u);
+                nc &= smask;
+                if (lane >= S) nc = 0u;
+                unsigned J = __ballot_sync(kFull, nc != col);
+                if (kd == 0) J = rowv;                     // superset shared by every insertion into v (diag included)
+                cc[(size_t)idx * 32 + lane] = nc;
+                if (dict && ((J >> lane) & 1u)) ci[(size_t)idx * 32 + lane] = (uint16_t)insert(nc);
+                if (lane == 0) {
+                    cj[idx] = J;
+                    if (cand_kind) cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
+                }
+                ++idx;
             }
-            nc &= smask;
-            if (lane >= S) nc = 0u;
-            const unsigned J = __ballot_sync(kFull, nc != col);
-            cc[(size_t)idx * 32 + lane] = nc;
-            if (lane == 0) {
-                cj[idx] = J;
-                if (cand_kind) cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
-            }
-            ++idx;
         }
+    }
+    if (!dict) return;
+    __syncthreads();
+    // dense ids: exclusive scan of the occupied slots (8 consecutive slots per thread)
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cnt += keys[tid * 8 + i] != 0u;
+    int incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int base = incl - cnt;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t k = keys[tid * 8 + i];
+        if (k != 0u) {
+            ids[tid * 8 + i] = (uint16_t)base;
+            if (base < dcap) dict_masks[(size_t)q * dcap + base] = k;
+            ++base;
+        }
+    }
+    if (tid == 255) {
+        nd[q] = base;
+        if (base > dcap) atomicOr(overflow, 1);
+    }
+    __syncthreads();
+    // hash slots -> dense ids (cand_id / base_id written by this CTA above; __syncthreads makes them visible)
+    if (tid < S) base_id[q * 32 + tid] = ids[base_id[q * 32 + tid]];
+    for (int i = tid; i < total * 32; i += 256) {
+        const int c = i >> 5, j = i & 31;
+        if ((cj[c] >> j) & 1u) ci[i] = ids[ci[i]];
     }
 }
 
@@ -202,6 +282,93 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
         for (int w = 0; w < kRows / 32; ++w) t += s_red[tid][w];
         partial[((size_t)q * etiles + blockIdx.y) * maxc + c0 + tid] = t;
     }
+}
+
+// ---- dictionary scoring ----------------------------------------------------------------------------------
+// scoreAdj for every candidate of every active search.  grid = (G row groups, searches), block = 16 warps, lane = E-gene
+// row of a 32-row tile.  Per tile: (1) table T[entry][row] = sum of the R columns in the entry's mask, ascending
+// S-gene order (the order of the Eigen product in src/mm.cpp:10) -- each warp takes every 16th entry; (2) every warp
+// takes a contiguous run of candidates: row maximum over the columns outside the candidate's changed set (recomputed
+// only when the set changes -- consecutive insertions into the same v share it) and over the changed ones (table
+// look-ups), max with 0 (rowMaxs(cbind(0, score)), R/mnems.r:452-454), fixed-shape sum over the 32 rows, accumulated
+// per candidate in ascending tile order.  Dynamic shared memory: T, the per-candidate sums, the masks.
+template <int SP>
+__global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
+    int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
+    const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks, const uint16_t *__restrict__ base_id,
+    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int q = blockIdx.y, g = blockIdx.x;
+    const int nc = ncand[q];
+    if (nc == 0) return;
+    const int ndq = min(nd[q], dcap);
+    double *T = reinterpret_cast<double *>(s_raw);                      // [dcap][32]
+    double *candsum = T + (size_t)dcap * kDictRows;                     // [maxc]
+    uint32_t *dmask = reinterpret_cast<uint32_t *>(candsum + maxc);     // [dcap]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = kDictThreads / 32;
+    for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = dict_masks[(size_t)q * dcap + i];
+    for (int c = tid; c < nc; c += kDictThreads) candsum[c] = 0.0;
+    const uint32_t bid = lane < S ? base_id[q * 32 + lane] : 0u;
+    const double *R = Rptr[q];
+    const uint32_t *cJ = cand_J + (size_t)q * maxc;
+    const uint16_t *cI = cand_id + (size_t)q * maxc * 32;
+    const int per = (nc + NW - 1) / NW;                                 // contiguous candidates per warp
+    const int cbeg = warp * per, cend = min(nc, cbeg + per);
+    __syncthreads();
+    const int ntiles = (E + kDictRows - 1) / kDictRows;
+    for (int tile = g; tile < ntiles; tile += G) {
+        const int row = tile * kDictRows + lane;
+        double r[SP];
+#pragma unroll
+        for (int s = 0; s < SP; ++s) r[s] = (s < S && row < E) ? R[(size_t)s * E + row] : 0.0;
+        // (1) the table: two entries per step for instruction-level parallelism
+        for (int ent = warp; ent < ndq; ent += 2 * NW) {
+            const uint32_t m0 = dmask[ent];
+            const bool two = ent + NW < ndq;
+            const uint32_t m1 = two ? dmask[ent + NW] : 0u;
+            double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+            for (int s = 0; s < SP; ++s) {
+                if ((m0 >> s) & 1u) { MN_KEEP_BRANCH(); w0 += r[s]; }
+                if ((m1 >> s) & 1u) { MN_KEEP_BRANCH(); w1 += r[s]; }
+            }
+            T[ent * kDictRows + lane] = w0;
+            if (two) T[(ent + NW) * kDictRows + lane] = w1;
+        }
+        __syncthreads();
+        // (2) the candidates of this warp
+        uint32_t lastJ = 0u;
+        double A = -INFINITY;                             // max over the columns outside lastJ (all of them: none yet)
+        bool haveA = false;
+        for (int c = cbeg; c < cend; ++c) {
+            uint32_t J = cJ[c];
+            const uint32_t myid = ((J >> lane) & 1u) ? cI[(size_t)c * 32 + lane] : 0u;
+            if (!haveA || J != lastJ) {
+                A = -INFINITY;
+                for (int j = 0; j < S; ++j) {
+                    const int id = __shfl_sync(kFull, bid, j);
+                    if (!((J >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
+                }
+                lastJ = J;
+                haveA = true;
+            }
+            double best = A;
+            while (J) {                                   // changed columns: look the new column sum up
+                const int j = __ffs(J) - 1;
+                J &= J - 1;
+                const int id = __shfl_sync(kFull, myid, j);
+                const double t = T[id * kDictRows + lane];
+                best = t > best ? t : best;        // plain compare: NaN never wins, like which.max
+            }
+            double val = best > 0.0 ? best : 0.0;
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(kFull, val, o);
+            if (lane == 0) candsum[c] += val;
+        }
+        __syncthreads();
+    }
+    for (int c = tid; c < nc; c += kDictThreads) partial[((size_t)q * G + g) * maxc + c] = candsum[c];
 }
 
 // ---- argmax, accept rule, graph update -------------------------------------------------------------------
@@ -395,6 +562,32 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
     return 0;
 }
 
+static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
+{
+    MN_LAUNCH(gen_kernel, n, 256, 0, st, sb->S, sb->maxc, sb->dcap, mode, sb->Prow.p, sb->active.p, sb->Pcol.p,
+              sb->cand_cols.p, sb->cand_J.p, sb->ncand.p, (int8_t *)nullptr, sb->dict_masks.p, sb->nd.p, sb->cand_id.p,
+              sb->base_id.p, sb->overflow.p);
+    return 0;
+}
+
+static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
+{
+    const int S = sb->S;
+    dim3 grid(sb->G, n);
+#define MN_SCORE(SPV)                                                                                              \
+    MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, sb->G,   \
+              sb->Rptr.p, sb->ncand.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->cand_J.p, sb->cand_id.p,     \
+              sb->partial.p)
+    if (S <= 8) MN_SCORE(8);
+    else if (S <= 16) MN_SCORE(16);
+    else if (S <= 24) MN_SCORE(24);
+    else MN_SCORE(32);
+#undef MN_SCORE
+    return 0;
+}
+
+constexpr int kGcap = 16;          // most row groups per search (partial sums kept per group)
+
 int search_create(int nmax, int E, int S, SearchBatch **out)
 {
     MN_ARG(nmax >= 1 && E >= 1 && S >= 1 && S <= MNEMCU_MAX_S, "bad search workspace size");
@@ -402,6 +595,16 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     sb->nmax = nmax; sb->E = E; sb->S = S;
     sb->etiles = (E + kRows - 1) / kRows;
     sb->maxc = std::max(1, 3 * S * (S - 1));
+    {   // dictionary capacity: pairwise unions + deletion masks + slack, limited by the 227 KB of shared memory
+        const int need = S * (S + 1) / 2 + S * S / 4 + 2 * S + 8;
+        const int fit = (int)((232448 - (size_t)sb->maxc * 8 - 512) / (kDictRows * 8 + 4));
+        sb->dcap = std::max(1, std::min(need, fit));
+        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (size_t)sb->maxc * 8 + (size_t)sb->dcap * 4;
+        cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+    }
     auto body = [&]() -> int {
         MN_TRY(sb->Rptr.alloc(nmax));
         MN_TRY(sb->Prow.alloc((size_t)nmax * 32, true)); MN_TRY(sb->Pcol.alloc((size_t)nmax * 32, true));
@@ -410,9 +613,12 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->closed_cols.alloc((size_t)nmax * 32));
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
         MN_TRY(sb->n_active.alloc(1, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
-        MN_TRY(sb->partial.alloc((size_t)nmax * sb->etiles * sb->maxc));
+        MN_TRY(sb->partial.alloc((size_t)nmax * kGcap * sb->maxc));
+        MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
+        MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
+        MN_TRY(sb->overflow.alloc(1, true));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
-        MN_CU(cudaMallocHost((void **)&sb->h_n_active, sizeof(int32_t)));
+        MN_CU(cudaMallocHost((void **)&sb->h_n_active, 2 * sizeof(int32_t)));
         return 0;
     };
     int rc = body();
@@ -432,27 +638,29 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
 {
     MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
     const int S = sb->S;
+    const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
+    sb->G = std::max(1, std::min(std::min(kGcap, ntiles), (2 * 148 + n - 1) / n));
     MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
     MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
-    // initial score of closure(better)
-    MN_LAUNCH(gen_kernel, n, 256, 0, st, S, sb->maxc, 0, sb->Prow.p, sb->active.p, sb->Pcol.p, sb->cand_cols.p,
-              sb->cand_J.p, sb->ncand.p, (int8_t *)nullptr);
-    MN_TRY(launch_score(sb, n, st));
-    MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->etiles, 0, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
+    // initial score of closure(better), R/mnems.r:135-141
+    MN_TRY(launch_gen(sb, n, 0, st));
+    MN_TRY(launch_score_dict(sb, n, st));
+    MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->G, 0, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
               sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
               sb->n_active.p);
     const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
     for (int it = 0; it < hard_cap; ++it) {
         MN_CU(cudaMemsetAsync(sb->n_active.p, 0, sizeof(int32_t), st));
-        MN_LAUNCH(gen_kernel, n, 256, 0, st, S, sb->maxc, 1, sb->Prow.p, sb->active.p, sb->Pcol.p, sb->cand_cols.p,
-                  sb->cand_J.p, sb->ncand.p, (int8_t *)nullptr);
-        MN_TRY(launch_score(sb, n, st));
-        MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->etiles, 1, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
+        MN_TRY(launch_gen(sb, n, 1, st));
+        MN_TRY(launch_score_dict(sb, n, st));
+        MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->G, 1, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
                   sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
                   sb->n_active.p);
         MN_CU(cudaMemcpyAsync(sb->h_n_active, sb->n_active.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MN_CU(cudaMemcpyAsync(sb->h_n_active + 1, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         MN_CU(cudaStreamSynchronize(st));
-        if (*sb->h_n_active == 0) break;
+        if (sb->h_n_active[1]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+        if (sb->h_n_active[0] == 0) break;
     }
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
@@ -608,7 +816,8 @@ extern "C" int mnemcu_neighbours(const uint8_t *P, int S, uint8_t *models, int8_
     MN_CU(cudaMemcpy(dg.p, P, (size_t)S * S, cudaMemcpyHostToDevice));
     MN_CU(cudaMemcpy(dact.p, &one, sizeof(one), cudaMemcpyHostToDevice));
     MN_TRY(launch_rows_from_u8(dg.p, 1, S, drow.p, 0));
-    MN_LAUNCH(gen_kernel, 1, 256, 0, 0, S, maxc, 1, drow.p, dact.p, dPcol.p, dcc.p, dJ.p, dn.p, dkind.p);
+    MN_LAUNCH(gen_kernel, 1, 256, 0, 0, S, maxc, 0, 1, drow.p, dact.p, dPcol.p, dcc.p, dJ.p, dn.p, dkind.p,
+              (uint32_t *)nullptr, (int32_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr, (int32_t *)nullptr);
     int32_t n = 0;
     MN_CU(cudaMemcpy(&n, dn.p, sizeof(n), cudaMemcpyDeviceToHost));
     if (n > 0) {
