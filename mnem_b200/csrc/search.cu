@@ -30,8 +30,8 @@ struct SearchBatch {
     size_t dict_smem = 0;
     DevBuf<const double *> Rptr;
     DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks;
-    DevBuf<uint16_t> cand_id, base_id;
-    DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, overflow;
+    DevBuf<uint16_t> cand_id, base_id, pair_id;
+    DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow;
     DevBuf<double> partial, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored;
     int32_t *h_n_active = nullptr;   // pinned: [0] searches still active, [1] dictionary overflow flag
@@ -55,15 +55,17 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
                                                   int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind,
                                                   uint32_t *__restrict__ dict_masks, int32_t *__restrict__ nd,
                                                   uint16_t *__restrict__ cand_id, uint16_t *__restrict__ base_id,
+                                                  uint16_t *__restrict__ pair_id, int32_t *__restrict__ nins,
                                                   int32_t *__restrict__ overflow)
 {
     __shared__ uint32_t keys[kDictHash];
     __shared__ uint16_t ids[kDictHash];
+    __shared__ uint16_t s_pair[32 * 32];
     __shared__ int s_warp[8];
     const int q = blockIdx.x, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     if (!active[q]) {
-        if (tid == 0) { ncand[q] = 0; if (nd) nd[q] = 0; }
+        if (tid == 0) { ncand[q] = 0; if (nd) { nd[q] = 0; nins[q] = 0; } }
         return;
     }
     const bool dict = dict_masks != nullptr;
@@ -95,10 +97,16 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
             const uint32_t ccol = warp_transpose(clo, lane, S);
             cc[lane] = ccol;
             if (dict && lane < S) ci[lane] = (uint16_t)insert(ccol);
-            if (lane == 0) { cj[0] = smask; ncand[q] = 1; }
+            if (lane == 0) { cj[0] = smask; ncand[q] = 1; if (dict) nins[q] = 0; }
         }
         total = 1;
     } else {
+        // insertion u -> v turns column j (for every j with x[v,j] = 1) into col_j | col_u: enter all pairs
+        if (dict)
+            for (int u = warp; u < S; u += nwarp) {
+                const uint32_t cu = __shfl_sync(kFull, col, u);
+                if (lane < S) s_pair[u * 32 + lane] = (uint16_t)insert(col | cu);
+            }
         const uint32_t T = warp_reduce_graph(row, lane, S);          // rows of transitive.reduction(better)
         const uint32_t Tcol = warp_transpose(T, lane, S);
         // lane v owns column v: rows u that yield a candidate, per kind
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
             base += __shfl_sync(kFull, incl, 31);
         }
         total = base;
-        if (tid == 0) ncand[q] = base;
+        if (tid == 0) { ncand[q] = base; if (dict) nins[q] = off[1]; }   // lane 0: off[1] = number of insertions
         for (int item = warp; item < 3 * S; item += nwarp) {
             const int kd = item / S, v = item - kd * S;
             uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
@@ -158,7 +166,8 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
                 unsigned J = __ballot_sync(kFull, nc != col);
                 if (kd == 0) J = rowv;                     // superset shared by every insertion into v (diag included)
                 cc[(size_t)idx * 32 + lane] = nc;
-                if (dict && ((J >> lane) & 1u)) ci[(size_t)idx * 32 + lane] = (uint16_t)insert(nc);
+                // insertions are scored from the pair table; only reversals / deletions need per-candidate ids
+                if (dict && kd != 0 && ((J >> lane) & 1u)) ci[(size_t)idx * 32 + lane] = (uint16_t)insert(nc);
                 if (lane == 0) {
                     cj[idx] = J;
                     if (cand_kind) cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
@@ -198,10 +207,14 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
     __syncthreads();
     // hash slots -> dense ids (cand_id / base_id written by this CTA above; __syncthreads makes them visible)
     if (tid < S) base_id[q * 32 + tid] = ids[base_id[q * 32 + tid]];
-    for (int i = tid; i < total * 32; i += 256) {
+    const int first = mode == 0 ? 0 : nins[q];            // written by thread 0 before the barriers above
+    for (int i = first * 32 + tid; i < total * 32; i += 256) {
         const int c = i >> 5, j = i & 31;
         if ((cj[c] >> j) & 1u) ci[i] = ids[ci[i]];
     }
+    if (mode != 0)
+        for (int i = tid; i < 32 * 32; i += 256)
+            pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
 }
 
 // ---- candidate scoring -----------------------------------------------------------------------------------
@@ -286,85 +299,170 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
 
 // ---- dictionary scoring ----------------------------------------------------------------------------------
 // scoreAdj for every candidate of every active search.  grid = (G row groups, searches), block = 16 warps, lane = E-gene
-// row of a 32-row tile.  Per tile: (1) table T[entry][row] = sum of the R columns in the entry's mask, ascending
-// S-gene order (the order of the Eigen product in src/mm.cpp:10) -- each warp takes every 16th entry; (2) every warp
-// takes a contiguous run of candidates: row maximum over the columns outside the candidate's changed set (recomputed
-// only when the set changes -- consecutive insertions into the same v share it) and over the changed ones (table
-// look-ups), max with 0 (rowMaxs(cbind(0, score)), R/mnems.r:452-454), fixed-shape sum over the 32 rows, accumulated
-// per candidate in ascending tile order.  Dynamic shared memory: T, the per-candidate sums, the masks.
+// row of a 32-row tile.  Per tile:
+// (1) table T[entry][row] = sum of the R columns in the entry's mask, ascending S-gene order (the order of the Eigen
+//     product in src/mm.cpp:10); each warp takes every 16th entry, two at a time.
+// (2) insertions, one v per warp at a time: inserting u -> v replaces column j by col_j | col_u for every j in row v
+//     (D_v).  A_v = max over the columns outside D_v is computed once; then for every j in D_v the S look-ups
+//     T[pair(u, j)] update B[u] (registers, u unrolled), and max(0, A_v, B[u]) is summed over the 32 rows for all u at
+//     once by a transposed butterfly (31 exchanges for 32 candidates instead of 5 per candidate).
+// (3) reversals / deletions: per candidate, changed columns by id, unchanged-column maximum cached while the changed
+//     set repeats.
+// Per-candidate sums accumulate in shared memory in ascending tile order.  Both reductions pair the rows as
+// (l, l^16), (l, l^8), ...: the same function of the 32 row values, so equal rows give bit-equal sums whatever the
+// candidate kind (exact score ties decide graphs, R/mnems.r:236, 279-283).
+// Dynamic shared memory: T, the per-candidate sums, the masks, the pair-id matrix.
 template <int SP>
 __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
-    const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks, const uint16_t *__restrict__ base_id,
+    const int32_t *__restrict__ nins, const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks,
+    const uint16_t *__restrict__ base_id, const uint16_t *__restrict__ pair_id, const uint32_t *__restrict__ Pcol,
     const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int q = blockIdx.y, g = blockIdx.x;
     const int nc = ncand[q];
     if (nc == 0) return;
+    const int ni = nins[q];
     const int ndq = min(nd[q], dcap);
     double *T = reinterpret_cast<double *>(s_raw);                      // [dcap][32]
     double *candsum = T + (size_t)dcap * kDictRows;                     // [maxc]
     uint32_t *dmask = reinterpret_cast<uint32_t *>(candsum + maxc);     // [dcap]
+    uint32_t *pid = dmask + ((dcap + 3) & ~3);      // [32][32]: pid[j*32 + u] = byte offset in T of the row of col_j | col_u
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kDictThreads / 32;
     for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = dict_masks[(size_t)q * dcap + i];
     for (int c = tid; c < nc; c += kDictThreads) candsum[c] = 0.0;
+    if (ni > 0)
+        for (int i = tid; i < 1024; i += kDictThreads) pid[i] = (uint32_t)pair_id[(size_t)q * 1024 + i] * (kDictRows * 8u);
     const uint32_t bid = lane < S ? base_id[q * 32 + lane] : 0u;
+    const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
+    const uint32_t pcol = lane < S ? Pcol[q * 32 + lane] : 0u;          // lane = column
+    const uint32_t zmask = lane < S ? (~pcol & smask) : 0u;            // rows u with P[u, lane] == 0: insertions into lane
+    int offv;                                                           // first candidate index of column `lane`
+    {
+        const int cnt = __popc(zmask);
+        int incl = cnt;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += t;
+        }
+        offv = incl - cnt;
+    }
     const double *R = Rptr[q];
     const uint32_t *cJ = cand_J + (size_t)q * maxc;
     const uint16_t *cI = cand_id + (size_t)q * maxc * 32;
-    const int per = (nc + NW - 1) / NW;                                 // contiguous candidates per warp
-    const int cbeg = warp * per, cend = min(nc, cbeg + per);
+    const int nrest = nc - ni;
+    const int per = (nrest + NW - 1) / NW;                              // contiguous reversal/deletion candidates per warp
+    const int cbeg = ni + warp * per, cend = min(nc, cbeg + per);
     __syncthreads();
     const int ntiles = (E + kDictRows - 1) / kDictRows;
     for (int tile = g; tile < ntiles; tile += G) {
         const int row = tile * kDictRows + lane;
-        double r[SP];
+        {
+            double r[SP];
 #pragma unroll
-        for (int s = 0; s < SP; ++s) r[s] = (s < S && row < E) ? R[(size_t)s * E + row] : 0.0;
-        // (1) the table: two entries per step for instruction-level parallelism
-        for (int ent = warp; ent < ndq; ent += 2 * NW) {
-            const uint32_t m0 = dmask[ent];
-            const bool two = ent + NW < ndq;
-            const uint32_t m1 = two ? dmask[ent + NW] : 0u;
-            double w0 = 0.0, w1 = 0.0;
+            for (int s = 0; s < SP; ++s) r[s] = (s < S && row < E) ? R[(size_t)s * E + row] : 0.0;
+            // (1) the table
+            for (int ent = warp; ent < ndq; ent += 2 * NW) {
+                const uint32_t m0 = dmask[ent];
+                const bool two = ent + NW < ndq;
+                const uint32_t m1 = two ? dmask[ent + NW] : 0u;
+                double w0 = 0.0, w1 = 0.0;
 #pragma unroll
-            for (int s = 0; s < SP; ++s) {
-                if ((m0 >> s) & 1u) { MN_KEEP_BRANCH(); w0 += r[s]; }
-                if ((m1 >> s) & 1u) { MN_KEEP_BRANCH(); w1 += r[s]; }
+                for (int s = 0; s < SP; ++s) {
+                    if ((m0 >> s) & 1u) { MN_KEEP_BRANCH(); w0 += r[s]; }
+                    if ((m1 >> s) & 1u) { MN_KEEP_BRANCH(); w1 += r[s]; }
+                }
+                T[ent * kDictRows + lane] = w0;
+                if (two) T[(ent + NW) * kDictRows + lane] = w1;
             }
-            T[ent * kDictRows + lane] = w0;
-            if (two) T[(ent + NW) * kDictRows + lane] = w1;
         }
         __syncthreads();
-        // (2) the candidates of this warp
-        uint32_t lastJ = 0u;
-        double A = -INFINITY;                             // max over the columns outside lastJ (all of them: none yet)
-        bool haveA = false;
-        for (int c = cbeg; c < cend; ++c) {
-            uint32_t J = cJ[c];
-            const uint32_t myid = ((J >> lane) & 1u) ? cI[(size_t)c * 32 + lane] : 0u;
-            if (!haveA || J != lastJ) {
-                A = -INFINITY;
+        // (2) insertions
+        if (ni > 0) {
+            for (int v = warp; v < S; v += NW) {
+                const uint32_t zm = __shfl_sync(kFull, zmask, v);
+                if (zm == 0u) continue;
+                const uint32_t Dv = __ballot_sync(kFull, (pcol >> v) & 1u);      // columns j with P[v, j] = 1 (diag included)
+                double A = -INFINITY;
                 for (int j = 0; j < S; ++j) {
                     const int id = __shfl_sync(kFull, bid, j);
-                    if (!((J >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
+                    if (!((Dv >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
                 }
-                lastJ = J;
-                haveA = true;
+                double B[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) B[u] = -INFINITY;
+                uint32_t m = Dv;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    // ids of col_j | col_u for all u: one 64-byte row, fetched as uniform 16-byte loads; the look-ups
+                    // are unconditional (also for u that are no candidates) so that they pipeline instead of
+                    // serialising behind 30 uniform branches
+                    uint32_t ofs[SP];
+#pragma unroll
+                    for (int w4 = 0; w4 < SP / 4; ++w4) {
+                        const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + w4 * 4);
+                        ofs[w4 * 4 + 0] = x.x; ofs[w4 * 4 + 1] = x.y; ofs[w4 * 4 + 2] = x.z; ofs[w4 * 4 + 3] = x.w;
+                    }
+                    const unsigned char *Tl = reinterpret_cast<const unsigned char *>(T + lane);
+#pragma unroll
+                    for (int u = 0; u < SP; ++u) {
+                        const double t = *reinterpret_cast<const double *>(Tl + ofs[u]);
+                        B[u] = t > B[u] ? t : B[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    double x = B[u] > A ? B[u] : A;
+                    x = x > 0.0 ? x : 0.0;
+                    B[u] = (u < SP && ((zm >> u) & 1u)) ? x : 0.0;
+                }
+                // transposed butterfly: afterwards lane l holds the sum over the 32 rows of B[l]
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const bool hi = (lane & d) != 0;
+#pragma unroll
+                    for (int i = 0; i < d; ++i) {
+                        const double send = hi ? B[i] : B[i + d];
+                        const double recv = __shfl_xor_sync(kFull, send, d);
+                        B[i] = (hi ? B[i + d] : B[i]) + recv;
+                    }
+                }
+                const int off = __shfl_sync(kFull, offv, v);
+                if ((zm >> lane) & 1u) candsum[off + __popc(zm & ((1u << lane) - 1u))] += B[0];
             }
-            double best = A;
-            while (J) {                                   // changed columns: look the new column sum up
-                const int j = __ffs(J) - 1;
-                J &= J - 1;
-                const int id = __shfl_sync(kFull, myid, j);
-                const double t = T[id * kDictRows + lane];
-                best = t > best ? t : best;        // plain compare: NaN never wins, like which.max
+        }
+        // (3) reversals and deletions (and the single closure "candidate" of the initial score)
+        {
+            uint32_t lastJ = 0u;
+            double A = -INFINITY;
+            bool haveA = false;
+            for (int c = cbeg; c < cend; ++c) {
+                uint32_t J = cJ[c];
+                const uint32_t myid = ((J >> lane) & 1u) ? cI[(size_t)c * 32 + lane] : 0u;
+                if (!haveA || J != lastJ) {
+                    A = -INFINITY;
+                    for (int j = 0; j < S; ++j) {
+                        const int id = __shfl_sync(kFull, bid, j);
+                        if (!((J >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
+                    }
+                    lastJ = J;
+                    haveA = true;
+                }
+                double best = A;
+                while (J) {
+                    const int j = __ffs(J) - 1;
+                    J &= J - 1;
+                    const int id = __shfl_sync(kFull, myid, j);
+                    const double t = T[id * kDictRows + lane];
+                    best = t > best ? t : best;        // plain compare: NaN never wins, like which.max
+                }
+                double val = best > 0.0 ? best : 0.0;
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
+                if (lane == 0) candsum[c] += val;
             }
-            double val = best > 0.0 ? best : 0.0;
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(kFull, val, o);
-            if (lane == 0) candsum[c] += val;
         }
         __syncthreads();
     }
@@ -566,7 +664,7 @@ static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
 {
     MN_LAUNCH(gen_kernel, n, 256, 0, st, sb->S, sb->maxc, sb->dcap, mode, sb->Prow.p, sb->active.p, sb->Pcol.p,
               sb->cand_cols.p, sb->cand_J.p, sb->ncand.p, (int8_t *)nullptr, sb->dict_masks.p, sb->nd.p, sb->cand_id.p,
-              sb->base_id.p, sb->overflow.p);
+              sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);
     return 0;
 }
 
@@ -576,8 +674,8 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     dim3 grid(sb->G, n);
 #define MN_SCORE(SPV)                                                                                              \
     MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, sb->G,   \
-              sb->Rptr.p, sb->ncand.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->cand_J.p, sb->cand_id.p,     \
-              sb->partial.p)
+              sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->pair_id.p,       \
+              sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
     else if (S <= 24) MN_SCORE(24);
@@ -586,7 +684,20 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     return 0;
 }
 
-constexpr int kGcap = 16;          // most row groups per search (partial sums kept per group)
+constexpr int kGcap = 32;          // most row groups per search (partial sums kept per group)
+
+// One CTA fits per SM (the table fills shared memory), so the launch runs in ceil(G*n/SMs) rounds of ceil(tiles/G)
+// tiles each: pick the G that minimises the product for the current number of active searches.
+static int pick_groups(int n_active, int ntiles, int sms)
+{
+    int best = 1;
+    long best_cost = -1;
+    for (int G = 1; G <= std::min(kGcap, ntiles); ++G) {
+        const long cost = (long)((G * (long)n_active + sms - 1) / sms) * ((ntiles + G - 1) / G);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
+    }
+    return best;
+}
 
 int search_create(int nmax, int E, int S, SearchBatch **out)
 {
@@ -597,9 +708,9 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     sb->maxc = std::max(1, 3 * S * (S - 1));
     {   // dictionary capacity: pairwise unions + deletion masks + slack, limited by the 227 KB of shared memory
         const int need = S * (S + 1) / 2 + S * S / 4 + 2 * S + 8;
-        const int fit = (int)((232448 - (size_t)sb->maxc * 8 - 512) / (kDictRows * 8 + 4));
+        const int fit = (int)((232448 - (size_t)sb->maxc * 8 - 4096 - 512) / (kDictRows * 8 + 4));
         sb->dcap = std::max(1, std::min(need, fit));
-        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (size_t)sb->maxc * 8 + (size_t)sb->dcap * 4;
+        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (size_t)sb->maxc * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
         cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
@@ -616,7 +727,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->partial.alloc((size_t)nmax * kGcap * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
-        MN_TRY(sb->overflow.alloc(1, true));
+        MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
+        MN_TRY(sb->nins.alloc(nmax, true));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
         MN_CU(cudaMallocHost((void **)&sb->h_n_active, 2 * sizeof(int32_t)));
         return 0;
@@ -639,7 +751,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
     const int S = sb->S;
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
-    sb->G = std::max(1, std::min(std::min(kGcap, ntiles), (2 * 148 + n - 1) / n));
+    sb->G = pick_groups(n, ntiles, 148);
     MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
     MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
     // initial score of closure(better), R/mnems.r:135-141
@@ -661,6 +773,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         MN_CU(cudaStreamSynchronize(st));
         if (sb->h_n_active[1]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
         if (sb->h_n_active[0] == 0) break;
+        sb->G = pick_groups(sb->h_n_active[0], ntiles, 148);
     }
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
@@ -817,7 +930,8 @@ extern "C" int mnemcu_neighbours(const uint8_t *P, int S, uint8_t *models, int8_
     MN_CU(cudaMemcpy(dact.p, &one, sizeof(one), cudaMemcpyHostToDevice));
     MN_TRY(launch_rows_from_u8(dg.p, 1, S, drow.p, 0));
     MN_LAUNCH(gen_kernel, 1, 256, 0, 0, S, maxc, 0, 1, drow.p, dact.p, dPcol.p, dcc.p, dJ.p, dn.p, dkind.p,
-              (uint32_t *)nullptr, (int32_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr, (int32_t *)nullptr);
+              (uint32_t *)nullptr, (int32_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr,
+              (int32_t *)nullptr, (int32_t *)nullptr);
     int32_t n = 0;
     MN_CU(cudaMemcpy(&n, dn.p, sizeof(n), cudaMemcpyDeviceToHost));
     if (n > 0) {

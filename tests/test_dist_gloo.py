@@ -1,0 +1,70 @@
+"""The N > 1 path on CPU: world_size-2 gloo processes shard the EM starts, each fits its shard (the CPU oracle stands
+in for the per-rank GPU fit -- this test is about the host-side sharding and the winner reduction, not about kernels)
+and the (ll, start id) reduction must pick the same winner as a single process (R/mnems.r:2222-2230)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from mnem_b200 import dist as mdist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import oracle as orc
+from mnem_b200 import simdata, dist as mdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+sim = simdata.make_config(dict(S=4, Egenes=3, C=300, mw=[0.5, 0.5], k=2, starts=5, uninform=0), seed=3)
+D = simdata.host_data(sim)
+init = simdata.init_phi(4, 2, 5, seed=9)
+my = mdist.shard_starts(5, rank, world)
+r = orc.mnem_em(D, sim["pert"], 4, init[my])
+winner, lls = mdist.gather_winner(my, r["ll"], 5)
+print(json.dumps(dict(rank=rank, my=my, winner=int(winner), lls=[float(x) for x in lls])))
+dist.destroy_process_group()
+"""
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_and_pick_winner_helpers():
+    assert mdist.shard_starts(10, 1, 4) == [1, 5, 9]
+    assert sorted(sum((mdist.shard_starts(7, r, 3) for r in range(3)), [])) == list(range(7))
+    assert mdist.pick_winner([1.0, 3.0, 3.0, 2.0]) == 2          # last maximal start
+    assert mdist.pick_winner([-np.inf, -np.inf]) == 1
+
+
+def test_two_rank_gloo_winner_matches_single_process():
+    import json
+
+    import oracle as orc
+    from mnem_b200 import simdata
+    port = _free_port()
+    src = WORKER % dict(root=ROOT, port=port)
+    procs = [subprocess.Popen([sys.executable, "-c", src, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=300)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(json.loads(o.strip().splitlines()[-1]))
+    sim = simdata.make_config(dict(S=4, Egenes=3, C=300, mw=[0.5, 0.5], k=2, starts=5, uninform=0), seed=3)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(4, 2, 5, seed=9)
+    ref = orc.mnem_em(D, sim["pert"], 4, init)
+    assert outs[0]["winner"] == outs[1]["winner"] == ref["best"]
+    np.testing.assert_array_equal(outs[0]["lls"], ref["ll"])
+    assert sorted(outs[0]["my"] + outs[1]["my"]) == list(range(5))
