@@ -379,17 +379,41 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
             }
         }
         __syncthreads();
+        // the four largest subweights of the current graph in this row: the maximum over the columns a candidate
+        // leaves unchanged is the first of them whose column is outside the changed set (full scan only if all
+        // four are inside)
+        double t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+        int i0 = 32, i1 = 32, i2 = 32, i3 = 32;              // 32 = no column
+        for (int j = 0; j < S; ++j) {
+            const int id = __shfl_sync(kFull, bid, j);
+            const double w = T[id * kDictRows + lane];
+            if (w > t0) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = t0; i1 = i0; t0 = w; i0 = j; }
+            else if (w > t1) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = w; i1 = j; }
+            else if (w > t2) { t3 = t2; i3 = i2; t2 = w; i2 = j; }
+            else if (w > t3) { t3 = w; i3 = j; }
+        }
+        auto unchanged_max = [&](uint32_t Jset) -> double {
+            const unsigned long long Jx = Jset;
+            const bool in0 = (Jx >> i0) & 1ull, in1 = (Jx >> i1) & 1ull, in2 = (Jx >> i2) & 1ull, in3 = (Jx >> i3) & 1ull;
+            double A = !in0 ? t0 : (!in1 ? t1 : (!in2 ? t2 : t3));
+            const bool need_scan = in0 && in1 && in2 && in3;
+            if (__any_sync(kFull, need_scan)) {
+                double sc = -INFINITY;
+                for (int j = 0; j < S; ++j) {
+                    const int id = __shfl_sync(kFull, bid, j);
+                    if (!((Jset >> j) & 1u)) { const double t = T[id * kDictRows + lane]; sc = t > sc ? t : sc; }
+                }
+                if (need_scan) A = sc;
+            }
+            return A;
+        };
         // (2) insertions
         if (ni > 0) {
             for (int v = warp; v < S; v += NW) {
                 const uint32_t zm = __shfl_sync(kFull, zmask, v);
                 if (zm == 0u) continue;
                 const uint32_t Dv = __ballot_sync(kFull, (pcol >> v) & 1u);      // columns j with P[v, j] = 1 (diag included)
-                double A = -INFINITY;
-                for (int j = 0; j < S; ++j) {
-                    const int id = __shfl_sync(kFull, bid, j);
-                    if (!((Dv >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
-                }
+                const double A = unchanged_max(Dv);
                 double B[32];
 #pragma unroll
                 for (int u = 0; u < 32; ++u) B[u] = -INFINITY;
@@ -443,11 +467,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                 uint32_t J = cJ[c];
                 const uint32_t myid = ((J >> lane) & 1u) ? cI[(size_t)c * 32 + lane] : 0u;
                 if (!haveA || J != lastJ) {
-                    A = -INFINITY;
-                    for (int j = 0; j < S; ++j) {
-                        const int id = __shfl_sync(kFull, bid, j);
-                        if (!((J >> j) & 1u)) { const double t = T[id * kDictRows + lane]; A = t > A ? t : A; }
-                    }
+                    A = unchanged_max(J);
                     lastJ = J;
                     haveA = true;
                 }
