@@ -172,9 +172,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// grid = (groups of MT pairs, E-gene tiles, chunks), block = tpb threads.  Two software pipelines keep HBM busy:
-// the weights of the NEXT 64 cells are fetched with cp.async while the current 64 are consumed, and the D values
-// of the next 4 cells are in flight (registers) while the current 4 are multiplied.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+
+constexpr int kStCells = 8;    // cells per pipeline stage
+constexpr int kStages = 3;     // stages in flight: 2 ahead of the one being consumed
+
+// grid = (groups of MT pairs, E-gene tiles, chunks), block = tpb threads.  A 3-stage cp.async ring keeps 16 cells
+// (64 KB per CTA at 256 threads) in flight ahead of the FMAs: each stage holds, for 8 cells, the CTA's slice of D
+// (16 bytes per thread and cell, straight from HBM to shared memory, L1 bypassed) and the 8 x MT weights.
 template <int MT>
 __global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict__ Dcol, int Epad,
                                                         const double *__restrict__ gam, int M, int Cp,
@@ -182,66 +190,64 @@ __global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict
                                                         const int32_t *__restrict__ chunk_n, double *__restrict__ partial)
 {
     constexpr int MTP = (MT + 1) & ~1;                 // even row length: weights are fetched as double2
-    __shared__ __align__(16) double s_g[2][kSub][MTP];
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int tpb = blockDim.x, tid = threadIdx.x;
+    double2 *sD = reinterpret_cast<double2 *>(s_dyn);                                   // [kStages][kStCells][tpb]
+    double *sG = reinterpret_cast<double *>(sD + (size_t)kStages * kStCells * tpb);     // [kStages][kStCells][MTP]
     const int chunk = blockIdx.z;
     const int m0 = blockIdx.x * MT;                     // groups vary fastest: the CTAs that re-read a tile run together
-    const int e = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
+    const int e = 2 * (blockIdx.y * tpb + tid);
     const bool live = e < Epad;
     const int cp0 = chunk_cp0[chunk];
     const int n = chunk_n[chunk];                       // multiple of 64
     double ax[MT], ay[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) { ax[m] = 0.0; ay[m] = 0.0; }
-
-    auto stage = [&](int buf, int c0) {
-        for (int i = threadIdx.x; i < kSub * MTP; i += blockDim.x) {
-            const int m = i / kSub, c = i - m * kSub;   // consecutive threads fetch consecutive cells
-            double *dst = &s_g[buf][c][m];
-            if (m < MT && m0 + m < M) {
-                if (gam) cp_async8(dst, gam + (size_t)(m0 + m) * Cp + cp0 + c0 + c);
-                else *dst = 1.0;
-            } else {
-                *dst = 0.0;
-            }
-        }
-        cp_async_commit();
-    };
-
     const double2 *p = reinterpret_cast<const double2 *>(Dcol + (size_t)cp0 * Epad + (live ? e : 0));
     const size_t stride = (size_t)Epad / 2;
-    double2 dn[4];
+
+    auto issue = [&](int st, int c0) {
+        if (c0 < n) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dn[j] = ld_stream2(p + (size_t)j * stride);
-    stage(0, 0);
-    int buf = 0;
-    for (int c0 = 0; c0 < n; c0 += kSub, buf ^= 1) {
-        if (c0 + kSub < n) { stage(buf ^ 1, c0 + kSub); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-#pragma unroll 2
-        for (int cl = 0; cl < kSub; cl += 4) {
-            double2 d[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = dn[j];
-            const int cn = c0 + cl + 4;
-            if (cn < n) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dn[j] = ld_stream2(p + (size_t)(cn + j) * stride);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int m = 0; m < MT; m += 2) {
-                    const double2 g = *reinterpret_cast<const double2 *>(&s_g[buf][cl + j][m]);   // broadcast LDS.128
-                    ax[m] = fma(d[j].x, g.x, ax[m]);
-                    ay[m] = fma(d[j].y, g.x, ay[m]);
-                    if (m + 1 < MT) {
-                        ax[m + 1] = fma(d[j].x, g.y, ax[m + 1]);
-                        ay[m + 1] = fma(d[j].y, g.y, ay[m + 1]);
-                    }
+            for (int j = 0; j < kStCells; ++j) cp_async16(&sD[(st * kStCells + j) * tpb + tid], p + (size_t)(c0 + j) * stride);
+            for (int i = tid; i < kStCells * MTP; i += tpb) {
+                const int m = i / kStCells, c = i - m * kStCells;
+                double *dst = &sG[(st * kStCells + c) * MTP + m];
+                if (m < MT && m0 + m < M) {
+                    if (gam) cp_async8(dst, gam + (size_t)(m0 + m) * Cp + cp0 + c0 + c);
+                    else *dst = 1.0;
+                } else {
+                    *dst = 0.0;
                 }
+            }
+        }
+        cp_async_commit();                              // always: keeps the group count uniform
+    };
+
+    issue(0, 0);
+    issue(1, kStCells);
+    int st = 0;
+    for (int c0 = 0; c0 < n; c0 += kStCells) {
+        issue(st == 0 ? 2 : st - 1, c0 + 2 * kStCells);     // (st + 2) % 3
+        cp_async_wait<2>();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kStCells; ++j) {
+            const double2 d = sD[(st * kStCells + j) * tpb + tid];
+            const double *g = &sG[(st * kStCells + j) * MTP];
+#pragma unroll
+            for (int m = 0; m < MT; m += 2) {
+                const double2 gg = *reinterpret_cast<const double2 *>(g + m);       // broadcast LDS.128
+                ax[m] = fma(d.x, gg.x, ax[m]);
+                ay[m] = fma(d.y, gg.x, ay[m]);
+                if (m + 1 < MT) {
+                    ax[m + 1] = fma(d.x, gg.y, ax[m + 1]);
+                    ay[m + 1] = fma(d.y, gg.y, ay[m + 1]);
+                }
+            }
         }
         __syncthreads();
+        st = st == 2 ? 0 : st + 1;
     }
     if (live) {
 #pragma unroll
@@ -272,7 +278,14 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, doubl
     int tpb = 256;
     while (tpb > 32 && tpb / 2 >= pairs) tpb /= 2;
     dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
-    MN_LAUNCH(mstats_kernel<MT>, grid, tpb, 0, st, cx->Dcol, cx->Epad, gam, M, cx->Cp, cx->chunk_cp0, cx->chunk_n,
+    constexpr int MTP = (MT + 1) & ~1;
+    const size_t smem = (size_t)kStages * kStCells * ((size_t)tpb * sizeof(double2) + MTP * sizeof(double));
+    static bool attr_set = false;
+    if (!attr_set) {
+        MN_CU(cudaFuncSetAttribute(mstats_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        attr_set = true;
+    }
+    MN_LAUNCH(mstats_kernel<MT>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, M, cx->Cp, cx->chunk_cp0, cx->chunk_n,
               partial);
     return 0;
 }
