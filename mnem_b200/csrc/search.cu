@@ -326,13 +326,11 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     const int ni = nins[q];
     const int ndq = min(nd[q], dcap);
     double *T = reinterpret_cast<double *>(s_raw);                      // [dcap][32]
-    double *candsum = T + (size_t)dcap * kDictRows;                     // [maxc]
-    uint32_t *dmask = reinterpret_cast<uint32_t *>(candsum + maxc);     // [dcap]
+    uint32_t *dmask = reinterpret_cast<uint32_t *>(T + (size_t)dcap * kDictRows);   // [dcap]
     uint32_t *pid = dmask + ((dcap + 3) & ~3);      // [32][32]: pid[j*32 + u] = byte offset in T of the row of col_j | col_u
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kDictThreads / 32;
     for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = dict_masks[(size_t)q * dcap + i];
-    for (int c = tid; c < nc; c += kDictThreads) candsum[c] = 0.0;
     if (ni > 0)
         for (int i = tid; i < 1024; i += kDictThreads) pid[i] = (uint32_t)pair_id[(size_t)q * 1024 + i] * (kDictRows * 8u);
     const uint32_t bid = lane < S ? base_id[q * 32 + lane] : 0u;
@@ -359,6 +357,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     const int ntiles = (E + kDictRows - 1) / kDictRows;
     for (int tile = g; tile < ntiles; tile += G) {
         const int row = tile * kDictRows + lane;
+        double *ptile = partial + ((size_t)q * ntiles + tile) * maxc;   // this tile's per-candidate sums
         {
             double r[SP];
 #pragma unroll
@@ -455,7 +454,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                     }
                 }
                 const int off = __shfl_sync(kFull, offv, v);
-                if ((zm >> lane) & 1u) candsum[off + __popc(zm & ((1u << lane) - 1u))] += B[0];
+                if ((zm >> lane) & 1u) ptile[off + __popc(zm & ((1u << lane) - 1u))] = B[0];
             }
         }
         // (3) reversals and deletions (and the single closure "candidate" of the initial score)
@@ -481,12 +480,11 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                 }
                 double val = best > 0.0 ? best : 0.0;
                 for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
-                if (lane == 0) candsum[c] += val;
+                if (lane == 0) ptile[c] = val;
             }
         }
         __syncthreads();
     }
-    for (int c = tid; c < nc; c += kDictThreads) partial[((size_t)q * G + g) * maxc + c] = candsum[c];
 }
 
 // ---- argmax, accept rule, graph update -------------------------------------------------------------------
@@ -508,7 +506,8 @@ __global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles
     double best = -INFINITY;
     int bidx = INT_MAX;
     for (int c = tid; c < nc; c += 128) {
-        double sc = 0.0;
+        double sc = 0.0;                                           // tiles in ascending order, whatever CTA produced them
+#pragma unroll 8
         for (int et = 0; et < etiles; ++et) sc += partial[((size_t)q * etiles + et) * maxc + c];
         if (isnan(sc)) sc = 0.0;                                   // scores[is.na(scores)] <- 0   R/mnems.r:235
         if (sc > best) { best = sc; bidx = c; }                    // ascending c: first maximum kept
@@ -728,9 +727,9 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     sb->maxc = std::max(1, 3 * S * (S - 1));
     {   // dictionary capacity: pairwise unions + deletion masks + slack, limited by the 227 KB of shared memory
         const int need = S * (S + 1) / 2 + S * S / 4 + 2 * S + 8;
-        const int fit = (int)((232448 - (size_t)sb->maxc * 8 - 4096 - 512) / (kDictRows * 8 + 4));
+        const int fit = (int)((232448 - 4096 - 512) / (kDictRows * 8 + 4));
         sb->dcap = std::max(1, std::min(need, fit));
-        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (size_t)sb->maxc * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
+        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
         cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
@@ -744,7 +743,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->closed_cols.alloc((size_t)nmax * 32));
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
         MN_TRY(sb->n_active.alloc(1, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
-        MN_TRY(sb->partial.alloc((size_t)nmax * kGcap * sb->maxc));
+        MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
@@ -777,7 +776,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     // initial score of closure(better), R/mnems.r:135-141
     MN_TRY(launch_gen(sb, n, 0, st));
     MN_TRY(launch_score_dict(sb, n, st));
-    MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->G, 0, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
+    MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, ntiles, 0, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
               sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
               sb->n_active.p);
     const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
@@ -785,7 +784,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         MN_CU(cudaMemsetAsync(sb->n_active.p, 0, sizeof(int32_t), st));
         MN_TRY(launch_gen(sb, n, 1, st));
         MN_TRY(launch_score_dict(sb, n, st));
-        MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, sb->G, 1, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
+        MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, ntiles, 1, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
                   sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
                   sb->n_active.p);
         MN_CU(cudaMemcpyAsync(sb->h_n_active, sb->n_active.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

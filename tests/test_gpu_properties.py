@@ -1,0 +1,105 @@
+"""Size-independent properties of the CUDA path at sizes the oracle cannot finish in seconds (BASELINE configs 3-4
+shapes: 20-24 S-genes, 1000 E-genes, 1e5 cells).  Run-to-run determinism, likelihood monotonicity, consistency of the
+pieces with each other, linearity of the contractions, batch-size independence."""
+import numpy as np
+import pytest
+
+import mnem_b200 as mb
+import oracle as orc
+from mnem_b200 import simdata
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    sim = simdata.make_config(dict(S=20, Egenes=50, C=100000, mw=[0.2] * 5, k=5, starts=6, uninform=0, complete=True),
+                              seed=1003)
+    cx = mb.Context.synthetic(sim)
+    init = simdata.init_phi(sim["S"], 5, 6, seed=77)
+    yield sim, cx, init
+    cx.close()
+
+
+def test_em_is_deterministic_and_batch_independent(big):
+    sim, cx, init = big
+    a = mb.em_run(cx, init, complete=True, batch=4)
+    b = mb.em_run(cx, init, complete=True, batch=4)
+    c = mb.em_run(cx, init, complete=True, batch=1)
+    for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
+        assert np.array_equal(a[key], b[key]), key            # bit-reproducible run to run
+        assert np.array_equal(a[key], c[key]), key            # sharing passes between starts changes nothing
+    assert a["best"] == b["best"] == c["best"]
+    for s in range(init.shape[0]):
+        lls = a["lls"][s]
+        assert len(lls) == a["n_iter"][s] >= 2
+        assert (np.diff(lls) >= 0).all()                      # accepted likelihood never decreases (R/mnems.r:2104-2108)
+        assert a["ll"][s] == lls.max()
+        np.testing.assert_allclose(a["mw"][s].sum(), 1.0, rtol=1e-12)
+        # the loop ends by the stop rule (no edge / theta change, R/mnems.r:2138-2141) or because the last E-step was
+        # not accepted (ll unchanged, :1955-1958)
+        stopped = a["phievo"][s][-1] == 0 and a["thetaevo"][s][-1] == 0
+        assert stopped or lls[-1] == lls[-2]
+    assert a["best"] == max(i for i in range(len(a["ll"])) if a["ll"][i] == a["ll"].max())
+
+
+def test_em_pieces_are_consistent_at_scale(big):
+    """The winner's stored probs must be reproduced by getProbs from its (phi, theta), and its graphs must be fixed
+    points of transitive reduction; the planted mixture is recovered well."""
+    sim, cx, init = big
+    r = mb.em_run(cx, init, complete=True)
+    b = r["best"]
+    res = [dict(adj=r["adj"][b][i], subtopo=r["theta"][b][i]) for i in range(5)]
+    pr = mb.getProbs(r["probs"][b], 5, cx, res, mw=r["mw"][b], complete=True)
+    np.testing.assert_array_equal(pr["probs"], r["probs"][b])
+    for i in range(5):
+        g = r["adj"][b][i]
+        assert np.array_equal(mb.transitive_reduction(g), g)
+        assert (np.diag(g) == 0).all()
+    post = mb.getAffinity(r["probs"][b], mw=r["mw"][b], complete=True)
+    hard = post.argmax(0)
+    # components are recovered up to permutation: every true component maps mostly onto one fitted component
+    purity = 0
+    for t in range(5):
+        cnt = np.bincount(hard[sim["comp"] == t], minlength=5)
+        purity += cnt.max()
+    assert purity / sim["C"] > 0.35          # well above the 1/k of a random assignment
+
+
+def test_contractions_are_linear_and_match_a_cpu_subsample(big):
+    sim, cx, init = big
+    rng = np.random.default_rng(0)
+    w1, w2 = rng.random(sim["C"]), rng.random(sim["C"])
+    R1, R2, R12 = mb.doMean(cx, w1), mb.doMean(cx, w2), mb.doMean(cx, 2.0 * w1 + w2)
+    np.testing.assert_allclose(R12, 2.0 * R1 + R2, rtol=1e-11, atol=1e-8)
+    # indicator weights of the first 3000 cells: equals the oracle on that sub-matrix
+    n = 3000
+    D = cx.read_data(0, n)
+    assert np.array_equal(D, simdata.host_data(sim, 0, n))
+    ind = np.zeros(sim["C"])
+    ind[:n] = 1.0
+    np.testing.assert_allclose(mb.doMean(cx, ind), orc.do_mean(D, sim["pert"][:n], sim["S"]), rtol=1e-11, atol=1e-9)
+    # E-step on the full matrix, checked on the same 3000 cells
+    phi = init[0]
+    theta = rng.integers(0, sim["S"] + 1, (5, sim["E"])).astype(np.int32)
+    res = [dict(adj=phi[i], subtopo=theta[i]) for i in range(5)]
+    got = mb.getProbs(np.zeros((5, sim["C"])), 5, cx, res, complete=True)
+    want = orc.get_probs(D, sim["pert"][:n], sim["S"], phi, theta, np.zeros((5, n)), None, complete=True)
+    np.testing.assert_allclose(got["probs"][:, :n], want["probs"], rtol=1e-12, atol=1e-12)
+
+
+def test_greedy_search_at_config5_shape():
+    """S = 30, E = 2000: the device search against the oracle on one planted problem (seconds on the CPU)."""
+    rng = np.random.default_rng(5)
+    S, E = 30, 2000
+    truth = orc.mytc(np.triu((rng.random((S, S)) < 0.25).astype(np.uint8), 1))
+    p = rng.permutation(S)
+    truth = truth[np.ix_(p, p)]
+    th = rng.integers(1, S + 1, E)
+    R = np.where(truth[:, th - 1].T > 0, 1.0, -1.0) * 4 + rng.normal(size=(E, S)) * 3
+    want = orc.nem_greedy(R, None)
+    got = mb.nem_greedy(R, None)
+    assert want["min_margin"] > 1e-13
+    assert np.array_equal(got["adj"], want["adj"]) and np.array_equal(got["subtopo"], want["theta"])
+    assert got["n_iter"] == want["n_iter"] and got["n_scored"] == want["n_raw"]
+    assert abs(got["score"] - want["score"]) <= 1e-12 * abs(want["score"])
