@@ -34,7 +34,8 @@ struct SearchBatch {
     DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow;
     DevBuf<double> partial, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored;
-    int32_t *h_n_active = nullptr;   // pinned: [0] searches still active, [1] dictionary overflow flag
+    int32_t *h_n_active = nullptr;   // pinned: [0], [1] moves accepted in even / odd iterations, [2] dictionary overflow
+    cudaEvent_t ev[2] = {nullptr, nullptr};
 };
 
 // ---- candidate generation + mask dictionary ----------------------------------------------------------------
@@ -49,8 +50,8 @@ struct SearchBatch {
 // hash order; they only index a table, so no result depends on them.
 // For insertions the "changed" set written to cand_J is the whole row of v (the columns the one-step closure may
 // touch): candidates that share v then share the set, and the scoring kernel reuses their unchanged-column maximum.
-__global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int mode, const uint32_t *__restrict__ Prow,
-                                                  const int32_t *__restrict__ active, uint32_t *__restrict__ Pcol,
+__device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, const uint32_t *Prow,
+                                                  const int32_t *active, uint32_t *__restrict__ Pcol,
                                                   uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
                                                   int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind,
                                                   uint32_t *__restrict__ dict_masks, int32_t *__restrict__ nd,
@@ -215,6 +216,16 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
     if (mode != 0)
         for (int i = tid; i < 32 * 32; i += 256)
             pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
+}
+
+__global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int mode, const uint32_t *Prow,
+                                                  const int32_t *active, uint32_t *Pcol, uint32_t *cand_cols,
+                                                  uint32_t *cand_J, int32_t *ncand, int8_t *cand_kind,
+                                                  uint32_t *dict_masks, int32_t *nd, uint16_t *cand_id,
+                                                  uint16_t *base_id, uint16_t *pair_id, int32_t *nins, int32_t *overflow)
+{
+    gen_body(S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id, base_id,
+             pair_id, nins, overflow);
 }
 
 // ---- candidate scoring -----------------------------------------------------------------------------------
@@ -488,24 +499,21 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
 }
 
 // ---- argmax, accept rule, graph update -------------------------------------------------------------------
-__global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles, int mode,
-                                                     const int32_t *__restrict__ ncand,
-                                                     const double *__restrict__ partial,
-                                                     const uint32_t *__restrict__ cand_cols,
-                                                     const uint32_t *__restrict__ Pcol, uint32_t *__restrict__ Prow,
-                                                     int32_t *__restrict__ active, double *__restrict__ oldscore,
-                                                     double *__restrict__ maxtrace, int32_t *__restrict__ niter,
-                                                     unsigned long long *__restrict__ nscored,
-                                                     int32_t *__restrict__ n_active)
+template <int NT>
+__device__ __forceinline__ void finish_body(int S, int maxc, int etiles, int mode, const int32_t *ncand,
+                                            const double *__restrict__ partial, const uint32_t *cand_cols,
+                                            const uint32_t *Pcol, uint32_t *Prow, int32_t *active, double *oldscore,
+                                            double *maxtrace, int32_t *niter, unsigned long long *nscored,
+                                            int32_t *n_active)
 {
-    __shared__ double s_best[128];
-    __shared__ int s_idx[128];
+    __shared__ double s_best[NT];
+    __shared__ int s_idx[NT];
     const int q = blockIdx.x, tid = threadIdx.x;
     if (!active[q]) return;
     const int nc = ncand[q];
     double best = -INFINITY;
     int bidx = INT_MAX;
-    for (int c = tid; c < nc; c += 128) {
+    for (int c = tid; c < nc; c += NT) {
         double sc = 0.0;                                           // tiles in ascending order, whatever CTA produced them
 #pragma unroll 8
         for (int et = 0; et < etiles; ++et) sc += partial[((size_t)q * etiles + et) * maxc + c];
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles
     s_best[tid] = best;
     s_idx[tid] = bidx;
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
+    for (int o = NT / 2; o > 0; o >>= 1) {
         if (tid < o) {
             const double ob = s_best[tid + o];
             const int oi = s_idx[tid + o];
@@ -558,6 +566,33 @@ __global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles
     } else if (tid == 0) {
         active[q] = 0;
     }
+}
+
+__global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles, int mode, const int32_t *ncand,
+                                                     const double *partial, const uint32_t *cand_cols,
+                                                     const uint32_t *Pcol, uint32_t *Prow, int32_t *active,
+                                                     double *oldscore, double *maxtrace, int32_t *niter,
+                                                     unsigned long long *nscored, int32_t *n_active)
+{
+    finish_body<128>(S, maxc, etiles, mode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter, nscored,
+                     n_active);
+}
+
+// finish of greedy iteration i fused with the candidate generation of iteration i + 1 (same CTA per search): one
+// launch less per iteration and no host round trip between the accept decision and the next neighbourhood.
+__global__ void __launch_bounds__(256) finish_gen_kernel(int S, int maxc, int etiles, int fmode, int dcap, int32_t *ncand,
+                                                         const double *partial, uint32_t *cand_cols, uint32_t *Pcol,
+                                                         uint32_t *Prow, int32_t *active, double *oldscore,
+                                                         double *maxtrace, int32_t *niter, unsigned long long *nscored,
+                                                         int32_t *n_active, uint32_t *cand_J, uint32_t *dict_masks,
+                                                         int32_t *nd, uint16_t *cand_id, uint16_t *base_id,
+                                                         uint16_t *pair_id, int32_t *nins, int32_t *overflow)
+{
+    finish_body<256>(S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
+                     nscored, n_active);
+    __syncthreads();       // the accepted graph (Prow) and the active flag are visible to the whole CTA
+    gen_body(S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd, cand_id,
+             base_id, pair_id, nins, overflow);
 }
 
 __global__ void search_init_kernel(int n, int S, const uint32_t *__restrict__ start_rows, uint32_t *__restrict__ Prow,
@@ -742,14 +777,17 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->adj_rows.alloc((size_t)nmax * 32)); MN_TRY(sb->closed_rows.alloc((size_t)nmax * 32));
         MN_TRY(sb->closed_cols.alloc((size_t)nmax * 32));
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
-        MN_TRY(sb->n_active.alloc(1, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
+        MN_TRY(sb->n_active.alloc(2, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
         MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
         MN_TRY(sb->nins.alloc(nmax, true));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
-        MN_CU(cudaMallocHost((void **)&sb->h_n_active, 2 * sizeof(int32_t)));
+        MN_CU(cudaMallocHost((void **)&sb->h_n_active, 4 * sizeof(int32_t)));
+        sb->h_n_active[0] = sb->h_n_active[1] = sb->h_n_active[2] = 0;
+        MN_CU(cudaEventCreateWithFlags(&sb->ev[0], cudaEventDisableTiming));
+        MN_CU(cudaEventCreateWithFlags(&sb->ev[1], cudaEventDisableTiming));
         return 0;
     };
     int rc = body();
@@ -762,6 +800,7 @@ void search_destroy(SearchBatch *sb)
 {
     if (!sb) return;
     if (sb->h_n_active) cudaFreeHost(sb->h_n_active);
+    for (int i = 0; i < 2; ++i) if (sb->ev[i]) cudaEventDestroy(sb->ev[i]);
     delete sb;
 }
 
@@ -776,24 +815,44 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     // initial score of closure(better), R/mnems.r:135-141
     MN_TRY(launch_gen(sb, n, 0, st));
     MN_TRY(launch_score_dict(sb, n, st));
-    MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, ntiles, 0, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
-              sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
-              sb->n_active.p);
+    auto fused = [&](int fmode) -> int {
+        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, ntiles, fmode, sb->dcap, sb->ncand.p, sb->partial.p,
+                  sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p,
+                  sb->nscored.p, sb->n_active.p + 0, sb->cand_J.p, sb->dict_masks.p, sb->nd.p, sb->cand_id.p, sb->base_id.p,
+                  sb->pair_id.p, sb->nins.p, sb->overflow.p);
+        return 0;
+    };
+    // iteration it: [finish(it-1) + gen(it)] -> score(it).  The host learns the number of searches that accepted a move
+    // one iteration late (the copy of iteration it is awaited while iteration it+1 is already queued), so the GPU never
+    // idles on a host round trip; the one surplus iteration at the end finds every search inactive and does nothing.
     const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
-    for (int it = 0; it < hard_cap; ++it) {
-        MN_CU(cudaMemsetAsync(sb->n_active.p, 0, sizeof(int32_t), st));
-        MN_TRY(launch_gen(sb, n, 1, st));
+    int pending = -1;                      // iteration whose n_active copy is in flight
+    bool done = false;
+    for (int it = 0; it < hard_cap && !done; ++it) {
+        const int slot = it & 1;
+        MN_CU(cudaMemsetAsync(sb->n_active.p + slot, 0, sizeof(int32_t), st));
+        // n_active[slot] counts the searches that accept a move in this fused finish
+        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, ntiles, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
+                  sb->partial.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
+                  sb->niter.p, sb->nscored.p, sb->n_active.p + slot, sb->cand_J.p, sb->dict_masks.p, sb->nd.p,
+                  sb->cand_id.p, sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);
         MN_TRY(launch_score_dict(sb, n, st));
-        MN_LAUNCH(finish_kernel, n, 128, 0, st, S, sb->maxc, ntiles, 1, sb->ncand.p, sb->partial.p, sb->cand_cols.p,
-                  sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p, sb->nscored.p,
-                  sb->n_active.p);
-        MN_CU(cudaMemcpyAsync(sb->h_n_active, sb->n_active.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        MN_CU(cudaMemcpyAsync(sb->h_n_active + 1, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        MN_CU(cudaStreamSynchronize(st));
-        if (sb->h_n_active[1]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
-        if (sb->h_n_active[0] == 0) break;
-        sb->G = pick_groups(sb->h_n_active[0], ntiles, 148);
+        MN_CU(cudaMemcpyAsync(sb->h_n_active + slot, sb->n_active.p + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MN_CU(cudaMemcpyAsync(sb->h_n_active + 2, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MN_CU(cudaEventRecord(sb->ev[slot], st));
+        if (pending >= 0) {
+            const int ps = pending & 1;
+            MN_CU(cudaEventSynchronize(sb->ev[ps]));
+            if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+            // iteration 0's finish is the initial score (mode 0): it accepts nothing by design
+            if (pending > 0 && sb->h_n_active[ps] == 0) done = true;
+            else if (pending > 0) sb->G = pick_groups(sb->h_n_active[ps], ntiles, 148);
+        }
+        pending = it;
     }
+    (void)fused;
+    MN_CU(cudaStreamSynchronize(st));
+    if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
     return 0;
