@@ -245,12 +245,29 @@ def run_ours(args):
         try:
             import psutil
             need = 8.0 * E * Cn
-            if psutil.virtual_memory().available < 2.5 * need * max(1, world):
-                raise MemoryError("not enough host memory for a pinned copy of D on every rank")
-            host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)       # column-major E x C
-            Dh = host.numpy().T
-            with mb.Context.synthetic(sim, device=local) as c0:
-                mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(host.numpy())))
+            if world == 1:
+                if psutil.virtual_memory().available < 2.5 * need:
+                    raise MemoryError("not enough host memory for a pinned copy of D")
+                host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)   # column-major E x C
+                hnp = host.numpy()
+            else:
+                # one host copy of D for all ranks of the node: a /dev/shm file, page-locked by every rank
+                if psutil.virtual_memory().available < 2.5 * need or psutil.disk_usage("/dev/shm").free < 1.2 * need:
+                    raise MemoryError("not enough host memory / /dev/shm for a shared copy of D")
+                path = "/dev/shm/mnem_b200_bench_D_%s.bin" % os.environ.get("MASTER_PORT", "0")
+                if local == 0:
+                    np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=(Cn, E)).flush()
+                barrier()
+                hnp = np.load(path, mmap_mode="r+")
+                rc = torch.cuda.cudart().cudaHostRegister(hnp.ctypes.data, hnp.nbytes, 0)
+                if int(rc) != 0:
+                    raise MemoryError("cudaHostRegister failed: %s" % rc)
+                host = None
+            Dh = hnp.T
+            if world == 1 or local == 0:
+                with mb.Context.synthetic(sim, device=local) as c0:
+                    mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
+            barrier()
             times, iters = [], []
             for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
                 barrier()
@@ -267,7 +284,12 @@ def run_ours(args):
             e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
                    "h2d_bytes_per_step": int(8 * E * Cn + 4 * Cn + len(my) * k * S * S), "d2h_bytes_per_step": int(d2h),
                    "seconds_per_step": float(np.mean(times)), "steps": len(times)}
-            del host
+            if world > 1:
+                torch.cuda.cudart().cudaHostUnregister(hnp.ctypes.data)
+                barrier()
+                if local == 0:
+                    os.remove(path)
+            del host, hnp, Dh
         except Exception as ex:                                                    # noqa: BLE001
             e2e = {"value": None, "unit": "EM iterations/s", "error": repr(ex)[:200]}
 

@@ -32,7 +32,7 @@ struct SearchBatch {
     DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks;
     DevBuf<uint16_t> cand_id, base_id, pair_id;
     DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow;
-    DevBuf<double> partial, oldscore, maxtrace;
+    DevBuf<double> partial, scores, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored;
     int32_t *h_n_active = nullptr;   // pinned: [0], [1] moves accepted in even / odd iterations, [2] dictionary overflow
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -714,6 +714,20 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
     return 0;
 }
 
+// scores[q][c] = sum over the row tiles, ascending -- fully parallel over candidates, so the single-CTA finish step
+// reads one value per candidate instead of one per (candidate, tile)
+__global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles, const int32_t *__restrict__ ncand,
+                                                           const double *__restrict__ partial, double *__restrict__ scores)
+{
+    const int q = blockIdx.y;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncand[q]) return;
+    double sc = 0.0;
+#pragma unroll 8
+    for (int et = 0; et < ntiles; ++et) sc += partial[((size_t)q * ntiles + et) * maxc + c];
+    scores[(size_t)q * maxc + c] = sc;
+}
+
 static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
 {
     MN_LAUNCH(gen_kernel, n, 256, 0, st, sb->S, sb->maxc, sb->dcap, mode, sb->Prow.p, sb->active.p, sb->Pcol.p,
@@ -735,6 +749,9 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     else if (S <= 24) MN_SCORE(24);
     else MN_SCORE(32);
 #undef MN_SCORE
+    const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
+    dim3 rgrid((sb->maxc + 255) / 256, n);
+    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p);
     return 0;
 }
 
@@ -779,6 +796,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
         MN_TRY(sb->n_active.alloc(2, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
         MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
+        MN_TRY(sb->scores.alloc((size_t)nmax * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
@@ -815,13 +833,6 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     // initial score of closure(better), R/mnems.r:135-141
     MN_TRY(launch_gen(sb, n, 0, st));
     MN_TRY(launch_score_dict(sb, n, st));
-    auto fused = [&](int fmode) -> int {
-        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, ntiles, fmode, sb->dcap, sb->ncand.p, sb->partial.p,
-                  sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p, sb->niter.p,
-                  sb->nscored.p, sb->n_active.p + 0, sb->cand_J.p, sb->dict_masks.p, sb->nd.p, sb->cand_id.p, sb->base_id.p,
-                  sb->pair_id.p, sb->nins.p, sb->overflow.p);
-        return 0;
-    };
     // iteration it: [finish(it-1) + gen(it)] -> score(it).  The host learns the number of searches that accepted a move
     // one iteration late (the copy of iteration it is awaited while iteration it+1 is already queued), so the GPU never
     // idles on a host round trip; the one surplus iteration at the end finds every search inactive and does nothing.
@@ -832,8 +843,8 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         const int slot = it & 1;
         MN_CU(cudaMemsetAsync(sb->n_active.p + slot, 0, sizeof(int32_t), st));
         // n_active[slot] counts the searches that accept a move in this fused finish
-        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, ntiles, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
-                  sb->partial.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
+        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
+                  sb->scores.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
                   sb->niter.p, sb->nscored.p, sb->n_active.p + slot, sb->cand_J.p, sb->dict_masks.p, sb->nd.p,
                   sb->cand_id.p, sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);
         MN_TRY(launch_score_dict(sb, n, st));
@@ -850,7 +861,6 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         }
         pending = it;
     }
-    (void)fused;
     MN_CU(cudaStreamSynchronize(st));
     if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);

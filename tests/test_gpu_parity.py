@@ -348,3 +348,21 @@ def test_ragged_segments_and_missing_padding():
     assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
     w = rng.random(len(pert))
     close(mb.doMean(D, w, pert), orc.do_mean(D, pert, S, w), rtol=1e-11, atol=1e-11)
+
+
+def test_bootstrap_matches_oracle_loop():
+    """bootstrap() R/mnems.r:2348-2369: size x k searches as one device batch vs one oracle search per resample."""
+    sim = simdata.make_config(dict(S=5, Egenes=6, C=900, mw=[0.5, 0.5], k=2, starts=2, uninform=0), seed=14)
+    D = simdata.host_data(sim) + np.random.default_rng(1).normal(size=(sim["E"], sim["C"])) * 0.3
+    init = simdata.init_phi(5, 2, 2, seed=3)
+    fit = mb.mnem(D, sim["pert"], phi=init)
+    support, idx = mb.bootstrap(fit, D, sim["pert"], size=12, p=0.8, seed=5)
+    post = orc.get_affinity(fit["probs"], fit["mw"])
+    for i in range(2):
+        R = orc.do_mean(D, sim["pert"], 5, post[i])
+        acc = np.zeros((5, 5))
+        for j in range(12):
+            r = orc.nem_greedy(R[idx[i, j]], None)
+            assert r["min_margin"] > 1e-13
+            acc += orc.mytc(r["adj"])
+        assert np.array_equal(support[i], acc / 12)
