@@ -5,7 +5,7 @@
   N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
 One "step" = one complete EM phase of mnem(D, phi = init): every EM start of the config (sharded over the ranks,
-start s on rank s mod N; D replicated) runs do_inits to convergence (R/mnems.r:1884-2165).  `value` = EM loop
+N > 1: the ranks drain one shared queue of starts, mnem_b200.dist.StartQueue; D replicated) runs do_inits to convergence (R/mnems.r:1884-2165).  `value` = EM loop
 iterations summed over all starts and ranks / device time of the step (CUDA events inside the library, max over
 ranks), with D already resident in HBM.  `e2e` times the same step through the C ABI from HOST buffers: the H2D copy
 of D (pinned memory), the layout pass, the EM phase and the D2H copy of the results are all inside the timed region.
@@ -166,8 +166,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sim, init, name = make_workload(args)
-    my = mdist.shard_starts(sim["starts"], rank, world)
-    my_init = init[my]
     k, E, Cn, S = sim["k"], sim["E"], sim["C"], sim["S"]
     launches0 = mb.launch_count()
 
@@ -198,20 +196,20 @@ def run_ours(args):
         if i == args.warmup:
             sampler.start()
             launches_timed = mb.launch_count()
+        queue = mdist.StartQueue(sim["starts"])          # N = 1: a local counter
         barrier()
         t0 = time.time()
-        r = mb.em_run(cx, my_init, complete=sim["complete"], batch=args.batch, want_probs=False) if len(my) else None
+        r = mb.em_run(cx, init, complete=sim["complete"], batch=args.batch, want_probs=False, next_start=queue)
         torch.cuda.synchronize()
         wall = time.time() - t0
         barrier()
-        st = r["stats"] if r else dict(ms_total=0.0, em_iters=0, cand_scored=0, ms_estep=0.0, passes_estep=0,
-                                       estep_bytes=0.0, ms_search=0.0, ms_mstats=0.0, passes_mstats=0, ms_mixture=0.0,
-                                       greedy_iters=0)
+        my = sorted(queue.taken)
+        st = r["stats"]
         ms = reduce_max(st["ms_total"])
         tot = reduce_sum([st["em_iters"], st["cand_scored"], st["greedy_iters"]])
         if i >= args.warmup:
             recs.append(dict(ms=ms, wall=reduce_max(wall), em_iters=tot[0], cand=tot[1], st=st))
-        winner, lls = mdist.gather_winner(my, r["ll"] if r else [], sim["starts"], device=dev)
+        winner, lls = mdist.gather_winner(my, r["ll"][my], sim["starts"], device=dev)
     clocks = sampler.stop()
     launches_timed = mb.launch_count() - launches_timed
     ms_step = float(np.mean([x["ms"] for x in recs]))
@@ -242,56 +240,46 @@ def run_ours(args):
     # ---- e2e: host buffers in, host buffers out ----
     e2e = None
     if not args.no_e2e:
+        # every rank holds its own pinned host copy of D (the caller's matrix); ranks agree on go / no-go first so that a
+        # rank that cannot allocate does not leave the others waiting at a barrier
+        host, err = None, None
         try:
             import psutil
             need = 8.0 * E * Cn
-            if world == 1:
-                if psutil.virtual_memory().available < 2.5 * need:
-                    raise MemoryError("not enough host memory for a pinned copy of D")
-                host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)   # column-major E x C
-                hnp = host.numpy()
-            else:
-                # one host copy of D for all ranks of the node: a /dev/shm file, page-locked by every rank
-                if psutil.virtual_memory().available < 2.5 * need or psutil.disk_usage("/dev/shm").free < 1.2 * need:
-                    raise MemoryError("not enough host memory / /dev/shm for a shared copy of D")
-                path = "/dev/shm/mnem_b200_bench_D_%s.bin" % os.environ.get("MASTER_PORT", "0")
-                if local == 0:
-                    np.lib.format.open_memmap(path, mode="w+", dtype=np.float64, shape=(Cn, E)).flush()
-                barrier()
-                hnp = np.load(path, mmap_mode="r+")
-                rc = torch.cuda.cudart().cudaHostRegister(hnp.ctypes.data, hnp.nbytes, 0)
-                if int(rc) != 0:
-                    raise MemoryError("cudaHostRegister failed: %s" % rc)
-                host = None
+            if psutil.virtual_memory().available < (1.5 + world) * need:
+                raise MemoryError("not enough host memory for a pinned copy of D per rank")
+            host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)       # column-major E x C
+        except Exception as ex:                                                    # noqa: BLE001
+            err = ex
+        if -reduce_max(-(1.0 if err is None else 0.0)) < 1.0:
+            e2e = {"value": None, "unit": "EM iterations/s", "error": repr(err)[:200] if err else "another rank failed"}
+        else:
+            hnp = host.numpy()
             Dh = hnp.T
-            if world == 1 or local == 0:
-                with mb.Context.synthetic(sim, device=local) as c0:
-                    mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
-            barrier()
+            with mb.Context.synthetic(sim, device=local) as c0:
+                mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
             times, iters = [], []
             for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
+                queue = mdist.StartQueue(sim["starts"])
                 barrier()
                 t0 = time.time()
                 with mb.Context(Dh, sim["pert"], device=local) as cxe:
-                    r = mb.em_run(cxe, my_init, complete=sim["complete"], batch=args.batch, want_probs=False) if len(my) else None
+                    r = mb.em_run(cxe, init, complete=sim["complete"], batch=args.batch, want_probs=False, next_start=queue)
+                my = sorted(queue.taken)
+                mdist.gather_winner(my, r["ll"][my], sim["starts"], device=dev)     # the winner is part of the result
                 torch.cuda.synchronize()
                 dt = reduce_max(time.time() - t0)
                 barrier()
                 if i >= 1:
                     times.append(dt)
-                    iters.append(reduce_sum([r["stats"]["em_iters"] if r else 0])[0])
-            d2h = len(my) * (k * S * S + 4 * k * E + 8 * k + 8 + 4 + 4 * 8 * 256)
+                    iters.append(reduce_sum([r["stats"]["em_iters"]])[0])
+            per_start = k * S * S + 4 * k * E + 8 * k + 8 + 4 + 4 * 8 * 256          # adj, theta, mw, ll, n_iter, traces
             e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
-                   "h2d_bytes_per_step": int(8 * E * Cn + 4 * Cn + len(my) * k * S * S), "d2h_bytes_per_step": int(d2h),
+                   "h2d_bytes_per_step": int(world * (8 * E * Cn + 4 * Cn + sim["starts"] * k * S * S)),
+                   "d2h_bytes_per_step": int(sim["starts"] * per_start),
                    "seconds_per_step": float(np.mean(times)), "steps": len(times)}
-            if world > 1:
-                torch.cuda.cudart().cudaHostUnregister(hnp.ctypes.data)
-                barrier()
-                if local == 0:
-                    os.remove(path)
-            del host, hnp, Dh
-        except Exception as ex:                                                    # noqa: BLE001
-            e2e = {"value": None, "unit": "EM iterations/s", "error": repr(ex)[:200]}
+            del hnp, Dh
+        del host
 
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
@@ -306,7 +294,8 @@ def run_ours(args):
         line = {"metric": "em_iterations_per_s", "value": value, "unit": "EM iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": name, "starts_per_rank": len(my), "batch": args.batch or max(1, 20 // k),
+                "config": {"workload": name, "starts_on_rank0": len(my),
+                           "sharding": "one queue of starts drained by all ranks" if world > 1 else "single GPU", "batch": args.batch or max(1, 20 // k),
                            "l2": "inputs larger than L2 (D = %.1f GB per layout)" % (8e-9 * E * Cn),
                            "candidate_count": "graphs generated and scored, before unique()"},
                 "em_iters_per_step": em_iters, "cand_scores_per_s": cand_rate,

@@ -122,6 +122,12 @@ typedef struct {
     int batch;           /* EM starts sharing one pass over D (0 = choose so that k*batch <= 20) */
     int max_trace;       /* capacity per start of the lls/phievo/thetaevo/mwevo arrays */
     int max_iter_guard;  /* hard stop per start, 0 = none (the reference has none when increase = TRUE) */
+    /* Optional shared work queue (several callers, one per GPU, fitting one set of starts): when non-NULL the
+     * next start index comes from next_start(user) -- any value outside 0..starts-1 means "drained" -- instead
+     * of 0, 1, 2, ...  Starts this caller did not fit keep n_iter = -1 and ll = -Inf.  The reference's analogue
+     * is the snowfall worker pool that do_inits is mapped over (R/mnems.r:2166-2170). */
+    int32_t (*next_start)(void *user);
+    void *next_start_user;
 } mnemcu_em_opts;
 
 typedef struct {
@@ -137,7 +143,8 @@ typedef struct {
 /* mnem(D, phi = init) EM phase: do_inits for every start, R/mnems.r:1884-2165 (explicit-phi entry :1792-1793).
  * init_phi: starts*k graphs.  Per-start outputs (start-major): adj (k graphs, reduced), theta (k*E), probs
  * (k x C = limits$probs$probs), mw (k = limits$mw), ll (limits$ll), n_iter, traces (max_trace each).
- * *best = index of the winning start by R/mnems.r:2222-2230 (last maximal ll).  stats may be NULL. */
+ * *best = index of the winning start by R/mnems.r:2222-2230 (last maximal ll) among the starts fitted by this
+ * call (-1 if it fitted none).  stats may be NULL. */
 int mnemcu_em_run(mnemcu_ctx *ctx, int starts, int k, const uint8_t *init_phi, const mnemcu_em_opts *opts,
                   uint8_t *adj_out, int32_t *theta_out, double *probs_out, double *mw_out, double *ll_out,
                   int32_t *n_iter_out, double *lls, double *phievo, double *thetaevo, double *mwevo, int32_t *best,

@@ -341,8 +341,13 @@ def sample_init(S, k, starts, seed=0):
     return init_phi(S, k, starts, seed)
 
 
-def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, max_iter_guard=0, want_probs=True):
-    """mnemcu_em_run on a Context: all starts, returns per-start arrays + winner + stats."""
+def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, max_iter_guard=0, want_probs=True,
+           next_start=None):
+    """mnemcu_em_run on a Context: all starts, returns per-start arrays + winner + stats.
+
+    next_start: optional callable returning the next start index to fit (or -1 when none is left) -- the ticket
+    function of a queue shared by several ranks (mnem_b200.dist.StartQueue).  Starts fitted elsewhere come back with
+    n_iter = -1 and ll = -inf."""
     init_phi = np.asarray(init_phi)
     starts, k = init_phi.shape[:2]
     S, E, Cn = cx.S, cx.E, cx.C
@@ -356,17 +361,29 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     best = C.c_int32(-1)
     st = EmStats()
-    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard))
+    cb_err = []
+
+    def _ticket(_user):
+        try:
+            return int(next_start())
+        except BaseException as ex:            # never let an exception unwind through the C frames
+            cb_err.append(ex)
+            return -1
+
+    cb = _lib.NEXT_START_FN(_ticket) if next_start is not None else _lib.NEXT_START_FN()
+    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None)
     check(load_library().mnemcu_em_run(cx._h, starts, k, u8p(pb), C.byref(o), u8p(adj), i32p(theta), dp(probs), dp(mw),
                                        dp(ll), i32p(nit), dp(tr[0]), dp(tr[1]), dp(tr[2]), dp(tr[3]), C.byref(best),
                                        C.byref(st)))
+    if cb_err:
+        raise cb_err[0]
     stats = {f: getattr(st, f) for f, _ in EmStats._fields_}
     return dict(best=best.value, adj=_ungraphs(adj, starts * k, S).reshape(starts, k, S, S), theta=theta,
                 probs=np.transpose(probs, (0, 2, 1)) if want_probs else None, mw=mw, ll=ll, n_iter=nit,
-                lls=[tr[0][s, :min(nit[s], max_trace)].copy() for s in range(starts)],
-                phievo=[tr[1][s, :min(nit[s], max_trace)].copy() for s in range(starts)],
-                thetaevo=[tr[2][s, :min(nit[s], max_trace)].copy() for s in range(starts)],
-                mwevo=[tr[3][s, :min(nit[s], max_trace)].copy() for s in range(starts)], stats=stats)
+                lls=[tr[0][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)],
+                phievo=[tr[1][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)],
+                thetaevo=[tr[2][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)],
+                mwevo=[tr[3][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)], stats=stats)
 
 
 def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0):

@@ -468,7 +468,17 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     const int T = en.T;
     const size_t kC = (size_t)k * C, kE = (size_t)k * E, kSS = (size_t)k * S * S;
     const int mt = opts->max_trace;
-    int next_start = 0, running = 0;
+    int next_seq = 0, running = 0;
+    // The next EM start: 0, 1, 2, ... or, when several callers (one per GPU) drain one queue, whatever the caller's
+    // ticket function hands out.  Results are always stored at the start's own index.
+    for (int s = 0; s < starts; ++s) { n_iter_out[s] = -1; ll_out[s] = -INFINITY; }
+    auto take_start = [&]() -> int {
+        if (opts->next_start) {
+            const int s = opts->next_start(opts->next_start_user);
+            return (s >= 0 && s < starts) ? s : -1;
+        }
+        return next_seq < starts ? next_seq++ : -1;
+    };
     cudaEvent_t evA, evB;
     MN_CU(cudaEventCreate(&evA)); MN_CU(cudaEventCreate(&evB));
     MN_CU(cudaEventRecord(evA, st));
@@ -534,7 +544,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     };
 
     auto body = [&]() -> int {
-        for (int b = 0; b < B && next_start < starts; ++b) MN_TRY(begin_slot(b, next_start++));
+        for (int b = 0; b < B; ++b) {
+            const int s0 = take_start();
+            if (s0 < 0) break;
+            MN_TRY(begin_slot(b, s0));
+        }
         long guard_ticks = 0;
         while (running > 0) {
             ++guard_ticks;
@@ -655,7 +669,8 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                 const bool guard = opts->max_iter_guard > 0 && s.count >= opts->max_iter_guard;
                 if (!again || guard) {
                     MN_TRY(finish_slot(b));
-                    if (next_start < starts) MN_TRY(begin_slot(b, next_start++));
+                    const int s1 = take_start();
+                    if (s1 >= 0) MN_TRY(begin_slot(b, s1));
                 }
             }
             if (guard_ticks > 100000) return set_err(MNEMCU_ERR_ARG, "EM did not terminate");

@@ -50,6 +50,7 @@ struct SearchBatch {
 // hash order; they only index a table, so no result depends on them.
 // For insertions the "changed" set written to cand_J is the whole row of v (the columns the one-step closure may
 // touch): candidates that share v then share the set, and the scoring kernel reuses their unchanged-column maximum.
+template <int NT>
 __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, const uint32_t *Prow,
                                                   const int32_t *active, uint32_t *__restrict__ Pcol,
                                                   uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
@@ -62,16 +63,18 @@ __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, co
     __shared__ uint32_t keys[kDictHash];
     __shared__ uint16_t ids[kDictHash];
     __shared__ uint16_t s_pair[32 * 32];
-    __shared__ int s_warp[8];
+    __shared__ int s_warp[NT / 32];
+    constexpr int kPer = kDictHash / NT;          // hash slots per thread in the dense-id scan
+    static_assert(kPer * NT == kDictHash, "thread count must divide the hash size");
     const int q = blockIdx.x, tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
     if (!active[q]) {
         if (tid == 0) { ncand[q] = 0; if (nd) { nd[q] = 0; nins[q] = 0; } }
         return;
     }
     const bool dict = dict_masks != nullptr;
     if (dict)
-        for (int i = tid; i < kDictHash; i += 256) keys[i] = 0u;
+        for (int i = tid; i < kDictHash; i += NT) keys[i] = 0u;
     __syncthreads();
     auto insert = [&](uint32_t m) -> int {          // returns the hash slot of m
         int h = (int)((m * 2654435761u) >> 21);
@@ -179,10 +182,10 @@ __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, co
     }
     if (!dict) return;
     __syncthreads();
-    // dense ids: exclusive scan of the occupied slots (8 consecutive slots per thread)
+    // dense ids: exclusive scan of the occupied slots (kPer consecutive slots per thread)
     int cnt = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cnt += keys[tid * 8 + i] != 0u;
+    for (int i = 0; i < kPer; ++i) cnt += keys[tid * kPer + i] != 0u;
     int incl = cnt;
     for (int o = 1; o < 32; o <<= 1) {
         const int t = __shfl_up_sync(kFull, incl, o);
@@ -193,15 +196,15 @@ __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, co
     int base = incl - cnt;
     for (int w = 0; w < warp; ++w) base += s_warp[w];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t k = keys[tid * 8 + i];
+    for (int i = 0; i < kPer; ++i) {
+        const uint32_t k = keys[tid * kPer + i];
         if (k != 0u) {
-            ids[tid * 8 + i] = (uint16_t)base;
+            ids[tid * kPer + i] = (uint16_t)base;
             if (base < dcap) dict_masks[(size_t)q * dcap + base] = k;
             ++base;
         }
     }
-    if (tid == 255) {
+    if (tid == NT - 1) {
         nd[q] = base;
         if (base > dcap) atomicOr(overflow, 1);
     }
@@ -209,12 +212,12 @@ __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, co
     // hash slots -> dense ids (cand_id / base_id written by this CTA above; __syncthreads makes them visible)
     if (tid < S) base_id[q * 32 + tid] = ids[base_id[q * 32 + tid]];
     const int first = mode == 0 ? 0 : nins[q];            // written by thread 0 before the barriers above
-    for (int i = first * 32 + tid; i < total * 32; i += 256) {
+    for (int i = first * 32 + tid; i < total * 32; i += NT) {
         const int c = i >> 5, j = i & 31;
         if ((cj[c] >> j) & 1u) ci[i] = ids[ci[i]];
     }
     if (mode != 0)
-        for (int i = tid; i < 32 * 32; i += 256)
+        for (int i = tid; i < 32 * 32; i += NT)
             pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
 }
 
@@ -224,8 +227,8 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
                                                   uint32_t *dict_masks, int32_t *nd, uint16_t *cand_id,
                                                   uint16_t *base_id, uint16_t *pair_id, int32_t *nins, int32_t *overflow)
 {
-    gen_body(S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id, base_id,
-             pair_id, nins, overflow);
+    gen_body<256>(S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id,
+                  base_id, pair_id, nins, overflow);
 }
 
 // ---- candidate scoring -----------------------------------------------------------------------------------
@@ -580,7 +583,8 @@ __global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles
 
 // finish of greedy iteration i fused with the candidate generation of iteration i + 1 (same CTA per search): one
 // launch less per iteration and no host round trip between the accept decision and the next neighbourhood.
-__global__ void __launch_bounds__(256) finish_gen_kernel(int S, int maxc, int etiles, int fmode, int dcap, int32_t *ncand,
+constexpr int kFgThreads = 1024;   // 32 warps: the 3*S candidate groups of a search spread over all of them
+__global__ void __launch_bounds__(kFgThreads) finish_gen_kernel(int S, int maxc, int etiles, int fmode, int dcap, int32_t *ncand,
                                                          const double *partial, uint32_t *cand_cols, uint32_t *Pcol,
                                                          uint32_t *Prow, int32_t *active, double *oldscore,
                                                          double *maxtrace, int32_t *niter, unsigned long long *nscored,
@@ -588,11 +592,11 @@ __global__ void __launch_bounds__(256) finish_gen_kernel(int S, int maxc, int et
                                                          int32_t *nd, uint16_t *cand_id, uint16_t *base_id,
                                                          uint16_t *pair_id, int32_t *nins, int32_t *overflow)
 {
-    finish_body<256>(S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
+    finish_body<kFgThreads>(S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
                      nscored, n_active);
     __syncthreads();       // the accepted graph (Prow) and the active flag are visible to the whole CTA
-    gen_body(S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd, cand_id,
-             base_id, pair_id, nins, overflow);
+    gen_body<kFgThreads>(S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd,
+                         cand_id, base_id, pair_id, nins, overflow);
 }
 
 __global__ void search_init_kernel(int n, int S, const uint32_t *__restrict__ start_rows, uint32_t *__restrict__ Prow,
@@ -843,7 +847,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         const int slot = it & 1;
         MN_CU(cudaMemsetAsync(sb->n_active.p + slot, 0, sizeof(int32_t), st));
         // n_active[slot] counts the searches that accept a move in this fused finish
-        MN_LAUNCH(finish_gen_kernel, n, 256, 0, st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
+        MN_LAUNCH(finish_gen_kernel, n, kFgThreads, 0, st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
                   sb->scores.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
                   sb->niter.p, sb->nscored.p, sb->n_active.p + slot, sb->cand_J.p, sb->dict_masks.p, sb->nd.p,
                   sb->cand_id.p, sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);

@@ -3,6 +3,42 @@ are sharded across ranks (one process per GPU) with no data-path collective.  Th
 (ll, start id) reduction that picks the winner, done with torch.distributed (NCCL on GPUs, gloo in CPU tests)."""
 import numpy as np
 
+_queue_serial = [0]
+
+
+class StartQueue:
+    """One queue of EM starts drained by all ranks: a ticket counter in the torch.distributed key-value store (the
+    rendezvous store every process group already has; `add` is atomic on the store's server).  A rank asks for its
+    next start whenever one of its slots frees up, so ranks whose starts converge quickly take more of them and all
+    GPUs run dry together -- the role snowfall's worker pool plays in the reference (R/mnems.r:2166-2170).  This is
+    control traffic (one small TCP round trip per start), not a data-path collective.
+
+    Every rank must construct its queues in the same order (the key is a per-process serial number).  Without an
+    initialised process group it degenerates to a local counter."""
+
+    def __init__(self, n_starts, store=None):
+        import torch.distributed as dist
+        self.n = int(n_starts)
+        self.taken = []
+        _queue_serial[0] += 1
+        self.key = "mnem_b200/start_queue/%d" % _queue_serial[0]
+        self.store = store
+        if store is None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from torch.distributed import distributed_c10d
+            self.store = distributed_c10d._get_default_store()
+        self._local = 0
+
+    def __call__(self):
+        if self.store is not None:
+            t = int(self.store.add(self.key, 1)) - 1
+        else:
+            t = self._local
+            self._local += 1
+        if t >= self.n:
+            return -1
+        self.taken.append(t)
+        return t
+
 
 def shard_starts(n_starts, rank, world):
     """Start s runs on rank s mod world (round-robin keeps the per-rank queues the same length +-1)."""

@@ -32,6 +32,39 @@ dist.destroy_process_group()
 """
 
 
+# the shared start queue: ranks pull tickets from the process group's store until it is drained
+WORKER_QUEUE = r"""
+import os, sys, json, time
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import oracle as orc
+from mnem_b200 import simdata, dist as mdist
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+sim = simdata.make_config(dict(S=4, Egenes=3, C=300, mw=[0.5, 0.5], k=2, starts=7, uninform=0), seed=3)
+D = simdata.host_data(sim)
+init = simdata.init_phi(4, 2, 7, seed=9)
+lls = {}
+for rep in range(2):                       # two queues in a row: keys must not collide
+    q = mdist.StartQueue(7)
+    lls = {}
+    while True:
+        s = q()
+        if s < 0:
+            break
+        lls[s] = float(orc.mnem_em(D, sim["pert"], 4, init[s:s + 1])["ll"][0])
+        time.sleep(0.01 * (rank + 1))     # uneven ranks: the faster one takes more starts
+    assert q() == -1
+    assert sorted(lls) == sorted(q.taken)
+    dist.barrier()
+ids = sorted(lls)
+winner, all_lls = mdist.gather_winner(ids, [lls[i] for i in ids], 7)
+print(json.dumps(dict(rank=rank, my=ids, winner=int(winner), lls=[float(x) for x in all_lls])))
+dist.destroy_process_group()
+"""
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -68,3 +101,32 @@ def test_two_rank_gloo_winner_matches_single_process():
     assert outs[0]["winner"] == outs[1]["winner"] == ref["best"]
     np.testing.assert_array_equal(outs[0]["lls"], ref["ll"])
     assert sorted(outs[0]["my"] + outs[1]["my"]) == list(range(5))
+
+
+def test_two_rank_shared_start_queue_covers_every_start_once():
+    import json
+
+    import oracle as orc
+    from mnem_b200 import simdata
+    port = _free_port()
+    src = WORKER_QUEUE % dict(root=ROOT, port=port)
+    procs = [subprocess.Popen([sys.executable, "-c", src, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=300)
+        assert p.returncode == 0, e[-2000:]
+        outs.append(json.loads(o.strip().splitlines()[-1]))
+    sim = simdata.make_config(dict(S=4, Egenes=3, C=300, mw=[0.5, 0.5], k=2, starts=7, uninform=0), seed=3)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(4, 2, 7, seed=9)
+    ref = orc.mnem_em(D, sim["pert"], 4, init)
+    assert sorted(outs[0]["my"] + outs[1]["my"]) == list(range(7))          # each start exactly once
+    assert outs[0]["winner"] == outs[1]["winner"] == ref["best"]
+    np.testing.assert_array_equal(outs[0]["lls"], ref["ll"])
+
+
+def test_start_queue_without_process_group_is_a_local_counter():
+    q = mdist.StartQueue(3)
+    assert [q(), q(), q(), q(), q()] == [0, 1, 2, -1, -1]
+    assert q.taken == [0, 1, 2]

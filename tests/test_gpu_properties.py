@@ -43,6 +43,33 @@ def test_em_is_deterministic_and_batch_independent(big):
     assert a["best"] == max(i for i in range(len(a["ll"])) if a["ll"][i] == a["ll"].max())
 
 
+def test_shared_start_queue_gives_the_same_fits(big):
+    """Two callers draining one queue (what the ranks of an N-GPU job do) fit every start exactly once, and every fit is
+    bit-identical to the single-call fit: a start's result does not depend on which starts share its passes."""
+    from mnem_b200 import dist as mdist
+    sim, cx, init = big
+    full = mb.em_run(cx, init, complete=True, batch=2)
+    q = mdist.StartQueue(init.shape[0])
+    first = {"n": 0}
+
+    def two_only():                       # caller A stops asking after two starts ...
+        if first["n"] >= 2:
+            return -1
+        first["n"] += 1
+        return q()
+    a = mb.em_run(cx, init, complete=True, batch=2, next_start=two_only)
+    b = mb.em_run(cx, init, complete=True, batch=2, next_start=q)      # ... caller B drains the rest
+    ida = [s for s in range(init.shape[0]) if a["n_iter"][s] >= 0]
+    idb = [s for s in range(init.shape[0]) if b["n_iter"][s] >= 0]
+    assert sorted(ida + idb) == list(range(init.shape[0])) and len(ida) == 2
+    assert np.isneginf(a["ll"][idb]).all() and np.isneginf(b["ll"][ida]).all()
+    for part, ids in ((a, ida), (b, idb)):
+        for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
+            assert np.array_equal(part[key][ids], full[key][ids]), key
+    lls = np.where(a["n_iter"] >= 0, a["ll"], b["ll"])
+    assert mdist.pick_winner(lls) == full["best"]
+
+
 def test_em_pieces_are_consistent_at_scale(big):
     """The winner's stored probs must be reproduced by getProbs from its (phi, theta), and its graphs must be fixed
     points of transitive reduction; the planted mixture is recovered well."""
