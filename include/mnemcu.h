@@ -12,7 +12,8 @@
  *     consecutive S*S blocks; S <= 32 in this build;
  *   - theta (E-gene attachment, `subtopo`) is int32[E], values 0..S, 0 = unattached (R/mnems.r:448-449);
  *   - pert is int32[C], values 1..S: the S-gene knocked down in each cell, i.e. as.integer(colnames(D))
- *     after modData() (R/mnems_low.r:415-433).  Multi-knock-down columns ("1_3", Rho path) are out of scope;
+ *     after modData() (R/mnems_low.r:415-433).  Data with multi-knock-down columns ("1_3") is given by its
+ *     S x C perturbation matrix Rho = getRho(D) (R/mnems_low.r:308-324) through mnemcu_ctx_create_rho;
  *   - `probs`/L is the k x C matrix of per-cell log ratios in units of log_b (R/mnems.r:1674-1675);
  *   - host pointers in, host pointers out; the caller owns every buffer.  Only mnemcu_ctx keeps device
  *     memory between calls; no host pointer is retained after a call returns;
@@ -87,6 +88,13 @@ int mnemcu_nem_greedy(const double *R, int E, int S, const uint8_t *start, int n
 /* ---- device-resident data context -------------------------------------------------------------------- */
 /* Uploads D (E x C) once, sorted by perturbation, in the two HBM layouts the kernels stream. */
 int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *pert, int S, int device, mnemcu_ctx **out);
+/* The Rho path of the reference (mnem(), nem(), getProbs(), doMean() called with Rho != NULL): Rho is S x C
+ * column-major, Rho[s,c] != 0 <=> S-gene s is knocked down in cell c (any number per cell, also none).  Every
+ * entry point that takes the context then follows the reference's Rho branches: effect of a cell =
+ * min(1, t(Rho) %*% closure(phi)) (R/mnems_low.r:613-616), doMean = (D diag w) %*% t(Rho') with the columns
+ * of Rho' normalised to sum 1 (:896-904).  The collapsed E x S matrix handed to the structure search is an
+ * ordinary single-knock-down problem (nem() re-derives Rho from it, R/mnems.r:101-107). */
+int mnemcu_ctx_create_rho(const double *D, int E, int C, const double *Rho, int S, int device, mnemcu_ctx **out);
 /* Same, but D is produced on the device by the simData-style generator (mnem_b200/simdata.py describes the
  * tables): comp[C] component of each cell (0-based), phi_true n_comp graphs (closed), theta_true n_comp*E
  * (0 = uninformative row).  D[e,c] = 2*bin - 1 + noise(seed, e + E*c). */

@@ -6,5 +6,5 @@ simData-style input generator (simdata.py).  There is no CPU fallback.
 """
 from ._lib import MnemcuError, load_library  # noqa: F401
 from .api import (Context, bootstrap, device_count, doMean, eigenMapMatMult, em_run, getAffinity, getIC, getLL, getProbs,  # noqa: F401
-                  launch_count, maxCol_row, mnem, mnemk, mod_data, neighbours, nem, nem_greedy, sample_init, scoreAdj,
+                  get_rho, get_sgenes, launch_count, maxCol_row, mnem, mnemk, mod_data, neighbours, nem, nem_greedy, sample_init, scoreAdj,
                   transClose_Del, transClose_Ins, transClose_W, transitive_closure, transitive_reduction)

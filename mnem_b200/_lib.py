@@ -55,6 +55,7 @@ SIGNATURES = {
     "mnemcu_score_adj": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, C.c_int, c_dp, c_i32p, c_dp]),
     "mnemcu_nem_greedy": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, c_u8p, c_i32p, c_dp, c_dp, c_i32p, c_i64p]),
     "mnemcu_ctx_create": (C.c_int, [c_dp, C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(c_ctx)]),
+    "mnemcu_ctx_create_rho": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.POINTER(c_ctx)]),
     "mnemcu_ctx_create_synthetic": (C.c_int, [C.c_int, C.c_int, c_i32p, C.c_int, c_u8p, C.c_int, c_u8p, c_i32p,
                                               C.c_uint64, C.c_int, C.POINTER(c_ctx)]),
     "mnemcu_synthetic_fill_host": (C.c_int, [c_dp, C.c_int, C.c_int64, C.c_int64, c_i32p, C.c_int, c_u8p, C.c_int,

@@ -46,7 +46,10 @@ def _natural_key(s):
 
 
 def mod_data(pert):
-    """modData()/getSgenes(): labels -> integers 1..S in natural order.  Returns (pert int32[C], S, labels)."""
+    """modData()/getSgenes(): labels -> integers 1..S in natural order.  Returns (pert int32[C], S, labels).
+
+    Labels with "_" ("1_3": several knock-downs in one cell) cannot be expressed as one integer per cell: use
+    get_rho() and the Rho path (Context(D, Rho=...) does this automatically)."""
     p = np.asarray(pert)
     if p.dtype.kind in "iu":
         S = int(p.max())
@@ -55,9 +58,32 @@ def mod_data(pert):
         return np.ascontiguousarray(p, dtype=np.int32), S, [str(i) for i in range(1, S + 1)]
     labs = sorted(set(str(x) for x in p), key=_natural_key)
     if any("_" in x for x in labs):
-        raise NotImplementedError("multi-knock-down columns (Rho path, R/mnems_low.r:613-616) are out of scope")
+        raise ValueError("multi-knock-down labels: use get_rho() / Context(D, pert) which takes the Rho path")
     idx = {x: i + 1 for i, x in enumerate(labs)}
     return np.array([idx[str(x)] for x in p], dtype=np.int32), len(labs), labs
+
+
+def get_sgenes(pert):
+    """getSgenes() R/mnems_low.r:1015-1023: the distinct S-gene names in the column labels, "_"-separated
+    combinations split, natural order."""
+    names = set()
+    for x in np.asarray(pert).ravel():
+        names.update(t for t in str(x).split("_") if t != "")
+    return sorted(names, key=_natural_key)
+
+
+def get_rho(pert, sgenes=None):
+    """getRho() R/mnems_low.r:308-324: S x C 0/1 matrix, Rho[s, c] = 1 <=> S-gene s is knocked down in cell c.
+    Column labels are S-gene names joined by "_" ("3", "1_3", ...)."""
+    labs = [str(x) for x in np.asarray(pert).ravel()]
+    sg = list(sgenes) if sgenes is not None else get_sgenes(labs)
+    idx = {s: i for i, s in enumerate(sg)}
+    Rho = np.zeros((len(sg), len(labs)))
+    for c, x in enumerate(labs):
+        for t in x.split("_"):
+            if t != "":
+                Rho[idx[t], c] = 1.0
+    return Rho, sg
 
 
 def launch_count():
@@ -74,13 +100,26 @@ def device_count():
 class Context:
     """The expression matrix resident in HBM (mnemcu_ctx).  Create once, reuse for every call on the same data."""
 
-    def __init__(self, D=None, pert=None, device=0, _handle=None, _dims=None):
+    def __init__(self, D=None, pert=None, device=0, Rho=None, _handle=None, _dims=None):
         self._lib = load_library()
         self._h = _lib.c_ctx()
         if _handle is not None:
             self._h, (self.E, self.C, self.S) = _handle, _dims
             return
         D = _f(D)
+        if Rho is None and pert is not None and np.asarray(pert).dtype.kind not in "iu" and \
+                any("_" in str(x) for x in np.asarray(pert).ravel()):
+            Rho, self.labels = get_rho(pert)                  # multi-knock-down labels: the Rho path
+        if Rho is not None:
+            Rho = _f(Rho)
+            S = Rho.shape[0]
+            if Rho.shape[1] != D.shape[1]:
+                raise ValueError("Rho must be S x C with one column per column of D")
+            if not hasattr(self, "labels"):
+                self.labels = [str(i) for i in range(1, S + 1)]
+            self.E, self.C, self.S = D.shape[0], D.shape[1], S
+            check(self._lib.mnemcu_ctx_create_rho(dp(D), self.E, self.C, dp(Rho), S, int(device), C.byref(self._h)))
+            return
         pert, S, self.labels = mod_data(pert)
         if D.shape[1] != len(pert):
             raise ValueError("pert must have one entry per column of D")
@@ -124,10 +163,10 @@ class Context:
             pass
 
 
-def _ctx(D, pert):
+def _ctx(D, pert, Rho=None):
     if isinstance(D, Context):
         return D, False
-    return Context(D, pert), True
+    return Context(D, pert, Rho=Rho), True
 
 
 # ---- src/mm.cpp ------------------------------------------------------------------------------------------------
@@ -226,9 +265,10 @@ def getLL(x, logtype=2, mw=None, data=None, complete=False):
 
 
 # ---- M-step -----------------------------------------------------------------------------------------------------
-def doMean(D, weights=None, pert=None):
-    """doMean on the Rho path: E x S matrix (or [n, E, S] for an [n, C] weight matrix)."""
-    cx, own = _ctx(D, pert)
+def doMean(D, weights=None, pert=None, Rho=None):
+    """doMean on the Rho path: E x S matrix (or [n, E, S] for an [n, C] weight matrix).  With multi-knock-down cells
+    (Rho given, or "_" labels in pert) a cell's weighted column is split evenly over its S-genes (:897-902)."""
+    cx, own = _ctx(D, pert, Rho)
     try:
         w = None
         n = 1
@@ -293,9 +333,9 @@ def nem_greedy(R, start=None):
     return out
 
 
-def nem(D, pert=None, start=None, weights=None):
-    """nem(D, search='greedy', start, weights, domean=TRUE): list(adj, score, subtopo, subweights, ...)."""
-    R = doMean(D, weights, pert)
+def nem(D, pert=None, start=None, weights=None, Rho=None):
+    """nem(D, search='greedy', start, weights, domean=TRUE, Rho): list(adj, score, subtopo, subweights, ...)."""
+    R = doMean(D, weights, pert, Rho)
     r = nem_greedy(R, None if start is None else np.asarray(start)[None] if np.asarray(start).ndim == 2 else start)
     sw = scoreAdj(R, r["adj"])["subweights"]
     return dict(adj=r["adj"], score=float(r["score"]), scores_max=float(r["max_trace"]), subtopo=r["subtopo"],
@@ -303,11 +343,11 @@ def nem(D, pert=None, start=None, weights=None):
 
 
 # ---- E-step -----------------------------------------------------------------------------------------------------
-def getProbs(probs, k, data, res, pert=None, mw=None, complete=False, logtype=2):
-    """getProbs(probs, k, data, res, ...): list(probs, subtopoX, mw, ll).
+def getProbs(probs, k, data, res, pert=None, mw=None, complete=False, logtype=2, Rho=None):
+    """getProbs(probs, k, data, res, ..., Rho): list(probs, subtopoX, mw, ll).
 
     res: list of k dicts with 'adj' and optionally 'subtopo' (all or none), like the reference's res list."""
-    cx, own = _ctx(data, pert)
+    cx, own = _ctx(data, pert, Rho)
     try:
         phi = np.stack([np.asarray(r["adj"]) for r in res])
         has = [r.get("subtopo") is not None for r in res]
@@ -386,13 +426,14 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
                 mwevo=[tr[3][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)], stats=stats)
 
 
-def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0):
-    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype).
+def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0,
+         Rho=None):
+    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho).
 
     Returns the fields of the reference's `mnem` object that the hot path produces: limits (per start), comp
     (phi reduced, theta), mw (lambda0, R/mnems.r:2298-2303), probs (k x C log ratios of the winner), lls, phievo,
     thetaevo, mwevo, ll, complete, plus best_start and the device-side stats."""
-    cx, own = _ctx(D, pert)
+    cx, own = _ctx(D, pert, Rho)
     try:
         if phi is not None:
             phi = np.asarray(phi)

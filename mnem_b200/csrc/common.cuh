@@ -95,18 +95,28 @@ constexpr unsigned kFull = 0xffffffffu;
 struct mnemcu_ctx {
     int device = 0;
     int E = 0, Epad = 0, C = 0, Cp = 0, S = 0, nblk = 0;
-    // cells sorted by perturbed S-gene, every segment padded to a multiple of 64 cells (padding = zeros)
+    // Cells are grouped by their SET of knocked-down S-genes.  Groups 0..S-1 are the single knock-downs (present even
+    // when empty), further groups are the distinct multi-knock-down sets of the Rho path (R/mnems_low.r:308-324,
+    // 613-616) in ascending mask order, plus the empty set if control cells exist.  G == S and multi == false for
+    // ordinary single-knock-down data, and everything below then reduces to "one segment per S-gene".
+    int G = 0;
+    bool multi = false;
+    std::vector<uint32_t> h_gmask;    // [G] bit s = S-gene s knocked down in the cells of the group
+    uint32_t *gmask = nullptr;        // device copy
+    double *gweight = nullptr;        // [G] 1 / max(1, popcount): the normalised Rho column of doMean, :897-902
+    int32_t *sg_ptr = nullptr, *sg_idx = nullptr;   // CSR: groups that contain S-gene s, ascending (device)
+    // cells sorted by group, every segment padded to a multiple of 64 cells (padding = zeros)
     double *Dcol = nullptr;        // [Cp][Epad]   a cell's E-genes contiguous       (M-step statistics kernel)
     double *Dblk = nullptr;        // [nblk][E][64] 64 cells contiguous per E-gene   (E-step kernel)
     int32_t *orig = nullptr;       // [Cp] original column of a sorted cell, -1 for padding
     int32_t *pos = nullptr;        // [C]  sorted position of an original column
-    int32_t *blk_seg = nullptr;    // [nblk] 0-based S-gene of each 64-cell block
+    int32_t *blk_seg = nullptr;    // [nblk] group of each 64-cell block
     std::vector<int32_t> h_pos, h_orig, h_blk_seg;
-    std::vector<int32_t> seg_start;   // [S+1] sorted/padded start of each segment
+    std::vector<int32_t> seg_start;   // [G+1] sorted/padded start of each segment
     // M-step statistics chunking: chunk j covers sorted cells [chunk_cp0[j], +chunk_n[j]) of one segment
     int chunk_cells = 0, nchunk = 0;
     int32_t *chunk_cp0 = nullptr, *chunk_n = nullptr, *chunk_seg = nullptr;
-    int32_t *seg_chunk0 = nullptr;   // [S+1] first chunk of each segment
+    int32_t *seg_chunk0 = nullptr;   // [G+1] first chunk of each segment
     std::vector<int32_t> h_seg_chunk0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
@@ -181,6 +191,11 @@ int launch_build_masks(const mnemcu_ctx *cx, const uint32_t *clo, const int32_t 
 // M-step statistics: R[m][s][e] = sum_{cp in segment s} Dcol[cp][e] * gam[m][cp]; gam == nullptr: weights 1.
 int launch_mstats(const mnemcu_ctx *cx, const double *gam, int M, double *partial, double *R, cudaStream_t st);
 size_t mstats_partial_elems(const mnemcu_ctx *cx, int M);
+// Rho path only (ctx->multi): per-group sums Rg[m][g][e] from the chunk partials of the last launch_mstats, and the
+// theta-free argmax over them (null column last)
+int launch_mstats_groups(const mnemcu_ctx *cx, const double *partial, int M, double *Rg, cudaStream_t st);
+int launch_theta_groups(const mnemcu_ctx *cx, const double *Rg, int M, const uint32_t *clo_cols, int32_t *theta,
+                        cudaStream_t st);
 // host layout k x C (column-major, original cell order)  <->  internal [k][Cp] (sorted, padded with 0)
 int launch_L_to_internal(const mnemcu_ctx *cx, const double *L_host_dev, int k, double *L_int, cudaStream_t st);
 int launch_L_from_internal(const mnemcu_ctx *cx, const double *L_int, int k, double *L_host_dev, cudaStream_t st);

@@ -92,11 +92,11 @@ __global__ void gather_cols_kernel(const double *__restrict__ Dcol, int E, int E
     slab[(size_t)cl * E + e] = Dcol[(size_t)pos[c0 + cl] * Epad + e];
 }
 
-static int ctx_layout(mnemcu_ctx *cx, int E, int C, const int32_t *pert, int S, int device)
+// cellmask[c]: set of knocked-down S-genes of cell c (bit s); exactly one bit for ordinary data
+static int ctx_layout(mnemcu_ctx *cx, int E, int C, const std::vector<uint32_t> &cellmask, int S, int device)
 {
     MN_ARG(E >= 1 && C >= 1, "E and C must be positive");
     MN_ARG(S >= 1 && S <= MNEMCU_MAX_S, "S must be in 1..32");
-    MN_ARG(pert != nullptr, "pert is NULL");
     int ndev = 0;
     MN_CU(cudaGetDeviceCount(&ndev));
     MN_ARG(device >= 0 && device < ndev, "no such CUDA device");
@@ -109,32 +109,69 @@ static int ctx_layout(mnemcu_ctx *cx, int E, int C, const int32_t *pert, int S, 
     cx->Epad = E + (E & 1);
     cx->C = C;
     cx->S = S;
-    std::vector<int64_t> cnt(S, 0);
-    for (int c = 0; c < C; ++c) {
-        if (pert[c] < 1 || pert[c] > S) return set_err(MNEMCU_ERR_ARG, "pert[%d] = %d outside 1..%d", c, pert[c], S);
-        cnt[pert[c] - 1]++;
+    // groups: the S single knock-downs first, then the other distinct sets in ascending mask order
+    cx->h_gmask.clear();
+    for (int s = 0; s < S; ++s) cx->h_gmask.push_back(1u << s);
+    {
+        std::vector<uint32_t> extra;
+        for (int c = 0; c < C; ++c)
+            if (__builtin_popcount(cellmask[c]) != 1) extra.push_back(cellmask[c]);
+        std::sort(extra.begin(), extra.end());
+        extra.erase(std::unique(extra.begin(), extra.end()), extra.end());
+        cx->h_gmask.insert(cx->h_gmask.end(), extra.begin(), extra.end());
+        cx->multi = !extra.empty();
     }
-    cx->seg_start.assign(S + 1, 0);
+    const int G = cx->G = (int)cx->h_gmask.size();
+    auto group_of = [&](uint32_t m) -> int {
+        if (__builtin_popcount(m) == 1) return __builtin_ctz(m);
+        return (int)(std::lower_bound(cx->h_gmask.begin() + S, cx->h_gmask.end(), m) - cx->h_gmask.begin());
+    };
+    std::vector<int32_t> cell_group(C);
+    std::vector<int64_t> cnt(G, 0);
+    for (int c = 0; c < C; ++c) {
+        cell_group[c] = group_of(cellmask[c]);
+        cnt[cell_group[c]]++;
+    }
+    cx->seg_start.assign(G + 1, 0);
     int64_t cp = 0;
-    for (int s = 0; s < S; ++s) {
-        cx->seg_start[s] = (int32_t)cp;
-        cp += (cnt[s] + kBlkCells - 1) / kBlkCells * kBlkCells;
+    for (int g = 0; g < G; ++g) {
+        cx->seg_start[g] = (int32_t)cp;
+        cp += (cnt[g] + kBlkCells - 1) / kBlkCells * kBlkCells;
     }
     MN_ARG(cp < (int64_t)1 << 31, "too many cells");
-    cx->seg_start[S] = (int32_t)cp;
+    cx->seg_start[G] = (int32_t)cp;
     cx->Cp = (int)cp;
     cx->nblk = cx->Cp / kBlkCells;
     cx->h_pos.assign(C, 0);
     cx->h_orig.assign(std::max(cx->Cp, 1), -1);
     std::vector<int32_t> fill(cx->seg_start.begin(), cx->seg_start.end() - 1);
     for (int c = 0; c < C; ++c) {   // stable: original order inside a segment
-        const int p = fill[pert[c] - 1]++;
+        const int p = fill[cell_group[c]]++;
         cx->h_pos[c] = p;
         cx->h_orig[p] = c;
     }
     cx->h_blk_seg.assign(std::max(cx->nblk, 1), 0);
-    for (int s = 0; s < S; ++s)
-        for (int b = cx->seg_start[s] / kBlkCells; b < cx->seg_start[s + 1] / kBlkCells; ++b) cx->h_blk_seg[b] = s;
+    for (int g = 0; g < G; ++g)
+        for (int b = cx->seg_start[g] / kBlkCells; b < cx->seg_start[g + 1] / kBlkCells; ++b) cx->h_blk_seg[b] = g;
+    {   // device tables of the groups
+        std::vector<double> gw(G);
+        for (int g = 0; g < G; ++g) gw[g] = 1.0 / std::max(1, __builtin_popcount(cx->h_gmask[g]));
+        std::vector<int32_t> ptr(S + 1, 0), idx;
+        for (int s = 0; s < S; ++s) {
+            ptr[s] = (int32_t)idx.size();
+            for (int g = 0; g < G; ++g)
+                if ((cx->h_gmask[g] >> s) & 1u) idx.push_back(g);
+        }
+        ptr[S] = (int32_t)idx.size();
+        MN_CU(cudaMalloc((void **)&cx->gmask, sizeof(uint32_t) * G));
+        MN_CU(cudaMalloc((void **)&cx->gweight, sizeof(double) * G));
+        MN_CU(cudaMalloc((void **)&cx->sg_ptr, sizeof(int32_t) * (S + 1)));
+        MN_CU(cudaMalloc((void **)&cx->sg_idx, sizeof(int32_t) * std::max<size_t>(1, idx.size())));
+        MN_CU(cudaMemcpy(cx->gmask, cx->h_gmask.data(), sizeof(uint32_t) * G, cudaMemcpyHostToDevice));
+        MN_CU(cudaMemcpy(cx->gweight, gw.data(), sizeof(double) * G, cudaMemcpyHostToDevice));
+        MN_CU(cudaMemcpy(cx->sg_ptr, ptr.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice));
+        MN_CU(cudaMemcpy(cx->sg_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice));
+    }
     // chunks for the M-step statistics kernel: aim at >= 4 CTAs per SM, chunk a multiple of 64 cells
     {
         const int pairs = cx->Epad / 2;
@@ -144,8 +181,8 @@ static int ctx_layout(mnemcu_ctx *cx, int E, int C, const int32_t *pert, int S, 
         cc = std::max<int64_t>(kBlkCells, std::min<int64_t>(4096, cc / kBlkCells * kBlkCells));
         cx->chunk_cells = (int)cc;
         std::vector<int32_t> cp0, cn, cs;
-        cx->h_seg_chunk0.assign(S + 1, 0);
-        for (int s = 0; s < S; ++s) {
+        cx->h_seg_chunk0.assign(G + 1, 0);
+        for (int s = 0; s < G; ++s) {
             cx->h_seg_chunk0[s] = (int32_t)cp0.size();
             for (int p = cx->seg_start[s]; p < cx->seg_start[s + 1]; p += cx->chunk_cells) {
                 cp0.push_back(p);
@@ -153,16 +190,16 @@ static int ctx_layout(mnemcu_ctx *cx, int E, int C, const int32_t *pert, int S, 
                 cs.push_back(s);
             }
         }
-        cx->h_seg_chunk0[S] = (int32_t)cp0.size();
+        cx->h_seg_chunk0[G] = (int32_t)cp0.size();
         cx->nchunk = (int)cp0.size();
         MN_CU(cudaMalloc((void **)&cx->chunk_cp0, sizeof(int32_t) * std::max(1, cx->nchunk)));
         MN_CU(cudaMalloc((void **)&cx->chunk_n, sizeof(int32_t) * std::max(1, cx->nchunk)));
         MN_CU(cudaMalloc((void **)&cx->chunk_seg, sizeof(int32_t) * std::max(1, cx->nchunk)));
-        MN_CU(cudaMalloc((void **)&cx->seg_chunk0, sizeof(int32_t) * (S + 1)));
+        MN_CU(cudaMalloc((void **)&cx->seg_chunk0, sizeof(int32_t) * (G + 1)));
         MN_CU(cudaMemcpy(cx->chunk_cp0, cp0.data(), sizeof(int32_t) * cx->nchunk, cudaMemcpyHostToDevice));
         MN_CU(cudaMemcpy(cx->chunk_n, cn.data(), sizeof(int32_t) * cx->nchunk, cudaMemcpyHostToDevice));
         MN_CU(cudaMemcpy(cx->chunk_seg, cs.data(), sizeof(int32_t) * cx->nchunk, cudaMemcpyHostToDevice));
-        MN_CU(cudaMemcpy(cx->seg_chunk0, cx->h_seg_chunk0.data(), sizeof(int32_t) * (S + 1), cudaMemcpyHostToDevice));
+        MN_CU(cudaMemcpy(cx->seg_chunk0, cx->h_seg_chunk0.data(), sizeof(int32_t) * (G + 1), cudaMemcpyHostToDevice));
     }
     MN_CU(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
     MN_CU(cudaMalloc((void **)&cx->pos, sizeof(int32_t) * C));
@@ -195,6 +232,7 @@ static void ctx_free(mnemcu_ctx *cx)
     cudaSetDevice(cx->device);
     cudaFree(cx->Dcol); cudaFree(cx->Dblk); cudaFree(cx->orig); cudaFree(cx->pos); cudaFree(cx->blk_seg);
     cudaFree(cx->chunk_cp0); cudaFree(cx->chunk_n); cudaFree(cx->chunk_seg); cudaFree(cx->seg_chunk0);
+    cudaFree(cx->gmask); cudaFree(cx->gweight); cudaFree(cx->sg_ptr); cudaFree(cx->sg_idx);
     if (cx->stream) cudaStreamDestroy(cx->stream);
     delete cx;
 }
@@ -203,13 +241,23 @@ static void ctx_free(mnemcu_ctx *cx)
 
 using namespace mn;
 
-extern "C" int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *pert, int S, int device,
-                                 mnemcu_ctx **out)
+static int pert_to_masks(const int32_t *pert, int C, int S, std::vector<uint32_t> &out)
 {
-    MN_ARG(out != nullptr && D != nullptr, "NULL pointer");
-    *out = nullptr;
+    MN_ARG(pert != nullptr, "pert is NULL");
+    MN_ARG(S >= 1 && S <= MNEMCU_MAX_S && C >= 1, "bad S / C");
+    out.resize(C);
+    for (int c = 0; c < C; ++c) {
+        if (pert[c] < 1 || pert[c] > S) return set_err(MNEMCU_ERR_ARG, "pert[%d] = %d outside 1..%d", c, pert[c], S);
+        out[c] = 1u << (pert[c] - 1);
+    }
+    return 0;
+}
+
+static int ctx_upload(const double *D, int E, int C, const std::vector<uint32_t> &cellmask, int S, int device,
+                      mnemcu_ctx **out)
+{
     mnemcu_ctx *cx = new mnemcu_ctx();
-    int rc = ctx_layout(cx, E, C, pert, S, device);
+    int rc = ctx_layout(cx, E, C, cellmask, S, device);
     if (rc) { ctx_free(cx); return rc; }
     // zero the padding, then stream D up in slabs of original columns through two staging buffers
     cudaError_t ce = cudaMemsetAsync(cx->Dcol, 0, sizeof(double) * (size_t)cx->Cp * cx->Epad, cx->stream);
@@ -243,6 +291,29 @@ extern "C" int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *p
     return 0;
 }
 
+extern "C" int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *pert, int S, int device,
+                                 mnemcu_ctx **out)
+{
+    MN_ARG(out != nullptr && D != nullptr, "NULL pointer");
+    *out = nullptr;
+    std::vector<uint32_t> cm;
+    MN_TRY(pert_to_masks(pert, C, S, cm));
+    return ctx_upload(D, E, C, cm, S, device, out);
+}
+
+extern "C" int mnemcu_ctx_create_rho(const double *D, int E, int C, const double *Rho, int S, int device,
+                                     mnemcu_ctx **out)
+{
+    MN_ARG(out != nullptr && D != nullptr && Rho != nullptr, "NULL pointer");
+    MN_ARG(S >= 1 && S <= MNEMCU_MAX_S && C >= 1, "bad S / C");
+    *out = nullptr;
+    std::vector<uint32_t> cm(C, 0u);
+    for (int c = 0; c < C; ++c)
+        for (int s = 0; s < S; ++s)
+            if (Rho[(size_t)c * S + s] != 0.0) cm[c] |= 1u << s;
+    return ctx_upload(D, E, C, cm, S, device, out);
+}
+
 extern "C" int mnemcu_ctx_create_synthetic(int E, int C, const int32_t *pert, int S, const uint8_t *comp, int n_comp,
                                            const uint8_t *phi_true, const int32_t *theta_true, uint64_t seed,
                                            int device, mnemcu_ctx **out)
@@ -252,8 +323,10 @@ extern "C" int mnemcu_ctx_create_synthetic(int E, int C, const int32_t *pert, in
     *out = nullptr;
     for (int c = 0; c < C; ++c)
         if (comp[c] >= n_comp) return set_err(MNEMCU_ERR_ARG, "comp[%d] = %d outside 0..%d", c, comp[c], n_comp - 1);
+    std::vector<uint32_t> cm;
+    MN_TRY(pert_to_masks(pert, C, S, cm));
     mnemcu_ctx *cx = new mnemcu_ctx();
-    int rc = ctx_layout(cx, E, C, pert, S, device);
+    int rc = ctx_layout(cx, E, C, cm, S, device);
     if (rc) { ctx_free(cx); return rc; }
     auto body = [&]() -> int {
         DevBuf<int32_t> d_pert, d_theta;

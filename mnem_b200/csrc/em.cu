@@ -103,7 +103,7 @@ struct Engine {
     double logtype = 2.0;
     cudaStream_t st = nullptr;
     std::vector<Slot> slots;
-    DevBuf<double> Lbuf, gam, R, partial, mixscratch, d_mw, d_mwtmp, d_ll, Lstage;
+    DevBuf<double> Lbuf, gam, R, Rg, partial, mixscratch, d_mw, d_mwtmp, d_ll, Lstage;
     DevBuf<int32_t> d_flag, d_theta, d_theta_tmp, d_theta_best, d_edge, d_thch, d_pairs, d_have_theta;
     DevBuf<uint32_t> d_res1, d_clo, d_clo_cols, d_start, maskT, d_best_rows;
     DevBuf<unsigned long long> d_counters;
@@ -163,7 +163,8 @@ struct Engine {
         MN_TRY(d_res1.alloc((size_t)M * 32, true)); MN_TRY(d_clo.alloc((size_t)M * 32, true));
         MN_TRY(d_clo_cols.alloc((size_t)M * 32, true)); MN_TRY(d_start.alloc((size_t)2 * M * 32, true));
         MN_TRY(d_best_rows.alloc((size_t)M * 32, true));
-        MN_TRY(maskT.alloc((size_t)cx->S * cx->E, true));
+        MN_TRY(maskT.alloc((size_t)cx->G * cx->E, true));
+        if (cx->multi) MN_TRY(Rg.alloc((size_t)M * cx->G * cx->E, true));
         MN_TRY(d_counters.alloc(2, true));
         MN_TRY(d_Rptr.alloc(M));
         MN_TRY(d_u8.alloc((size_t)M * cx->S * cx->S));
@@ -261,7 +262,12 @@ struct Engine {
     int op_theta_init(const std::vector<int> &list)
     {
         if (list.empty()) return 0;
-        MN_TRY(launch_theta(d_Rptr.p, M, cx->E, cx->S, d_clo_cols.p, 1, d_theta_tmp.p, nullptr, st));
+        if (cx->multi) {
+            MN_TRY(launch_mstats_groups(cx, partial.p, M, Rg.p, st));
+            MN_TRY(launch_theta_groups(cx, Rg.p, M, d_clo_cols.p, d_theta_tmp.p, st));
+        } else {
+            MN_TRY(launch_theta(d_Rptr.p, M, cx->E, cx->S, d_clo_cols.p, 1, d_theta_tmp.p, nullptr, st));
+        }
         for (int b : list)
             MN_CU(cudaMemcpyAsync(d_theta.p + (size_t)b * k * cx->E, d_theta_tmp.p + (size_t)b * k * cx->E,
                                   sizeof(int32_t) * (size_t)k * cx->E, cudaMemcpyDeviceToDevice, st));

@@ -364,10 +364,32 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     const double *R = Rptr[q];
     const uint32_t *cJ = cand_J + (size_t)q * maxc;
     const uint16_t *cI = cand_id + (size_t)q * maxc * 32;
+    // Work items of a tile, handed out by a shared counter so that the 16 warps finish together (an insertion target v
+    // costs |D_v| rounds of 32 look-ups, anything from 1 to S): first the insertion targets, most expensive first, then
+    // the reversal / deletion candidates in chunks of kRestChunk.
+    __shared__ int s_vlist[32];
+    __shared__ int s_nv;
+    __shared__ int s_ctr[2];
+    constexpr int kRestChunk = 4;
+    if (warp == 0) {
+        const bool valid = zmask != 0u;
+        int cost = 0;
+        for (int j = 0; j < S; ++j) cost += (__shfl_sync(kFull, pcol, j) >> lane) & 1u;     // |D_lane| = ones in row `lane`
+        int rank = 0;
+        for (int o = 0; o < 32; ++o) {
+            const int oc = __shfl_sync(kFull, cost, o);
+            const bool ov = __shfl_sync(kFull, (int)valid, o) != 0;
+            if (ov && (oc > cost || (oc == cost && o < lane))) ++rank;
+        }
+        if (valid) s_vlist[rank] = lane;
+        const unsigned vm = __ballot_sync(kFull, valid);
+        if (lane == 0) { s_nv = ni > 0 ? __popc(vm) : 0; s_ctr[0] = 0; s_ctr[1] = 0; }
+    }
     const int nrest = nc - ni;
-    const int per = (nrest + NW - 1) / NW;                              // contiguous reversal/deletion candidates per warp
-    const int cbeg = ni + warp * per, cend = min(nc, cbeg + per);
+    const int nchunks = (nrest + kRestChunk - 1) / kRestChunk;
     __syncthreads();
+    const int nv = s_nv;
+    int parity = 0;
     const int ntiles = (E + kDictRows - 1) / kDictRows;
     for (int tile = g; tile < ntiles; tile += G) {
         const int row = tile * kDictRows + lane;
@@ -420,16 +442,22 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
             }
             return A;
         };
-        // (2) insertions
-        if (ni > 0) {
-            for (int v = warp; v < S; v += NW) {
+        if (tid == 0) s_ctr[parity ^ 1] = 0;                  // next tile's counter (idle until after the barrier below)
+        while (true) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&s_ctr[parity], 1);
+            item = __shfl_sync(kFull, item, 0);
+            if (item >= nv + nchunks) break;
+            if (item < nv) {
+                // (2) insertions into v
+                const int v = s_vlist[item];
                 const uint32_t zm = __shfl_sync(kFull, zmask, v);
-                if (zm == 0u) continue;
                 const uint32_t Dv = __ballot_sync(kFull, (pcol >> v) & 1u);      // columns j with P[v, j] = 1 (diag included)
                 const double A = unchanged_max(Dv);
+                const double A0 = A > 0.0 ? A : 0.0;                 // max(0, unchanged columns): the floor of every candidate
                 double B[32];
 #pragma unroll
-                for (int u = 0; u < 32; ++u) B[u] = -INFINITY;
+                for (int u = 0; u < 32; ++u) B[u] = A0;
                 uint32_t m = Dv;
                 while (m) {
                     const int j = __ffs(m) - 1;
@@ -437,9 +465,9 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                     // ids of col_j | col_u for all u: one 64-byte row, fetched as uniform 16-byte loads; the look-ups
                     // are unconditional (also for u that are no candidates) so that they pipeline instead of
                     // serialising behind 30 uniform branches
-                    uint32_t ofs[SP];
+                    uint32_t ofs[(SP + 3) / 4 * 4];
 #pragma unroll
-                    for (int w4 = 0; w4 < SP / 4; ++w4) {
+                    for (int w4 = 0; w4 < (SP + 3) / 4; ++w4) {
                         const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + w4 * 4);
                         ofs[w4 * 4 + 0] = x.x; ofs[w4 * 4 + 1] = x.y; ofs[w4 * 4 + 2] = x.z; ofs[w4 * 4 + 3] = x.w;
                     }
@@ -451,11 +479,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
-                    double x = B[u] > A ? B[u] : A;
-                    x = x > 0.0 ? x : 0.0;
-                    B[u] = (u < SP && ((zm >> u) & 1u)) ? x : 0.0;
-                }
+                for (int u = 0; u < 32; ++u) B[u] = (u < SP && ((zm >> u) & 1u)) ? B[u] : 0.0;
                 // transposed butterfly: afterwards lane l holds the sum over the 32 rows of B[l]
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) {
@@ -469,10 +493,10 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                 }
                 const int off = __shfl_sync(kFull, offv, v);
                 if ((zm >> lane) & 1u) ptile[off + __popc(zm & ((1u << lane) - 1u))] = B[0];
+                continue;
             }
-        }
-        // (3) reversals and deletions (and the single closure "candidate" of the initial score)
-        {
+            // (3) reversals and deletions (and the single closure "candidate" of the initial score)
+            const int cbeg = ni + (item - nv) * kRestChunk, cend = min(nc, cbeg + kRestChunk);
             uint32_t lastJ = 0u;
             double A = -INFINITY;
             bool haveA = false;
@@ -497,6 +521,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
                 if (lane == 0) ptile[c] = val;
             }
         }
+        parity ^= 1;
         __syncthreads();
     }
 }
@@ -751,6 +776,8 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
     else if (S <= 24) MN_SCORE(24);
+    else if (S <= 28) MN_SCORE(28);
+    else if (S <= 30) MN_SCORE(30);
     else MN_SCORE(32);
 #undef MN_SCORE
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
@@ -789,6 +816,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
     }
     auto body = [&]() -> int {

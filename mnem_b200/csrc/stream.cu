@@ -131,26 +131,33 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
     }
 }
 
-// maskT[s][e]: bit m = phi_m closure [s, theta_m(e)]  (adj1[, subtopo] of R/mnems_low.r:621-624, theta 0 -> null column)
+// maskT[g][e]: bit m = adj1_m[cells of group g, theta_m(e)]  (adj1[, subtopo] of R/mnems_low.r:621-624, theta 0 -> null
+// column), where adj1 = min(1, t(Rho) %*% closure(phi_m)) (:613-616): the OR of the closure rows of the group's S-genes.
+// For single knock-downs the group is one S-gene and this is phi_m closure [s, theta_m(e)].
 __global__ void build_masks_kernel(const uint32_t *__restrict__ clo, const int32_t *__restrict__ theta, int M, int E,
-                                   int S, uint32_t *__restrict__ maskT)
+                                   int S, const uint32_t *__restrict__ gmask, uint32_t *__restrict__ maskT)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
+    const int g = blockIdx.y;
     if (e >= E) return;
+    const uint32_t gm = gmask[g];
     uint32_t w = 0;
     for (int m = 0; m < M; ++m) {
         const int t = theta[(size_t)m * E + e];
-        if (t > 0 && t <= S && ((clo[m * 32 + s] >> (t - 1)) & 1u)) w |= 1u << m;
+        if (t > 0 && t <= S) {
+            uint32_t hit = 0;
+            for (uint32_t r = gm; r; r &= r - 1) hit |= clo[m * 32 + (__ffs(r) - 1)];
+            if ((hit >> (t - 1)) & 1u) w |= 1u << m;
+        }
     }
-    maskT[(size_t)s * E + e] = w;
+    maskT[(size_t)g * E + e] = w;
 }
 
 int launch_build_masks(const mnemcu_ctx *cx, const uint32_t *clo, const int32_t *theta, int M, uint32_t *maskT,
                        cudaStream_t st)
 {
-    dim3 grid((cx->E + 127) / 128, cx->S);
-    MN_LAUNCH(build_masks_kernel, grid, 128, 0, st, clo, theta, M, cx->E, cx->S, maskT);
+    dim3 grid((cx->E + 127) / 128, cx->G);
+    MN_LAUNCH(build_masks_kernel, grid, 128, 0, st, clo, theta, M, cx->E, cx->S, cx->gmask, maskT);
     return 0;
 }
 
@@ -257,16 +264,82 @@ __global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict
     }
 }
 
-// R[m][s][e] (E x S column-major per pair) = sum over the chunks of segment s, ascending
+// R[m][s][e] (E x S column-major per pair) = sum over the groups g that contain S-gene s (ascending) of
+// w_g * (sum over the chunks of segment g, ascending), w_g = 1 / |g|: (D diag gamma) %*% t(Rho') with the columns of
+// Rho' normalised to sum 1, R/mnems_low.r:896-904.  Single knock-down data: one group per S-gene, w = 1, and the
+// result is the plain ascending chunk sum (0 + x * 1 is exact).
 __global__ void mstats_reduce_kernel(const double *__restrict__ partial, int M, int E, int Epad, int S,
-                                     const int32_t *__restrict__ seg_chunk0, double *__restrict__ R)
+                                     const int32_t *__restrict__ seg_chunk0, const int32_t *__restrict__ sg_ptr,
+                                     const int32_t *__restrict__ sg_idx, const double *__restrict__ gweight,
+                                     double *__restrict__ R)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y, m = blockIdx.z;
     if (e >= E) return;
+    double tot = 0.0;
+    for (int i = sg_ptr[s]; i < sg_ptr[s + 1]; ++i) {
+        const int g = sg_idx[i];
+        double acc = 0.0;
+        for (int ch = seg_chunk0[g]; ch < seg_chunk0[g + 1]; ++ch) acc += partial[((size_t)ch * M + m) * Epad + e];
+        tot += acc * gweight[g];
+    }
+    R[((size_t)m * S + s) * E + e] = tot;
+}
+
+// Rg[m][g][e] = sum over the chunks of segment g (un-normalised): the per-group collapsed data the theta-free E-step of
+// the Rho path needs, because min(1, t(Rho) %*% adj1) is an OR over a cell's S-genes, not a sum.
+__global__ void mstats_groups_kernel(const double *__restrict__ partial, int M, int E, int Epad, int G,
+                                     const int32_t *__restrict__ seg_chunk0, double *__restrict__ Rg)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y, m = blockIdx.z;
+    if (e >= E) return;
     double acc = 0.0;
-    for (int ch = seg_chunk0[s]; ch < seg_chunk0[s + 1]; ++ch) acc += partial[((size_t)ch * M + m) * Epad + e];
-    R[((size_t)m * S + s) * E + e] = acc;
+    for (int ch = seg_chunk0[g]; ch < seg_chunk0[g + 1]; ++ch) acc += partial[((size_t)ch * M + m) * Epad + e];
+    Rg[((size_t)m * G + g) * E + e] = acc;
+}
+
+// theta-free E-step on the Rho path, R/mnems_low.r:617-619: theta[m][e] = first argmax_j over
+// ((D diag gamma_m) %*% cbind(adj1, 0))[e, j], adj1[c, j] = OR_{s in group(c)} closure_m[s, j]; the cells of a group
+// share their row of adj1, so W[e, j] = sum_{g : gmask_g & col_j != 0} Rg[m][g][e] (ascending g).  Null column LAST.
+__global__ void __launch_bounds__(128) theta_groups_kernel(const double *__restrict__ Rg, int E, int S, int G,
+                                                           const uint32_t *__restrict__ gmask,
+                                                           const uint32_t *__restrict__ clo_cols,
+                                                           int32_t *__restrict__ theta)
+{
+    __shared__ uint32_t s_col[32];
+    const int m = blockIdx.y, tid = threadIdx.x;
+    if (tid < 32) s_col[tid] = clo_cols[m * 32 + tid];
+    __syncthreads();
+    const int e = blockIdx.x * blockDim.x + tid;
+    if (e >= E) return;
+    const double *r = Rg + (size_t)m * G * E + e;
+    double best = -INFINITY;
+    int arg = 0;
+    for (int j = 0; j < S; ++j) {
+        const uint32_t col = s_col[j];
+        double w = 0.0;
+        for (int g = 0; g < G; ++g)
+            if (gmask[g] & col) w += r[(size_t)g * E];
+        if (w > best) { best = w; arg = j + 1; }
+    }
+    if (0.0 > best) arg = 0;
+    theta[(size_t)m * E + e] = arg;
+}
+
+int launch_mstats_groups(const mnemcu_ctx *cx, const double *partial, int M, double *Rg, cudaStream_t st)
+{
+    dim3 grid((cx->E + 127) / 128, cx->G, M);
+    MN_LAUNCH(mstats_groups_kernel, grid, 128, 0, st, partial, M, cx->E, cx->Epad, cx->G, cx->seg_chunk0, Rg);
+    return 0;
+}
+
+int launch_theta_groups(const mnemcu_ctx *cx, const double *Rg, int M, const uint32_t *clo_cols, int32_t *theta,
+                        cudaStream_t st)
+{
+    dim3 grid((cx->E + 127) / 128, M);
+    MN_LAUNCH(theta_groups_kernel, grid, 128, 0, st, Rg, cx->E, cx->S, cx->G, cx->gmask, clo_cols, theta);
+    return 0;
 }
 
 size_t mstats_partial_elems(const mnemcu_ctx *cx, int M) { return (size_t)cx->nchunk * M * cx->Epad; }
@@ -305,7 +378,8 @@ int launch_mstats(const mnemcu_ctx *cx, const double *gam, int M, double *partia
     }
     if (rc) return rc;
     dim3 grid((cx->E + 127) / 128, cx->S, M);
-    MN_LAUNCH(mstats_reduce_kernel, grid, 128, 0, st, partial, M, cx->E, cx->Epad, cx->S, cx->seg_chunk0, R);
+    MN_LAUNCH(mstats_reduce_kernel, grid, 128, 0, st, partial, M, cx->E, cx->Epad, cx->S, cx->seg_chunk0, cx->sg_ptr,
+              cx->sg_idx, cx->gweight, R);
     return 0;
 }
 

@@ -147,3 +147,45 @@ def init_phi(S, k, starts, seed=0):
             np.fill_diagonal(a, 0)
             out[s, i] = a
     return out
+
+
+def make_multi(S=5, Egenes=4, C=600, mw=(0.4, 0.6), multi=(0.25, 0.1), uninform=0, seed=0):
+    """Small simData(multi = c(p2, p3))-style problem with double / triple knock-downs (R/mnems.r:3099-3132):
+    a fraction p2 of the cells carries two knocked-down S-genes, p3 three; a cell shows the effect of an E-gene when
+    ANY of its S-genes is an ancestor-or-self of the E-gene's attachment (the OR of R/mnems_low.r:613-616).
+    Host-side NumPy only (tests): returns dict(D, labels, Rho, masks, pert_enc, S, E, C, k, phi_true, theta_true)
+    where pert_enc is the oracle's encoding (s for a single knock-down, -mask otherwise)."""
+    rng = np.random.default_rng(seed)
+    k = len(mw)
+    E = S * Egenes + uninform
+    phi = np.zeros((k, S, S), dtype=np.uint8)
+    theta = np.zeros((k, E), dtype=np.int32)
+    for i in range(k):
+        a = np.triu((rng.random((S, S)) < 0.3).astype(np.uint8), 1)
+        perm = rng.permutation(S)
+        phi[i] = _closure(a[np.ix_(perm, perm)])
+        th = np.repeat(np.arange(1, S + 1, dtype=np.int32), Egenes)
+        theta[i, : S * Egenes] = th[rng.permutation(S * Egenes)]
+    comp = rng.choice(k, size=C, p=np.asarray(mw) / np.sum(mw))
+    n_ko = rng.choice([1, 2, 3], size=C, p=[1 - multi[0] - multi[1], multi[0], multi[1]])
+    masks = np.zeros(C, dtype=np.uint32)
+    labels = []
+    for c in range(C):
+        genes = np.sort(rng.choice(S, size=min(n_ko[c], S), replace=False))
+        for g in genes:
+            masks[c] |= np.uint32(1) << np.uint32(g)
+        labels.append("_".join(str(g + 1) for g in genes))
+    Rho = np.zeros((S, C))
+    for s in range(S):
+        Rho[s] = (masks >> np.uint32(s)) & 1
+    D = np.zeros((E, C))
+    for c in range(C):
+        eff = (Rho[:, c] @ phi[comp[c]]) > 0                                  # [S] which attachments are hit
+        att = theta[comp[c]]
+        hit = np.where(att > 0, eff[np.maximum(att, 1) - 1], rng.random(E) < 0.5)
+        D[:, c] = np.where(hit, 1.0, -1.0)
+    D += rng.normal(size=(E, C))
+    single = np.array([bin(int(m)).count("1") == 1 for m in masks])
+    pert_enc = np.where(single, np.log2(np.maximum(masks, 1)).astype(np.int64) + 1, -masks.astype(np.int64)).astype(np.int32)
+    return dict(D=np.asfortranarray(D), labels=labels, Rho=Rho, masks=masks, pert_enc=pert_enc, S=S, E=E, C=C, k=k,
+                phi_true=phi, theta_true=theta, comp=comp)

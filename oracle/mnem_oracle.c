@@ -21,8 +21,13 @@
  * with -DORC_ACC_DOUBLE to get the behaviour of an R built with --disable-long-double (or arm64).
  *
  * Layout: every matrix is column-major like R.  Graphs are uint8 0/1 S x S, adj[i + j*S] = 1 <=> edge
- * i -> j (parent row, child column).  theta is int32[E] in 0..S, 0 = unattached.  pert is int32[C] in 1..S
- * (single knock-down per cell; the multi-KO Rho path of R/mnems_low.r:613-616 is not restated).
+ * i -> j (parent row, child column).  theta is int32[E] in 0..S, 0 = unattached.
+ *
+ * pert is int32[C]: a value in 1..S is the single S-gene knocked down in the cell; a value <= 0 is minus the
+ * bit mask of the knocked-down S-genes (bit s-1 = S-gene s; 0 = none), i.e. a column of Rho = getRho(D)
+ * (R/mnems_low.r:308-324) for a multi-knock-down cell ("1_3").  The Rho path then follows the reference:
+ * effect rows are min(1, t(Rho) %*% adj1) (R/mnems_low.r:613-616, R/mnems.r:433-435) and doMean divides the
+ * contribution of a cell with n > 1 knock-downs by n (R/mnems_low.r:896-904).  Masks need S <= 31.
  */
 #include <math.h>
 #include <stdint.h>
@@ -39,6 +44,16 @@ typedef long double acc_t;
 #endif
 
 #define ORC_MAXS 64
+
+/* set of knocked-down S-genes of a cell as a bit mask (see the note on `pert` above) */
+static inline uint32_t pert_mask(int32_t p) { return p > 0 ? 1u << (p - 1) : (uint32_t)(-(int64_t)p); }
+/* adj1[c, j] of R/mnems_low.r:613-616: min(1, sum_s Rho[s,c] * A[s,j]) */
+static inline int cell_effect(const uint8_t *A, int S, uint32_t pm, int j)
+{
+    for (int s = 0; s < S; s++)
+        if (((pm >> s) & 1u) && A[s + j * S]) return 1;
+    return 0;
+}
 
 /* ------------------------------------------------------------------------------------------------ */
 /* src/mm.cpp                                                                                       */
@@ -263,13 +278,25 @@ void orc_do_mean(const double *D, int E, int C, const int32_t *pert, int S, cons
     memset(R, 0, sizeof(double) * (size_t)E * S);
     for (int c = 0; c < C; c++) {
         if (w && w[c] == 0.0) continue;
-        double *r = R + (size_t)(pert[c] - 1) * E;
         const double *d = D + (size_t)c * E;
-        if (w) {
-            double wc = w[c];
-            for (int e = 0; e < E; e++) r[e] += d[e] * wc;   /* built with -ffp-contract=off: mul then add */
-        } else {
-            for (int e = 0; e < E; e++) r[e] += d[e];
+        const uint32_t pm = pert_mask(pert[c]);
+        const int n = __builtin_popcount(pm);
+        if (n == 1) {
+            double *r = R + (size_t)__builtin_ctz(pm) * E;
+            if (w) {
+                double wc = w[c];
+                for (int e = 0; e < E; e++) r[e] += d[e] * wc;   /* built with -ffp-contract=off: mul then add */
+            } else {
+                for (int e = 0; e < E; e++) r[e] += d[e];
+            }
+        } else if (n > 1) {
+            /* Rho column normalised to sum 1 (:897-902): each knocked-down S-gene receives (D*w) * (1/n) */
+            const double rho = 1.0 / n;
+            for (int s = 0; s < S; s++)
+                if ((pm >> s) & 1u) {
+                    double *r = R + (size_t)s * E;
+                    for (int e = 0; e < E; e++) r[e] += (w ? d[e] * w[c] : d[e]) * rho;
+                }
         }
     }
 }
@@ -513,9 +540,9 @@ double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, 
                     for (int c = 0; c < C; c++) {
                         double g = post[i + (size_t)c * k];
                         const double *d = D + (size_t)c * E;
-                        int p = pert[c] - 1;
+                        const uint32_t pm = pert_mask(pert[c]);
                         for (int j = 0; j < S; j++)
-                            if (A[p + j * S]) {
+                            if (cell_effect(A, S, pm, j)) {
                                 double *w = Wtmp + (size_t)j * E;
                                 for (int e = 0; e < E; e++) w[e] += d[e] * g;
                             }
@@ -527,11 +554,13 @@ double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, 
                 /* :624,631 L[i,c] = colSums(data * t(adj1[, subtopo])) : long-double, ascending e */
                 for (int c = 0; c < C; c++) {
                     const double *d = D + (size_t)c * E;
-                    int p = pert[c] - 1;
+                    const uint32_t pm = pert_mask(pert[c]);
+                    uint8_t eff[ORC_MAXS];
+                    for (int j = 0; j < S; j++) eff[j] = (uint8_t)cell_effect(A, S, pm, j);
                     acc_t s = 0;
                     for (int e = 0; e < E; e++) {
                         int t = thi[e];
-                        if (t <= S && A[p + (t - 1) * S]) s += d[e];
+                        if (t <= S && eff[t - 1]) s += d[e];
                     }
                     probs0[i + (size_t)c * k] = (double)s;
                 }

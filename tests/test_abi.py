@@ -71,5 +71,12 @@ def test_mod_data_natural_order():
     pert, S, labs = mb.mod_data(["g10", "g2", "g1", "g2", "g10"])
     assert labs == ["g1", "g2", "g10"] and S == 3
     assert pert.tolist() == [3, 2, 1, 2, 3]
-    with pytest.raises(NotImplementedError):
-        mb.mod_data(["1_2", "1"])
+    with pytest.raises(ValueError):
+        mb.mod_data(["1_2", "1"])                      # one integer per cell cannot express a double knock-down
+
+
+def test_get_rho_follows_getRho():
+    """getRho() R/mnems_low.r:308-324 on "_"-joined labels; S-genes in natural order."""
+    Rho, sg = mb.get_rho(["2", "10_2", "1", "10", "1_2_10"])
+    assert sg == ["1", "2", "10"]
+    assert Rho.tolist() == [[0, 0, 1, 0, 1], [1, 1, 0, 0, 1], [0, 1, 0, 1, 1]]

@@ -240,10 +240,12 @@ def test_get_probs_theta_free(S, E, Cn, k):
 
 
 # ---- the EM loop -------------------------------------------------------------------------------------------------
-def check_em(sim, D, init, complete, batch=0):
+def check_em(sim, D, init, complete, batch=0, gpu_pert=None):
+    """gpu_pert: what the CUDA side is given when it differs from the oracle's encoding sim["pert"] (the Rho path:
+    "_"-joined labels for the GPU, -mask integers for the oracle)."""
     refs = [orc.mnem_em(D, sim["pert"], sim["S"], init, complete=complete, nthreads=8, noise_mode=m) for m in (0, 1, 2)]
     ref = refs[0]
-    res = mb.mnem(D, sim["pert"], phi=init, complete=complete, batch=batch)
+    res = mb.mnem(D, sim["pert"] if gpu_pert is None else gpu_pert, phi=init, complete=complete, batch=batch)
     starts = init.shape[0]
     # Decision margins (SURVEY section 7): a greedy / restart decision closer than 1e-13 relative is rounding noise
     # in ANY implementation -- such a case cannot pin anything, pick another seed.
@@ -366,3 +368,70 @@ def test_bootstrap_matches_oracle_loop():
             assert r["min_margin"] > 1e-13
             acc += orc.mytc(r["adj"])
         assert np.array_equal(support[i], acc / 12)
+
+
+# ---- Rho path: cells with several knock-downs ------------------------------------------------
+@pytest.mark.parametrize("S,Eg,Cn,seed", [(4, 3, 300, 1), (6, 5, 2000, 2), (12, 8, 5000, 3)])
+def test_rho_path_do_mean_and_get_probs(S, Eg, Cn, seed):
+    """doMean with normalised Rho columns (R/mnems_low.r:896-904), E-step with OR-ed effect rows (:613-616), theta
+    given and theta = NULL, on data with single, double and triple knock-downs."""
+    m = simdata.make_multi(S=S, Egenes=Eg, C=Cn, mw=(0.5, 0.5), seed=seed)
+    D, pe, E, k = m["D"], m["pert_enc"], m["E"], 2
+    rng = np.random.default_rng(seed)
+    w = rng.random((3, Cn))
+    w[rng.random((3, Cn)) < 0.05] = 0.0
+    with mb.Context(D, m["labels"]) as cx:                       # "_" labels -> getRho -> mnemcu_ctx_create_rho
+        assert cx.S == S
+        R = mb.doMean(cx, w)
+        R0 = mb.doMean(cx)
+        for j in range(3):
+            close(R[j], orc.do_mean(D, pe, S, w[j]), rtol=1e-11, atol=1e-11)
+        close(R0, orc.do_mean(D, pe, S), rtol=1e-11, atol=1e-11)
+        res = [dict(adj=orc.transitive_reduction(rand_graph(rng, S, 0.3)), subtopo=rng.integers(0, S + 1, E).astype(np.int32))
+               for _ in range(k)]
+        L_in = rng.normal(size=(k, Cn))
+        got = mb.getProbs(L_in, k, cx, res, complete=True)
+        want = orc.get_probs(D, pe, S, np.stack([r["adj"] for r in res]), np.stack([r["subtopo"] for r in res]), L_in, None,
+                             complete=True)
+        close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
+        assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
+        phi = simdata.init_phi(S, k, 1, seed=seed)[0]
+        L0 = np.zeros((k, Cn))
+        got = mb.getProbs(L0, k, cx, [dict(adj=p) for p in phi])
+        want = orc.get_probs(D, pe, S, phi, None, L0, None)
+        assert np.array_equal(got["theta_used"], want["theta_used"])
+        close(got["probs"], want["probs"], rtol=1e-10, atol=1e-10)
+        assert abs(got["ll"] - want["ll"]) <= RTOL * abs(want["ll"])
+    # the same context from an explicit Rho matrix
+    close(mb.doMean(D, w[0], Rho=m["Rho"]), orc.do_mean(D, pe, S, w[0]), rtol=1e-11, atol=1e-11)
+
+
+def test_rho_path_with_control_cells_and_empty_sgenes():
+    """Cells without any knock-down (all-zero Rho column) have no effects and enter no S-gene's mean; an S-gene that
+    is only ever knocked down together with others has no segment of its own."""
+    m = simdata.make_multi(S=5, Egenes=4, C=400, seed=9)
+    D, Rho = m["D"], m["Rho"].copy()
+    Rho[:, :25] = 0.0                                             # control cells
+    only_multi = Rho[4] * (Rho.sum(0) == 1) > 0                   # give S-gene 5 a partner wherever it is alone
+    Rho[0, only_multi] = 1.0
+    masks = (Rho.T @ (1 << np.arange(5))).astype(np.int64)
+    single = np.array([bin(int(x)).count("1") == 1 for x in masks])
+    pe = np.where(single, np.log2(np.maximum(masks, 1)).astype(np.int64) + 1, -masks).astype(np.int32)
+    rng = np.random.default_rng(4)
+    w = rng.random(400)
+    close(mb.doMean(D, w, Rho=Rho), orc.do_mean(D, pe, 5, w), rtol=1e-11, atol=1e-11)
+    res = [dict(adj=rand_graph(rng, 5, 0.3), subtopo=rng.integers(0, 6, m["E"]).astype(np.int32)) for _ in range(2)]
+    got = mb.getProbs(np.zeros((2, 400)), 2, D, res, Rho=Rho)
+    want = orc.get_probs(D, pe, 5, np.stack([r["adj"] for r in res]), np.stack([r["subtopo"] for r in res]),
+                         np.zeros((2, 400)), None)
+    close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
+    assert (got["probs"][:, :25] == 0).all()
+
+
+@pytest.mark.parametrize("S,Eg,Cn,seed", [(5, 4, 900, 21), (7, 6, 3000, 22)])
+def test_rho_path_em(S, Eg, Cn, seed):
+    """mnem() on multi-knock-down data: graphs and theta bit-exact, likelihoods to 1e-9 (same bar as single knock-downs)."""
+    m = simdata.make_multi(S=S, Egenes=Eg, C=Cn, mw=(0.45, 0.55), seed=seed)
+    sim = dict(S=S, pert=m["pert_enc"])
+    init = simdata.init_phi(S, 2, 4, seed=seed)
+    check_em(sim, m["D"], init, complete=False, gpu_pert=m["labels"])

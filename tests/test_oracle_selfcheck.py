@@ -265,3 +265,63 @@ def test_em_oracle_properties():
     rf = orc.mnem_em(D, sim["pert"], sim["S"], init, acc="f64")
     assert np.array_equal(rf["adj"], r1["adj"]) and np.array_equal(rf["theta"], r1["theta"])
     np.testing.assert_allclose(rf["ll"], r1["ll"], rtol=1e-12)
+
+
+# ---- Rho path: cells with several knock-downs (R/mnems_low.r:308-324, 613-616, 896-904) ------------------------------
+def test_rho_path_matches_the_matrix_formulas():
+    """The oracle's multi-knock-down branches against the reference's own matrix expressions evaluated in NumPy:
+    doMean = (D * w) %*% t(Rho') with Rho' columns normalised to sum 1; E-step effect rows min(1, t(Rho) %*% adj1);
+    theta-free E-step argmax over (D * gamma) %*% cbind(adj1, 0)."""
+    m = simdata.make_multi(S=5, Egenes=3, C=260, seed=12)
+    D, Rho, pe, S, E, Cn, k = m["D"], m["Rho"], m["pert_enc"], m["S"], m["E"], m["C"], m["k"]
+    assert (Rho.sum(0) > 1).any() and (Rho.sum(0) == 1).any()
+    rng = np.random.default_rng(2)
+    w = rng.random(Cn)
+    w[rng.random(Cn) < 0.1] = 0.0
+    Rn = Rho / np.maximum(Rho.sum(0), 1)[None, :]
+    np.testing.assert_allclose(orc.do_mean(D, pe, S, w), (D * w) @ Rn.T, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(orc.do_mean(D, pe, S), D @ Rn.T, rtol=1e-12, atol=1e-12)
+    phi = np.stack([rand_graph(rng, S, 0.3, dag=True) for _ in range(k)])
+    theta = rng.integers(0, S + 1, (k, E)).astype(np.int32)
+
+    def estep(phi_i, th):
+        adj1 = np.minimum(1, Rho.T @ np_closure(phi_i))                       # C x S
+        adj1 = np.concatenate([adj1, np.zeros((Cn, 1))], 1)
+        sub = np.where(th == 0, S + 1, th)
+        return (D * adj1[:, sub - 1].T).sum(0)                                # colSums(data * t(adj2))
+
+    r = orc.get_probs(D, pe, S, phi, theta, np.zeros((k, Cn)), None)
+    want = np.stack([estep(phi[i], theta[i]) for i in range(k)])
+    np.testing.assert_allclose(r["probs"], want, rtol=1e-12, atol=1e-12)
+    # theta = NULL: one replay of the inner loop
+    r0 = orc.get_probs(D, pe, S, phi, None, np.zeros((k, Cn)), None)
+    mw = orc.mw_update(np.zeros((k, Cn)), np.ones(k) / k, na_guard=True)
+    probs, best, llold = np.zeros((k, Cn)), np.zeros((k, Cn)), -np.inf
+    for _ in range(10):
+        post = orc.get_affinity(probs, mw)
+        new = np.zeros((k, Cn))
+        for i in range(k):
+            adj1 = np.minimum(1, Rho.T @ np_closure(phi[i]))
+            W = (D * post[i]) @ np.concatenate([adj1, np.zeros((Cn, 1))], 1)
+            th = W.argmax(1) + 1
+            th[th == S + 1] = 0
+            new[i] = estep(phi[i], th)
+        ll0 = orc.get_ll(new, mw)
+        if ll0 > llold:
+            best = new
+        probs, llold = new, ll0
+        mw = orc.mw_update(probs, mw)
+    np.testing.assert_allclose(r0["probs"], best, rtol=1e-12, atol=1e-12)
+    assert abs(r0["ll"] - llold) <= 1e-12 * abs(llold)
+
+
+def test_rho_path_reduces_to_the_single_knockdown_path():
+    """Encoding single knock-downs as masks must not change a bit of the EM fit."""
+    sim = simdata.make_config(dict(S=4, Egenes=3, C=200, mw=[0.5, 0.5], k=2, starts=2, uninform=0), seed=5)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(4, 2, 2, seed=1)
+    a = orc.mnem_em(D, sim["pert"], 4, init)
+    enc = -(1 << (sim["pert"].astype(np.int64) - 1))
+    b = orc.mnem_em(D, enc.astype(np.int32), 4, init)
+    for key in ("adj", "theta", "probs", "ll", "mw"):
+        assert np.array_equal(a[key], b[key]), key
