@@ -78,12 +78,21 @@ int mnemcu_get_ll(const double *L, int k, int C, const double *mw, int complete,
  * score[n]; theta (n*E) and W (n*E*S, `subweights`) may be NULL. */
 int mnemcu_score_adj(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close, double *score,
                      int32_t *theta, double *W);
+/* scoreAdj(..., marginal = TRUE, logtype) R/mnems.r:455-457: score = sum_e log_b(sum_j b^cbind(0, R %*% adj)[e, j]);
+ * theta and W as above (the attachment is the same argmax). */
+int mnemcu_score_adj_marginal(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close,
+                              double logtype, double *score, int32_t *theta, double *W);
 /* nem(search = "greedy", runs = 1) R/mnems.r:111-142,203-307,362-379 for n independent searches:
  * R is n blocks of E x S, start n graphs (NULL = empty starts).  Outputs per search: adj (transitively
  * reduced), theta, score (nem$score), max_trace (max(nem$scores)), n_iter accepted moves, n_scored
  * candidate graphs scored (before unique()). */
 int mnemcu_nem_greedy(const double *R, int E, int S, const uint8_t *start, int n, uint8_t *adj_out,
                       int32_t *theta_out, double *score, double *max_trace, int32_t *n_iter, int64_t *n_scored);
+/* nem(search = "greedy", marginal = TRUE, logtype): the same hill-climb with every scoreAdj call in its marginal
+ * form (R/mnems.r:135, 208, 363). */
+int mnemcu_nem_greedy_marginal(const double *R, int E, int S, const uint8_t *start, int n, double logtype,
+                               uint8_t *adj_out, int32_t *theta_out, double *score, double *max_trace,
+                               int32_t *n_iter, int64_t *n_scored);
 
 /* ---- device-resident data context -------------------------------------------------------------------- */
 /* Uploads D (E x C) once, sorted by perturbation, in the two HBM layouts the kernels stream. */

@@ -53,6 +53,9 @@ SIGNATURES = {
     "mnemcu_get_affinity": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, c_dp]),
     "mnemcu_get_ll": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_double, c_dp]),
     "mnemcu_score_adj": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, C.c_int, c_dp, c_i32p, c_dp]),
+    "mnemcu_score_adj_marginal": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, C.c_int, C.c_double, c_dp, c_i32p, c_dp]),
+    "mnemcu_nem_greedy_marginal": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, C.c_double, c_u8p, c_i32p, c_dp, c_dp,
+                                             c_i32p, c_i64p]),
     "mnemcu_nem_greedy": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, c_u8p, c_i32p, c_dp, c_dp, c_i32p, c_i64p]),
     "mnemcu_ctx_create": (C.c_int, [c_dp, C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(c_ctx)]),
     "mnemcu_ctx_create_rho": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.POINTER(c_ctx)]),

@@ -286,8 +286,8 @@ def doMean(D, weights=None, pert=None, Rho=None):
             cx.close()
 
 
-def scoreAdj(D, adj, pert=None, trans_close=True, dotopo=True):
-    """scoreAdj(D, adj, method='llr', marginal=FALSE): list(score, subtopo, subweights).
+def scoreAdj(D, adj, pert=None, trans_close=True, dotopo=True, marginal=False, logtype=2):
+    """scoreAdj(D, adj, method='llr', marginal, logtype): list(score, subtopo, subweights).
 
     D may be the raw E x C data (collapsed with doMean first: sum_c D[e,c] adj[pert(c), j] = (R %*% adj)[e, j]) or
     an already collapsed E x S matrix when pert is None.  adj may be one graph or a stack [n, S, S]."""
@@ -300,15 +300,20 @@ def scoreAdj(D, adj, pert=None, trans_close=True, dotopo=True):
     score = np.zeros(n)
     theta = np.zeros((n, E), dtype=np.int32)
     W = np.zeros((n, S, E))
-    check(load_library().mnemcu_score_adj(dp(R), E, S, u8p(b), n, int(bool(trans_close)), dp(score), i32p(theta), dp(W)))
+    if marginal:
+        check(load_library().mnemcu_score_adj_marginal(dp(R), E, S, u8p(b), n, int(bool(trans_close)), float(logtype),
+                                                       dp(score), i32p(theta), dp(W)))
+    else:
+        check(load_library().mnemcu_score_adj(dp(R), E, S, u8p(b), n, int(bool(trans_close)), dp(score), i32p(theta), dp(W)))
     W = np.transpose(W, (0, 2, 1))
     if np.asarray(adj).ndim == 2:
         return dict(score=float(score[0]), subtopo=theta[0] if dotopo else None, subweights=W[0])
     return dict(score=score, subtopo=theta if dotopo else None, subweights=W)
 
 
-def nem_greedy(R, start=None):
-    """Batched nem(search='greedy') on collapsed matrices R [n, E, S] (or [E, S]); start [n, S, S] or None."""
+def nem_greedy(R, start=None, marginal=False, logtype=2):
+    """Batched nem(search='greedy', marginal, logtype) on collapsed matrices R [n, E, S] (or [E, S]); start [n, S, S]
+    or None."""
     R = np.asarray(R, dtype=np.float64)
     single = R.ndim == 2
     if single:
@@ -325,18 +330,23 @@ def nem_greedy(R, start=None):
     score, mtr = np.zeros(n), np.zeros(n)
     nit = np.zeros(n, dtype=np.int32)
     nsc = np.zeros(n, dtype=np.int64)
-    check(load_library().mnemcu_nem_greedy(dp(Rb), E, S, u8p(sb), n, u8p(adj), i32p(theta), dp(score), dp(mtr), i32p(nit),
-                                           nsc.ctypes.data_as(_lib.c_i64p)))
+    if marginal:
+        check(load_library().mnemcu_nem_greedy_marginal(dp(Rb), E, S, u8p(sb), n, float(logtype), u8p(adj), i32p(theta),
+                                                        dp(score), dp(mtr), i32p(nit), nsc.ctypes.data_as(_lib.c_i64p)))
+    else:
+        check(load_library().mnemcu_nem_greedy(dp(Rb), E, S, u8p(sb), n, u8p(adj), i32p(theta), dp(score), dp(mtr),
+                                               i32p(nit), nsc.ctypes.data_as(_lib.c_i64p)))
     out = dict(adj=_ungraphs(adj, n, S), subtopo=theta, score=score, max_trace=mtr, n_iter=nit, n_scored=nsc)
     if single:
         out = {k_: v[0] for k_, v in out.items()}
     return out
 
 
-def nem(D, pert=None, start=None, weights=None, Rho=None):
-    """nem(D, search='greedy', start, weights, domean=TRUE, Rho): list(adj, score, subtopo, subweights, ...)."""
+def nem(D, pert=None, start=None, weights=None, Rho=None, marginal=False, logtype=2):
+    """nem(D, search='greedy', start, weights, domean=TRUE, Rho, marginal, logtype): list(adj, score, subtopo, ...)."""
     R = doMean(D, weights, pert, Rho)
-    r = nem_greedy(R, None if start is None else np.asarray(start)[None] if np.asarray(start).ndim == 2 else start)
+    r = nem_greedy(R, None if start is None else np.asarray(start)[None] if np.asarray(start).ndim == 2 else start,
+                   marginal=marginal, logtype=logtype)
     sw = scoreAdj(R, r["adj"])["subweights"]
     return dict(adj=r["adj"], score=float(r["score"]), scores_max=float(r["max_trace"]), subtopo=r["subtopo"],
                 subweights=sw, n_iter=int(r["n_iter"]), n_scored=int(r["n_scored"]))

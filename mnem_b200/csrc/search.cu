@@ -27,6 +27,8 @@ constexpr int kDictThreads = 512;
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
     int dcap = 0, G = 1;              // dictionary capacity (entries), row groups per search
+    int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
+    double logtype = 2.0;
     size_t dict_smem = 0;
     DevBuf<const double *> Rptr;
     DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks;
@@ -242,14 +244,19 @@ __device__ __forceinline__ double col_sum(const double (&r)[SP], uint32_t m)
     return w;
 }
 
-template <int SP>
+// MARG: scoreAdj(marginal = TRUE), R/mnems.r:455-457: a row contributes log_b(sum_j b^cbind(0, score)[e, j]) instead of
+// its maximum.  The powers of the unchanged columns are cached per row; the row sum runs over the null column and then
+// the S-gene columns in ascending order.
+__device__ __forceinline__ double pow_logtype(double b, double y) { return b == 2.0 ? exp2(y) : pow(b, y); }
+
+template <int SP, bool MARG>
 __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, int etiles,
                                                       const double *const *__restrict__ Rptr,
                                                       const int32_t *__restrict__ ncand,
                                                       const uint32_t *__restrict__ Pcol,
                                                       const uint32_t *__restrict__ cand_cols,
                                                       const uint32_t *__restrict__ cand_J,
-                                                      double *__restrict__ partial)
+                                                      double *__restrict__ partial, double logtype)
 {
     __shared__ uint32_t s_pcol[32];
     __shared__ uint32_t s_ccol[kCT][32];
@@ -278,13 +285,23 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
     for (int j = 0; j < SP; ++j) {
         if (j < S) {
             const double w = col_sum<SP>(r, s_pcol[j]);
-            s_W[j][tid] = w;
+            s_W[j][tid] = MARG ? pow_logtype(logtype, w) : w;
             if (w > m1) { m2 = m1; a2 = a1; m1 = w; a1 = j; }
             else if (w > m2) { m2 = w; a2 = j; }
         }
     }
+    const double inv_lb = MARG ? 1.0 / log(logtype) : 0.0;
     for (int ci = 0; ci < nloc; ++ci) {
         uint32_t J = s_J[ci];
+        if (MARG) {
+            double rs = pow_logtype(logtype, 0.0);
+            for (int j = 0; j < S; ++j)
+                rs += ((J >> j) & 1u) ? pow_logtype(logtype, col_sum<SP>(r, s_ccol[ci][j])) : s_W[j][tid];
+            double val = e < E ? log(rs) * inv_lb : 0.0;
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_down_sync(kFull, val, o);
+            if (lane == 0) s_red[ci][warp] = val;
+            continue;
+        }
         double best;                       // maximum over the columns the candidate shares with the current graph
         if (!((J >> a1) & 1u)) best = m1;
         else if (!((J >> a2) & 1u) && a2 != a1) best = m2;
@@ -733,8 +750,14 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
     dim3 grid((sb->maxc + kCT - 1) / kCT, sb->etiles, n);
     const int S = sb->S;
 #define MN_SCORE(SPV)                                                                                              \
-    MN_LAUNCH(score_kernel<SPV>, grid, kRows, 0, st, sb->E, S, sb->maxc, sb->etiles, sb->Rptr.p, sb->ncand.p,      \
-              sb->Pcol.p, sb->cand_cols.p, sb->cand_J.p, sb->partial.p)
+    do {                                                                                                           \
+        if (sb->marginal)                                                                                          \
+            MN_LAUNCH((score_kernel<SPV, true>), grid, kRows, 0, st, sb->E, S, sb->maxc, sb->etiles, sb->Rptr.p,   \
+                      sb->ncand.p, sb->Pcol.p, sb->cand_cols.p, sb->cand_J.p, sb->partial.p, sb->logtype);         \
+        else                                                                                                       \
+            MN_LAUNCH((score_kernel<SPV, false>), grid, kRows, 0, st, sb->E, S, sb->maxc, sb->etiles, sb->Rptr.p,  \
+                      sb->ncand.p, sb->Pcol.p, sb->cand_cols.p, sb->cand_J.p, sb->partial.p, sb->logtype);         \
+    } while (0)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
     else if (S <= 24) MN_SCORE(24);
@@ -768,6 +791,12 @@ static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
 static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
 {
     const int S = sb->S;
+    if (sb->marginal) {   // the dictionary trick needs a row MAXIMUM; the marginal score re-sums the changed columns per candidate
+        MN_TRY(launch_score(sb, n, st));
+        dim3 rg((sb->maxc + 255) / 256, n);
+        MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p);
+        return 0;
+    }
     dim3 grid(sb->G, n);
 #define MN_SCORE(SPV)                                                                                              \
     MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, sb->G,   \
@@ -914,14 +943,17 @@ const unsigned long long *search_nscored(const SearchBatch *sb) { return sb->nsc
 using namespace mn;
 
 // ---- ABI ---------------------------------------------------------------------------------------------------
-extern "C" int mnemcu_nem_greedy(const double *R, int E, int S, const uint8_t *start, int n, uint8_t *adj_out,
-                                 int32_t *theta_out, double *score, double *max_trace, int32_t *n_iter,
-                                 int64_t *n_scored)
+static int nem_greedy_impl(const double *R, int E, int S, const uint8_t *start, int n, int marginal, double logtype,
+                           uint8_t *adj_out, int32_t *theta_out, double *score, double *max_trace, int32_t *n_iter,
+                           int64_t *n_scored)
 {
     MN_ARG(R && adj_out && theta_out, "NULL pointer");
     MN_ARG(E >= 1 && S >= 1 && S <= MNEMCU_MAX_S && n >= 1, "bad size");
+    MN_ARG(!marginal || (logtype > 0 && logtype != 1.0), "logtype must be a valid log base");
     SearchBatch *sb = nullptr;
     MN_TRY(search_create(n, E, S, &sb));
+    sb->marginal = marginal ? 1 : 0;
+    sb->logtype = logtype;
     auto body = [&]() -> int {
         DevBuf<double> dR;
         DevBuf<uint8_t> dg;
@@ -954,6 +986,20 @@ extern "C" int mnemcu_nem_greedy(const double *R, int E, int S, const uint8_t *s
     return rc;
 }
 
+extern "C" int mnemcu_nem_greedy(const double *R, int E, int S, const uint8_t *start, int n, uint8_t *adj_out,
+                                 int32_t *theta_out, double *score, double *max_trace, int32_t *n_iter,
+                                 int64_t *n_scored)
+{
+    return nem_greedy_impl(R, E, S, start, n, 0, 2.0, adj_out, theta_out, score, max_trace, n_iter, n_scored);
+}
+
+extern "C" int mnemcu_nem_greedy_marginal(const double *R, int E, int S, const uint8_t *start, int n, double logtype,
+                                          uint8_t *adj_out, int32_t *theta_out, double *score, double *max_trace,
+                                          int32_t *n_iter, int64_t *n_scored)
+{
+    return nem_greedy_impl(R, E, S, start, n, 1, logtype, adj_out, theta_out, score, max_trace, n_iter, n_scored);
+}
+
 // scoreAdj for n candidate graphs against one R: uses the same scoring kernel with every column marked changed
 __global__ void score_api_prep_kernel(int S, int maxc, int n, const uint32_t *__restrict__ cols_in,
                                       uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
@@ -984,13 +1030,16 @@ __global__ void cols_from_rows_kernel(int S, int trans_close, const uint32_t *__
     cols[q * 32 + lane] = warp_transpose(row, lane, S);
 }
 
-extern "C" int mnemcu_score_adj(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close,
-                                double *score, int32_t *theta, double *W)
+static int score_adj_impl(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close, int marginal,
+                          double logtype, double *score, int32_t *theta, double *W)
 {
     MN_ARG(R && adj && score, "NULL pointer");
     MN_ARG(E >= 1 && S >= 1 && S <= MNEMCU_MAX_S && n >= 1, "bad size");
+    MN_ARG(!marginal || (logtype > 0 && logtype != 1.0), "logtype must be a valid log base");
     SearchBatch sb;
     sb.nmax = 1; sb.E = E; sb.S = S; sb.etiles = (E + kRows - 1) / kRows; sb.maxc = n;
+    sb.marginal = marginal ? 1 : 0;
+    sb.logtype = logtype;
     DevBuf<double> dR, dscore, dW;
     DevBuf<uint8_t> dg;
     DevBuf<uint32_t> drows, dcols;
@@ -1024,6 +1073,18 @@ extern "C" int mnemcu_score_adj(const double *R, int E, int S, const uint8_t *ad
     }
     MN_CU(cudaDeviceSynchronize());
     return 0;
+}
+
+extern "C" int mnemcu_score_adj(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close,
+                                double *score, int32_t *theta, double *W)
+{
+    return score_adj_impl(R, E, S, adj, n, trans_close, 0, 2.0, score, theta, W);
+}
+
+extern "C" int mnemcu_score_adj_marginal(const double *R, int E, int S, const uint8_t *adj, int n, int trans_close,
+                                         double logtype, double *score, int32_t *theta, double *W)
+{
+    return score_adj_impl(R, E, S, adj, n, trans_close, 1, logtype, score, theta, W);
 }
 
 // c(get.ins.fast, get.rev.tc, get.del.tc)(P) for one graph, as uint8 matrices (test / inspection entry point)

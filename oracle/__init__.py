@@ -48,6 +48,7 @@ def lib(acc="ld"):
         _LIBS[acc] = C.CDLL(path)
         _LIBS[acc].orc_get_ll.restype = C.c_double
         _LIBS[acc].orc_score_adj.restype = C.c_double
+        _LIBS[acc].orc_score_adj_m.restype = C.c_double
         _LIBS[acc].orc_get_probs.restype = C.c_double
     return _LIBS[acc]
 
@@ -187,26 +188,28 @@ def do_mean(D, pert, S, weights=None, acc="ld"):
     return R
 
 
-def score_adj(R, adj, trans_close=True, acc="ld"):
-    """scoreAdj(D=R, adj, dotopo=TRUE) -> (score, theta 0..S, W)."""
+def score_adj(R, adj, trans_close=True, marginal=False, logtype=2.0, acc="ld"):
+    """scoreAdj(D=R, adj, marginal, dotopo=TRUE) -> (score, theta 0..S, W)."""
     R = _f(R)
     E, S = R.shape
     b = _graphs(adj)
     theta = np.zeros(E, dtype=np.int32)
     W = np.zeros((E, S), order="F")
-    sc = lib(acc).orc_score_adj(_d(R), E, S, _u8(b), int(bool(trans_close)), _i32(theta), _d(W))
+    sc = lib(acc).orc_score_adj_m(_d(R), E, S, _u8(b), int(bool(trans_close)), int(bool(marginal)), C.c_double(logtype),
+                                  _i32(theta), _d(W))
     return sc, theta, W
 
 
-def nem_greedy(R, start=None, acc="ld"):
-    """nem(search='greedy') on collapsed data -> dict(adj reduced, theta, score, max_trace, n_iter, n_scored)."""
+def nem_greedy(R, start=None, marginal=False, logtype=2.0, acc="ld"):
+    """nem(search='greedy', marginal) on collapsed data -> dict(adj reduced, theta, score, max_trace, n_iter, n_scored)."""
     R = _f(R)
     E, S = R.shape
     sb = _graphs(start) if start is not None else None
     adj = np.zeros(S * S, dtype=np.uint8)
     theta = np.zeros(E, dtype=np.int32)
     info = NemInfo()
-    lib(acc).orc_nem_greedy(_d(R), E, S, _u8(sb) if sb is not None else None, _u8(adj), _i32(theta), C.byref(info))
+    lib(acc).orc_nem_greedy_m(_d(R), E, S, _u8(sb) if sb is not None else None, int(bool(marginal)), C.c_double(logtype),
+                              _u8(adj), _i32(theta), C.byref(info))
     return dict(adj=_ungraphs(adj, 1, S)[0], theta=theta, score=info.score, max_trace=info.max_trace,
                 n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin, n_raw=info.n_raw)
 

@@ -336,18 +336,44 @@ static double score_total(const double *W, int E, int S, int32_t *theta)
     return (double)tot;
 }
 
-/* Public: scoreAdj(D=R, adj, trans.close, dotopo=TRUE).  W_out (E x S) and theta may be NULL. */
-double orc_score_adj(const double *R, int E, int S, const uint8_t *adj_in, int trans_close, int32_t *theta,
-                     double *W_out)
+/* marginal = TRUE, R/mnems.r:455-457: pscore <- logtype^cbind(0, score); sum(log(rowSums(pscore))/log(logtype)).
+ * rowSums and sum accumulate in long double; theta (dotopo) is the same argmax as in the max variant (:447-450). */
+static double score_total_marginal(const double *W, int E, int S, double logtype, int32_t *theta)
+{
+    acc_t tot = 0;
+    const double lb = log(logtype);
+    for (int e = 0; e < E; e++) {
+        double best = 0.0;
+        int32_t arg = 0;
+        acc_t rs = rpow(logtype, 0.0);
+        for (int j = 0; j < S; j++) {
+            double v = W[e + (size_t)j * E];
+            if (v > best) { best = v; arg = j + 1; }
+            rs += rpow(logtype, v);
+        }
+        if (theta) theta[e] = arg;
+        tot += log((double)rs) / lb;
+    }
+    return (double)tot;
+}
+
+/* Public: scoreAdj(D=R, adj, trans.close, marginal, logtype, dotopo=TRUE).  W_out (E x S) and theta may be NULL. */
+double orc_score_adj_m(const double *R, int E, int S, const uint8_t *adj_in, int trans_close, int marginal,
+                       double logtype, int32_t *theta, double *W_out)
 {
     uint8_t adj[ORC_MAXS * ORC_MAXS];
     memcpy(adj, adj_in, (size_t)S * S);
     if (trans_close) orc_mytc(adj, S);                                                   /* :428-430 */
     double *W = W_out ? W_out : (double *)malloc(sizeof(double) * (size_t)E * S);
     score_cols(R, E, S, adj, NULL, W);
-    double sc = score_total(W, E, S, theta);
+    double sc = marginal ? score_total_marginal(W, E, S, logtype, theta) : score_total(W, E, S, theta);
     if (!W_out) free(W);
     return sc;
+}
+double orc_score_adj(const double *R, int E, int S, const uint8_t *adj_in, int trans_close, int32_t *theta,
+                     double *W_out)
+{
+    return orc_score_adj_m(R, E, S, adj_in, trans_close, 0, 2.0, theta, W_out);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -425,8 +451,17 @@ typedef struct {
     long n_raw;          /* candidates generated before unique() */
 } orc_nem_info;
 
+void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int marginal, double logtype,
+                      uint8_t *adj_out, int32_t *theta_out, orc_nem_info *info);
 void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t *adj_out, int32_t *theta_out,
                     orc_nem_info *info)
+{
+    orc_nem_greedy_m(R, E, S, start, 0, 2.0, adj_out, theta_out, info);
+}
+
+/* marginal != 0: every scoreAdj call of the search carries marginal = TRUE (R/mnems.r:135, 208, 363) */
+void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int marginal, double logtype,
+                      uint8_t *adj_out, int32_t *theta_out, orc_nem_info *info)
 {
     const int SS = S * S;
     uint8_t better[ORC_MAXS * ORC_MAXS], tmp[ORC_MAXS * ORC_MAXS];
@@ -439,7 +474,7 @@ void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t
     uint8_t *models = (uint8_t *)malloc((size_t)3 * SS * SS + SS);
     int8_t *kind = (int8_t *)malloc((size_t)3 * SS + 1);
     int haveP = 0;
-    double oldscore = orc_score_adj(R, E, S, better, 1, NULL, NULL);             /* :135-141 closes inside */
+    double oldscore = orc_score_adj_m(R, E, S, better, 1, marginal, logtype, NULL, NULL);   /* :135-141 closes inside */
     double maxtrace = oldscore;
     long nscored = 0, nraw = 0;
     int niter = 0;
@@ -465,7 +500,7 @@ void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t
                 memcpy(Wc, P, sizeof(double) * (size_t)E * S);
                 score_cols(R, E, S, cand, chg, Wc);
             }
-            sc = score_total(Wc, E, S, NULL);
+            sc = marginal ? score_total_marginal(Wc, E, S, logtype, NULL) : score_total(Wc, E, S, NULL);
             if (isnan(sc)) sc = 0.0;                                             /* :235 */
             nscored++;
             if (sc > bests) {                                                    /* which.max: first */
@@ -489,7 +524,7 @@ void orc_nem_greedy(const double *R, int E, int S, const uint8_t *start, uint8_t
         } else break;                                                            /* :287-289 */
     }
     /* :362-369 theta from the closed final graph, :374 reduction */
-    orc_score_adj(R, E, S, better, 1, theta_out, NULL);
+    orc_score_adj_m(R, E, S, better, 1, marginal, logtype, theta_out, NULL);
     orc_trans_reduce(better, S, adj_out);
     if (info) { info->score = oldscore; info->max_trace = maxtrace; info->n_iter = niter; info->n_scored = nscored;
                 info->min_margin = minmargin; info->n_raw = nraw; }

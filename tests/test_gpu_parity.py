@@ -435,3 +435,36 @@ def test_rho_path_em(S, Eg, Cn, seed):
     sim = dict(S=S, pert=m["pert_enc"])
     init = simdata.init_phi(S, 2, 4, seed=seed)
     check_em(sim, m["D"], init, complete=False, gpu_pert=m["labels"])
+
+
+# ---- marginal = TRUE scoring (R/mnems.r:455-457) ------------------------------------------------
+@pytest.mark.parametrize("S,E,logtype", [(3, 10, 2.0), (8, 100, 2.0), (20, 333, np.e), (30, 600, 2.0)])
+def test_score_adj_marginal(S, E, logtype):
+    rng = np.random.default_rng(S + E)
+    R = rng.normal(size=(E, S)) * 3
+    adjs = np.stack([rand_graph(rng, S, rng.uniform(0.02, 0.5)) for _ in range(20)])
+    for tc in (True, False):
+        got = mb.scoreAdj(R, adjs, trans_close=tc, marginal=True, logtype=logtype)
+        for i, a in enumerate(adjs):
+            sc, th, W = orc.score_adj(R, a, trans_close=tc, marginal=True, logtype=logtype)
+            assert np.array_equal(got["subweights"][i], W)
+            assert np.array_equal(got["subtopo"][i], th)
+            assert abs(got["score"][i] - sc) <= RTOL * abs(sc)
+
+
+@pytest.mark.parametrize("S,E,n,logtype", [(3, 10, 4, 2.0), (6, 40, 6, 2.0), (10, 100, 4, np.e), (16, 130, 2, 2.0)])
+def test_nem_greedy_marginal(S, E, n, logtype):
+    """nem(marginal = TRUE): same moves, same graph, same theta as the oracle; scores to 1e-9 (log / pow are libm on one
+    side and CUDA math on the other, so a decision must be clearer than 1e-9 for the case to be admissible)."""
+    rng = np.random.default_rng(2000 + S)
+    R = np.stack([planted_R(rng, S, E, snr=1.0) / 4 for _ in range(n)])      # small values: b^W stays finite
+    starts = np.stack([orc.transitive_reduction(rand_graph(rng, S, 0.15, dag=True)) if i % 2 else np.zeros((S, S))
+                       for i in range(n)])
+    got = mb.nem_greedy(R, starts, marginal=True, logtype=logtype)
+    for i in range(n):
+        want = orc.nem_greedy(R[i], starts[i], marginal=True, logtype=logtype)
+        assert want["min_margin"] > 1e-9, "near-tie between candidates; pick another seed"
+        assert np.array_equal(got["adj"][i], want["adj"])
+        assert np.array_equal(got["subtopo"][i], want["theta"])
+        assert got["n_iter"][i] == want["n_iter"] and got["n_scored"][i] == want["n_raw"]
+        assert abs(got["score"][i] - want["score"]) <= RTOL * abs(want["score"])

@@ -325,3 +325,25 @@ def test_rho_path_reduces_to_the_single_knockdown_path():
     b = orc.mnem_em(D, enc.astype(np.int32), 4, init)
     for key in ("adj", "theta", "probs", "ll", "mw"):
         assert np.array_equal(a[key], b[key]), key
+
+
+# ---- marginal = TRUE scoring (R/mnems.r:455-457) -------------------------------------------------------------------
+@pytest.mark.parametrize("logtype", [2.0, np.e, 10.0])
+def test_marginal_score_matches_the_formula(logtype):
+    rng = np.random.default_rng(11)
+    S, E = 7, 31
+    R = rng.normal(size=(E, S)) * 2
+    for _ in range(6):
+        adj = rand_graph(rng, S, 0.3)
+        for tc in (True, False):
+            sc, th, W = orc.score_adj(R, adj, trans_close=tc, marginal=True, logtype=logtype)
+            A = np_closure(adj) if tc else (adj != 0).astype(int)
+            full = np.concatenate([np.zeros((E, 1)), R @ A], 1)
+            want = (np.log((logtype ** full).sum(1)) / np.log(logtype)).sum()
+            assert abs(sc - want) <= 1e-12 * abs(want)
+            assert (th == full.argmax(1)).all()                      # dotopo: same attachment as the max variant
+            np.testing.assert_allclose(W, R @ A, rtol=1e-12, atol=1e-12)
+    # the marginal search only swaps the score: from the same start it must never end below its starting score
+    r = orc.nem_greedy(R, None, marginal=True, logtype=logtype)
+    s0 = orc.score_adj(R, np.zeros((S, S)), marginal=True, logtype=logtype)[0]
+    assert r["score"] >= s0 and r["max_trace"] == r["score"]
