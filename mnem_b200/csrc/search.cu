@@ -24,18 +24,17 @@ constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionar
 constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
 constexpr int kDictThreads = 512;
 constexpr int kFiltThreads = 384;  // FP32 filter pass: 12 warps per CTA, two CTAs per SM
-constexpr int kRsCap = 6;          // candidates per search rescored one by one after the filter pass (more: exact kernel)
+constexpr int kRsCap = 64;         // candidates per search rescored exactly after the filter pass
 constexpr int kRsThreads = 512;
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
-    int dcap = 0, G = 1, Gx = 1;      // dictionary capacity (entries), row groups per search (filter / exact launch)
+    int dcap = 0, G = 1;              // dictionary capacity (entries), row groups per search
     int exact_only = 0;               // skip the FP32 filter, score every candidate in FP64 (MNEMCU_EXACT_SCORES=1)
     size_t filt_smem = 0;
     int filt_ctas = 1;                // resident filter CTAs per SM
     DevBuf<double> rs_scratch;        // [nmax][ntiles][kRsCap]
     DevBuf<unsigned long long> rs_stats;   // [0] candidates rescored, [1] searches that overflowed the cap
-    DevBuf<int32_t> need_exact;       // [nmax] set by rescore_kernel: score this search with the exact kernel
     int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
     double logtype = 2.0;
     size_t dict_smem = 0;
@@ -367,14 +366,12 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
     int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
     const int32_t *__restrict__ nins, const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks,
     const uint16_t *__restrict__ base_id, const uint16_t *__restrict__ pair_id, const uint32_t *__restrict__ Pcol,
-    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial,
-    const int32_t *__restrict__ only)
+    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int q = blockIdx.y, g = blockIdx.x;
     const int nc = ncand[q];
     if (nc == 0) return;
-    if (only && !only[q]) return;                  // exact pass after the filter: only the searches that asked for it
     const int ni = nins[q];
     const int ndq = min(nd[q], dcap);
     VT *T = reinterpret_cast<VT *>(s_raw);                              // [dcap][32]
@@ -430,7 +427,7 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
     const int nv = s_nv;
     int parity = 0;
     const int ntiles = (E + kDictRows - 1) / kDictRows;
-    for (int tile = g; tile < ntiles; tile += (int)gridDim.x) {       // G row groups = gridDim.x
+    for (int tile = g; tile < ntiles; tile += G) {
         const int row = tile * kDictRows + lane;
         double *ptile = partial + ((size_t)q * ntiles + tile) * maxc;   // this tile's per-candidate sums
         {
@@ -566,19 +563,17 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
 // ---- exact rescoring after the FP32 filter pass ------------------------------------------------------------------
 // scores[q][c] holds the filter score a_c of every candidate, |a_c - s_c| <= eps * s_c with eps = 6 * 2^-24 (see
 // score_dict_kernel) and s_c >= 0 the exact score.  The exact maximum is therefore among the candidates with
-// a_c >= a_max * (1 - 2 eps); the window used is 1e-6 (> 2 eps = 7.2e-7), NaN / Inf filter scores always qualify.  Up to
-// kRsCap qualifying candidates (typically one to three) are recomputed here in FP64 with the summation order of the
-// exact kernel -- ascending S-genes per column, rows of a 32-row tile paired (l, l^16), (l, l^8), ..., tiles ascending --
-// so the values finish_body compares are bit-identical to what score_dict_kernel<double> produces; everything else gets
-// -Inf and cannot win.  More qualifying candidates (plateaus: many neighbours with exactly the current score): the
-// search raises need_exact[q] and the exact kernel scores all its candidates in the next launch.
-// grid = searches, block = kRsThreads.
+// a_c >= a_max * (1 - 2 eps); the window used is 1e-6 (> 2 eps = 7.2e-7), NaN / Inf filter scores always qualify.  Those
+// candidates (typically one to three, plus exact ties) are recomputed here in FP64 with the summation order of the exact
+// kernel -- ascending S-genes per column, rows of a 32-row tile paired (l, l^16), (l, l^8), ..., tiles ascending -- so the
+// values finish_body compares are bit-identical to what score_dict_kernel<double> would have produced; everything else
+// gets -Inf and cannot win.  More than kRsCap qualifying candidates (mass ties): all candidates are recomputed, kRsCap at
+// a time.  grid = searches, block = kRsThreads.
 template <int SP>
 __global__ void __launch_bounds__(kRsThreads) rescore_kernel(int E, int S, int maxc, const double *const *__restrict__ Rptr,
                                                             const int32_t *__restrict__ ncand,
                                                             const uint32_t *__restrict__ cand_cols,
                                                             double *__restrict__ scores, double *__restrict__ scratch,
-                                                            int32_t *__restrict__ need_exact,
                                                             unsigned long long *__restrict__ stats)
 {
     __shared__ int s_list[kRsCap];
@@ -587,7 +582,6 @@ __global__ void __launch_bounds__(kRsThreads) rescore_kernel(int E, int S, int m
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kRsThreads / 32;
     const int nc = ncand[q];
-    if (tid == 0) need_exact[q] = 0;
     if (nc == 0) return;
     double *sc = scores + (size_t)q * maxc;
     const int ntiles = (E + kDictRows - 1) / kDictRows;
@@ -604,42 +598,47 @@ __global__ void __launch_bounds__(kRsThreads) rescore_kernel(int E, int S, int m
         if (!(v < thr)) {                                   // NaN and +Inf qualify
             const int idx = atomicAdd(&s_cnt, 1);
             if (idx < kRsCap) s_list[idx] = c;
+        } else {
+            sc[c] = -INFINITY;
         }
     }
     __syncthreads();
-    const int ns = s_cnt;
-    if (ns > kRsCap) {                                      // uniform: leave the field to the exact kernel
-        if (tid == 0) { need_exact[q] = 1; atomicAdd(&stats[1], 1ull); }
-        return;
+    const int total = s_cnt;
+    const bool overflow = total > kRsCap;
+    const int nchunk = overflow ? (nc + kRsCap - 1) / kRsCap : 1;
+    if (tid == 0) {
+        atomicAdd(&stats[0], (unsigned long long)(overflow ? nc : total));
+        if (overflow) atomicAdd(&stats[1], 1ull);
     }
-    for (int c = tid; c < nc; c += kRsThreads)
-        if (sc[c] < thr) sc[c] = -INFINITY;
-    if (tid == 0) atomicAdd(&stats[0], (unsigned long long)ns);
     const double *R = Rptr[q];
     double *part = scratch + (size_t)q * ntiles * kRsCap;
-    for (int tile = warp; tile < ntiles; tile += NW) {
-        const int row = tile * kDictRows + lane;
-        double r[SP];
+    for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int ns = overflow ? min(kRsCap, nc - chunk * kRsCap) : total;
+        for (int tile = warp; tile < ntiles; tile += NW) {
+            const int row = tile * kDictRows + lane;
+            double r[SP];
 #pragma unroll
-        for (int s2 = 0; s2 < SP; ++s2) r[s2] = (s2 < S && row < E) ? R[(size_t)s2 * E + row] : 0.0;
-        for (int i = 0; i < ns; ++i) {
-            const int c = s_list[i];
-            const uint32_t mycol = lane < S ? cand_cols[((size_t)q * maxc + c) * 32 + lane] : 0u;
-            double best = -INFINITY;
-            for (int j = 0; j < S; ++j) {
-                const double w = col_sum<SP>(r, __shfl_sync(kFull, mycol, j));
-                best = w > best ? w : best;                 // NaN never wins
+            for (int s2 = 0; s2 < SP; ++s2) r[s2] = (s2 < S && row < E) ? R[(size_t)s2 * E + row] : 0.0;
+            for (int i = 0; i < ns; ++i) {
+                const int c = overflow ? chunk * kRsCap + i : s_list[i];
+                const uint32_t mycol = lane < S ? cand_cols[((size_t)q * maxc + c) * 32 + lane] : 0u;
+                double best = -INFINITY;
+                for (int j = 0; j < S; ++j) {
+                    const double w = col_sum<SP>(r, __shfl_sync(kFull, mycol, j));
+                    best = w > best ? w : best;             // NaN never wins
+                }
+                double val = best > 0.0 ? best : 0.0;       // rowMaxs(cbind(0, score))
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
+                if (lane == 0) part[(size_t)tile * kRsCap + i] = val;
             }
-            double val = best > 0.0 ? best : 0.0;           // rowMaxs(cbind(0, score))
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
-            if (lane == 0) part[(size_t)tile * kRsCap + i] = val;
         }
-    }
-    __syncthreads();
-    if (tid < ns) {
-        double t = 0.0;
-        for (int et = 0; et < ntiles; ++et) t += part[(size_t)et * kRsCap + tid];
-        sc[s_list[tid]] = t;
+        __syncthreads();
+        if (tid < ns) {
+            double t = 0.0;
+            for (int et = 0; et < ntiles; ++et) t += part[(size_t)et * kRsCap + tid];
+            sc[overflow ? chunk * kRsCap + tid : s_list[tid]] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -869,13 +868,11 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
 // scores[q][c] = sum over the row tiles, ascending -- fully parallel over candidates, so the single-CTA finish step
 // reads one value per candidate instead of one per (candidate, tile)
 __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles, const int32_t *__restrict__ ncand,
-                                                           const double *__restrict__ partial, double *__restrict__ scores,
-                                                           const int32_t *__restrict__ only)
+                                                           const double *__restrict__ partial, double *__restrict__ scores)
 {
     const int q = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand[q]) return;
-    if (only && !only[q]) return;
     double sc = 0.0;
 #pragma unroll 8
     for (int et = 0; et < ntiles; ++et) sc += partial[((size_t)q * ntiles + et) * maxc + c];
@@ -896,8 +893,7 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     if (sb->marginal) {   // the dictionary trick needs a row MAXIMUM; the marginal score re-sums the changed columns per candidate
         MN_TRY(launch_score(sb, n, st));
         dim3 rg((sb->maxc + 255) / 256, n);
-        MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p,
-                  (const int32_t *)nullptr);
+        MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p);
         return 0;
     }
     dim3 grid(sb->G, n);
@@ -906,8 +902,7 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
 #define MN_ARGS sb->E, S, sb->maxc, sb->dcap, sb->G, sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p,  \
                 sb->base_id.p, sb->pair_id.p, sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p
     if (sb->exact_only) {
-#define MN_SCORE(SPV) MN_LAUNCH((score_dict_kernel<SPV, double, kDictThreads, 1>), grid, kDictThreads, sb->dict_smem, st, \
-                                MN_ARGS, (const int32_t *)nullptr)
+#define MN_SCORE(SPV) MN_LAUNCH((score_dict_kernel<SPV, double, kDictThreads, 1>), grid, kDictThreads, sb->dict_smem, st, MN_ARGS)
         if (S <= 8) MN_SCORE(8);
         else if (S <= 16) MN_SCORE(16);
         else if (S <= 24) MN_SCORE(24);
@@ -915,26 +910,16 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
         else if (S <= 30) MN_SCORE(30);
         else MN_SCORE(32);
 #undef MN_SCORE
-        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p,
-                  (const int32_t *)nullptr);
+        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p);
         return 0;
     }
-    // filter pass in FP32, then the exact FP64 scores of the candidates it cannot separate from the best; searches on a
-    // plateau (more than kRsCap such candidates) go through the exact kernel instead.  The exact launch uses the row-group
-    // count of the FP64 table (one CTA per SM); its CTAs exit at once for the searches that did not ask.
-    dim3 xgrid(sb->Gx, n);
+    // filter pass in FP32, then the exact FP64 scores of the candidates it cannot separate from the best
 #define MN_SCORE(SPV)                                                                                              \
     do {                                                                                                           \
-        MN_LAUNCH((score_dict_kernel<SPV, float, kFiltThreads, 2>), grid, kFiltThreads, sb->filt_smem, st, MN_ARGS, \
-                  (const int32_t *)nullptr);                                                                       \
-        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p, \
-                  (const int32_t *)nullptr);                                                                       \
+        MN_LAUNCH((score_dict_kernel<SPV, float, kFiltThreads, 2>), grid, kFiltThreads, sb->filt_smem, st, MN_ARGS);  \
+        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p); \
         MN_LAUNCH(rescore_kernel<SPV>, n, kRsThreads, 0, st, sb->E, S, sb->maxc, sb->Rptr.p, sb->ncand.p,           \
-                  sb->cand_cols.p, sb->scores.p, sb->rs_scratch.p, sb->need_exact.p, sb->rs_stats.p);              \
-        MN_LAUNCH((score_dict_kernel<SPV, double, kDictThreads, 1>), xgrid, kDictThreads, sb->dict_smem, st, MN_ARGS, \
-                  (const int32_t *)sb->need_exact.p);                                                              \
-        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p, \
-                  (const int32_t *)sb->need_exact.p);                                                              \
+                  sb->cand_cols.p, sb->scores.p, sb->rs_scratch.p, sb->rs_stats.p);                                \
     } while (0)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
@@ -998,7 +983,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
         MN_TRY(sb->scores.alloc((size_t)nmax * sb->maxc));
         MN_TRY(sb->rs_scratch.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * kRsCap));
-        MN_TRY(sb->rs_stats.alloc(2, true)); MN_TRY(sb->need_exact.alloc(nmax, true));
+        MN_TRY(sb->rs_stats.alloc(2, true));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
@@ -1031,7 +1016,6 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
     const int slots = 148 * (sb->exact_only || sb->marginal ? 1 : sb->filt_ctas);
     sb->G = pick_groups(n, ntiles, slots);
-    sb->Gx = std::min(kGcap, ntiles);      // exact pass after the filter: few searches take part, give each many CTAs
     MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
     MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
     // initial score of closure(better), R/mnems.r:135-141
