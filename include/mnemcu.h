@@ -155,8 +155,6 @@ typedef struct {
     int64_t passes_mstats;
     double ms_total, ms_estep, ms_mstats, ms_search, ms_mixture;   /* CUDA-event times */
     double estep_bytes;      /* algorithmic bytes moved by all E-step launches */
-    int64_t cand_rescored;   /* candidates whose score was recomputed in FP64 after the FP32 filter pass */
-    int64_t rescore_overflows; /* (search, greedy iteration) pairs in which the filter could not narrow the field */
 } mnemcu_em_stats;
 
 /* mnem(D, phi = init) EM phase: do_inits for every start, R/mnems.r:1884-2165 (explicit-phi entry :1792-1793).

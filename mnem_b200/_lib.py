@@ -34,8 +34,7 @@ class EmStats(C.Structure):
     _fields_ = [("em_iters", C.c_int64), ("cand_scored", C.c_int64), ("greedy_iters", C.c_int64),
                 ("passes_estep", C.c_int64), ("passes_mstats", C.c_int64), ("ms_total", C.c_double),
                 ("ms_estep", C.c_double), ("ms_mstats", C.c_double), ("ms_search", C.c_double),
-                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double), ("cand_rescored", C.c_int64),
-                ("rescore_overflows", C.c_int64)]
+                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol of include/mnemcu.h

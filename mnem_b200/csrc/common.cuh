@@ -237,9 +237,6 @@ const double *search_score(const SearchBatch *sb);          // [n] nem$score
 const double *search_maxtrace(const SearchBatch *sb);       // [n] max(nem$scores)
 const int32_t *search_niter(const SearchBatch *sb);         // [n]
 const unsigned long long *search_nscored(const SearchBatch *sb);   // [n]
-// totals since search_create: [0] candidates rescored in FP64 after the FP32 filter pass, [1] searches x iterations in
-// which more than the cap qualified (everything rescored)
-int search_rescore_stats(const SearchBatch *sb, unsigned long long out[2]);
 // theta[q][e] = first argmax_j (R_q %*% cols_q)[e, j] with the null column FIRST (null_last = 0, R/mnems.r:447-450)
 // or LAST (null_last = 1, R/mnems_low.r:617-619); W_out (n*E*S) optional.  cols: [n][32] column masks.
 int launch_theta(const double *const *R_dev_ptrs_dev, int n, int E, int S, const uint32_t *cols, int null_last,

@@ -693,10 +693,6 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         cudaMemcpy(en.h_counters, en.d_counters.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost);
         en.stats.cand_scored = (int64_t)en.h_counters[0];
         en.stats.greedy_iters = (int64_t)en.h_counters[1];
-        if (en.sb) {
-            unsigned long long rs[2] = {0, 0};
-            if (search_rescore_stats(en.sb, rs) == 0) { en.stats.cand_rescored = (int64_t)rs[0]; en.stats.rescore_overflows = (int64_t)rs[1]; }
-        }
         *best_out = winner;
         if (stats_out) *stats_out = en.stats;
     }

@@ -23,18 +23,10 @@ constexpr int kRows = 128;     // E-gene rows per score CTA (= threads)
 constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionary (power of two)
 constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
 constexpr int kDictThreads = 512;
-constexpr int kFiltThreads = 384;  // FP32 filter pass: 12 warps per CTA, two CTAs per SM
-constexpr int kRsCap = 64;         // candidates per search rescored exactly after the filter pass
-constexpr int kRsThreads = 512;
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
     int dcap = 0, G = 1;              // dictionary capacity (entries), row groups per search
-    int exact_only = 0;               // skip the FP32 filter, score every candidate in FP64 (MNEMCU_EXACT_SCORES=1)
-    size_t filt_smem = 0;
-    int filt_ctas = 1;                // resident filter CTAs per SM
-    DevBuf<double> rs_scratch;        // [nmax][ntiles][kRsCap]
-    DevBuf<unsigned long long> rs_stats;   // [0] candidates rescored, [1] searches that overflowed the cap
     int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
     double logtype = 2.0;
     size_t dict_smem = 0;
@@ -351,18 +343,8 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
 // (l, l^16), (l, l^8), ...: the same function of the 32 row values, so equal rows give bit-equal sums whatever the
 // candidate kind (exact score ties decide graphs, R/mnems.r:236, 279-283).
 // Dynamic shared memory: T, the per-candidate sums, the masks, the pair-id matrix.
-//
-// VT = double: the exact scores.  VT = float: the FILTER pass -- every table entry is the exact FP64 column sum rounded
-// once to FP32 (rounding is monotone, so a row maximum of rounded entries is the rounded row maximum) and the 32 rows of
-// a tile are added in FP32, which bounds the relative error of a candidate's score by (1 + 5) * 2^-24 (all terms are
-// >= 0).  Look-ups then cost LDS.32 + FMNMX instead of LDS.64 + DSETP + 2 FSEL, the table is half the size (two CTAs per
-// SM), and rescore_kernel below recomputes in FP64 only the few candidates the filter cannot separate from the best.
-template <typename VT> __device__ __forceinline__ VT vmax(VT a, VT b);
-template <> __device__ __forceinline__ double vmax<double>(double a, double b) { return b > a ? b : a; }   // NaN in b never wins
-template <> __device__ __forceinline__ float vmax<float>(float a, float b) { return fmaxf(a, b); }         // same (a is never NaN)
-
-template <int SP, typename VT, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
+template <int SP>
+__global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
     const int32_t *__restrict__ nins, const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks,
     const uint16_t *__restrict__ base_id, const uint16_t *__restrict__ pair_id, const uint32_t *__restrict__ Pcol,
@@ -374,15 +356,14 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
     if (nc == 0) return;
     const int ni = nins[q];
     const int ndq = min(nd[q], dcap);
-    VT *T = reinterpret_cast<VT *>(s_raw);                              // [dcap][32]
+    double *T = reinterpret_cast<double *>(s_raw);                      // [dcap][32]
     uint32_t *dmask = reinterpret_cast<uint32_t *>(T + (size_t)dcap * kDictRows);   // [dcap]
     uint32_t *pid = dmask + ((dcap + 3) & ~3);      // [32][32]: pid[j*32 + u] = byte offset in T of the row of col_j | col_u
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NT / 32;
-    constexpr VT kNegInf = -INFINITY;
-    for (int i = tid; i < ndq; i += NT) dmask[i] = dict_masks[(size_t)q * dcap + i];
+    constexpr int NW = kDictThreads / 32;
+    for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = dict_masks[(size_t)q * dcap + i];
     if (ni > 0)
-        for (int i = tid; i < 1024; i += NT) pid[i] = (uint32_t)pair_id[(size_t)q * 1024 + i] * (uint32_t)(kDictRows * sizeof(VT));
+        for (int i = tid; i < 1024; i += kDictThreads) pid[i] = (uint32_t)pair_id[(size_t)q * 1024 + i] * (kDictRows * 8u);
     const uint32_t bid = lane < S ? base_id[q * 32 + lane] : 0u;
     const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
     const uint32_t pcol = lane < S ? Pcol[q * 32 + lane] : 0u;          // lane = column
@@ -445,34 +426,34 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
                     if ((m0 >> s) & 1u) { MN_KEEP_BRANCH(); w0 += r[s]; }
                     if ((m1 >> s) & 1u) { MN_KEEP_BRANCH(); w1 += r[s]; }
                 }
-                T[ent * kDictRows + lane] = (VT)w0;                   // float: round to nearest, once
-                if (two) T[(ent + NW) * kDictRows + lane] = (VT)w1;
+                T[ent * kDictRows + lane] = w0;
+                if (two) T[(ent + NW) * kDictRows + lane] = w1;
             }
         }
         __syncthreads();
         // the four largest subweights of the current graph in this row: the maximum over the columns a candidate
         // leaves unchanged is the first of them whose column is outside the changed set (full scan only if all
         // four are inside)
-        VT t0 = kNegInf, t1 = kNegInf, t2 = kNegInf, t3 = kNegInf;
+        double t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
         int i0 = 32, i1 = 32, i2 = 32, i3 = 32;              // 32 = no column
         for (int j = 0; j < S; ++j) {
             const int id = __shfl_sync(kFull, bid, j);
-            const VT w = T[id * kDictRows + lane];
+            const double w = T[id * kDictRows + lane];
             if (w > t0) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = t0; i1 = i0; t0 = w; i0 = j; }
             else if (w > t1) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = w; i1 = j; }
             else if (w > t2) { t3 = t2; i3 = i2; t2 = w; i2 = j; }
             else if (w > t3) { t3 = w; i3 = j; }
         }
-        auto unchanged_max = [&](uint32_t Jset) -> VT {
+        auto unchanged_max = [&](uint32_t Jset) -> double {
             const unsigned long long Jx = Jset;
             const bool in0 = (Jx >> i0) & 1ull, in1 = (Jx >> i1) & 1ull, in2 = (Jx >> i2) & 1ull, in3 = (Jx >> i3) & 1ull;
-            VT A = !in0 ? t0 : (!in1 ? t1 : (!in2 ? t2 : t3));
+            double A = !in0 ? t0 : (!in1 ? t1 : (!in2 ? t2 : t3));
             const bool need_scan = in0 && in1 && in2 && in3;
             if (__any_sync(kFull, need_scan)) {
-                VT sc = kNegInf;
+                double sc = -INFINITY;
                 for (int j = 0; j < S; ++j) {
                     const int id = __shfl_sync(kFull, bid, j);
-                    if (!((Jset >> j) & 1u)) sc = vmax<VT>(sc, T[id * kDictRows + lane]);
+                    if (!((Jset >> j) & 1u)) { const double t = T[id * kDictRows + lane]; sc = t > sc ? t : sc; }
                 }
                 if (need_scan) A = sc;
             }
@@ -489,9 +470,9 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
                 const int v = s_vlist[item];
                 const uint32_t zm = __shfl_sync(kFull, zmask, v);
                 const uint32_t Dv = __ballot_sync(kFull, (pcol >> v) & 1u);      // columns j with P[v, j] = 1 (diag included)
-                const VT A = unchanged_max(Dv);
-                const VT A0 = A > (VT)0 ? A : (VT)0;                 // max(0, unchanged columns): the floor of every candidate
-                VT B[32];
+                const double A = unchanged_max(Dv);
+                const double A0 = A > 0.0 ? A : 0.0;                 // max(0, unchanged columns): the floor of every candidate
+                double B[32];
 #pragma unroll
                 for (int u = 0; u < 32; ++u) B[u] = A0;
                 uint32_t m = Dv;
@@ -510,30 +491,31 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
                     const unsigned char *Tl = reinterpret_cast<const unsigned char *>(T + lane);
 #pragma unroll
                     for (int u = 0; u < SP; ++u) {
-                        B[u] = vmax<VT>(B[u], *reinterpret_cast<const VT *>(Tl + ofs[u]));
+                        const double t = *reinterpret_cast<const double *>(Tl + ofs[u]);
+                        B[u] = t > B[u] ? t : B[u];
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 32; ++u) B[u] = (u < SP && ((zm >> u) & 1u)) ? B[u] : (VT)0;
+                for (int u = 0; u < 32; ++u) B[u] = (u < SP && ((zm >> u) & 1u)) ? B[u] : 0.0;
                 // transposed butterfly: afterwards lane l holds the sum over the 32 rows of B[l]
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) {
                     const bool hi = (lane & d) != 0;
 #pragma unroll
                     for (int i = 0; i < d; ++i) {
-                        const VT send = hi ? B[i] : B[i + d];
-                        const VT recv = __shfl_xor_sync(kFull, send, d);
+                        const double send = hi ? B[i] : B[i + d];
+                        const double recv = __shfl_xor_sync(kFull, send, d);
                         B[i] = (hi ? B[i + d] : B[i]) + recv;
                     }
                 }
                 const int off = __shfl_sync(kFull, offv, v);
-                if ((zm >> lane) & 1u) ptile[off + __popc(zm & ((1u << lane) - 1u))] = (double)B[0];
+                if ((zm >> lane) & 1u) ptile[off + __popc(zm & ((1u << lane) - 1u))] = B[0];
                 continue;
             }
             // (3) reversals and deletions (and the single closure "candidate" of the initial score)
             const int cbeg = ni + (item - nv) * kRestChunk, cend = min(nc, cbeg + kRestChunk);
             uint32_t lastJ = 0u;
-            VT A = kNegInf;
+            double A = -INFINITY;
             bool haveA = false;
             for (int c = cbeg; c < cend; ++c) {
                 uint32_t J = cJ[c];
@@ -543,101 +525,20 @@ __global__ void __launch_bounds__(NT, MINB) score_dict_kernel(
                     lastJ = J;
                     haveA = true;
                 }
-                VT best = A;
+                double best = A;
                 while (J) {
                     const int j = __ffs(J) - 1;
                     J &= J - 1;
                     const int id = __shfl_sync(kFull, myid, j);
-                    best = vmax<VT>(best, T[id * kDictRows + lane]);        // NaN never wins, like which.max
+                    const double t = T[id * kDictRows + lane];
+                    best = t > best ? t : best;        // plain compare: NaN never wins, like which.max
                 }
-                VT val = best > (VT)0 ? best : (VT)0;
+                double val = best > 0.0 ? best : 0.0;
                 for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
-                if (lane == 0) ptile[c] = (double)val;
+                if (lane == 0) ptile[c] = val;
             }
         }
         parity ^= 1;
-        __syncthreads();
-    }
-}
-
-// ---- exact rescoring after the FP32 filter pass ------------------------------------------------------------------
-// scores[q][c] holds the filter score a_c of every candidate, |a_c - s_c| <= eps * s_c with eps = 6 * 2^-24 (see
-// score_dict_kernel) and s_c >= 0 the exact score.  The exact maximum is therefore among the candidates with
-// a_c >= a_max * (1 - 2 eps); the window used is 1e-6 (> 2 eps = 7.2e-7), NaN / Inf filter scores always qualify.  Those
-// candidates (typically one to three, plus exact ties) are recomputed here in FP64 with the summation order of the exact
-// kernel -- ascending S-genes per column, rows of a 32-row tile paired (l, l^16), (l, l^8), ..., tiles ascending -- so the
-// values finish_body compares are bit-identical to what score_dict_kernel<double> would have produced; everything else
-// gets -Inf and cannot win.  More than kRsCap qualifying candidates (mass ties): all candidates are recomputed, kRsCap at
-// a time.  grid = searches, block = kRsThreads.
-template <int SP>
-__global__ void __launch_bounds__(kRsThreads) rescore_kernel(int E, int S, int maxc, const double *const *__restrict__ Rptr,
-                                                            const int32_t *__restrict__ ncand,
-                                                            const uint32_t *__restrict__ cand_cols,
-                                                            double *__restrict__ scores, double *__restrict__ scratch,
-                                                            unsigned long long *__restrict__ stats)
-{
-    __shared__ int s_list[kRsCap];
-    __shared__ int s_cnt;
-    __shared__ double s_red[kRsThreads / 32];
-    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = kRsThreads / 32;
-    const int nc = ncand[q];
-    if (nc == 0) return;
-    double *sc = scores + (size_t)q * maxc;
-    const int ntiles = (E + kDictRows - 1) / kDictRows;
-    double mx = -INFINITY;
-    for (int c = tid; c < nc; c += kRsThreads) { const double v = sc[c]; if (v > mx) mx = v; }
-    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(kFull, mx, o); if (t > mx) mx = t; }
-    if (lane == 0) s_red[warp] = mx;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (int w = 0; w < NW; ++w) if (s_red[w] > mx) mx = s_red[w];
-    const double thr = mx - fabs(mx) * 1e-6 - 1e-300;
-    for (int c = tid; c < nc; c += kRsThreads) {
-        const double v = sc[c];
-        if (!(v < thr)) {                                   // NaN and +Inf qualify
-            const int idx = atomicAdd(&s_cnt, 1);
-            if (idx < kRsCap) s_list[idx] = c;
-        } else {
-            sc[c] = -INFINITY;
-        }
-    }
-    __syncthreads();
-    const int total = s_cnt;
-    const bool overflow = total > kRsCap;
-    const int nchunk = overflow ? (nc + kRsCap - 1) / kRsCap : 1;
-    if (tid == 0) {
-        atomicAdd(&stats[0], (unsigned long long)(overflow ? nc : total));
-        if (overflow) atomicAdd(&stats[1], 1ull);
-    }
-    const double *R = Rptr[q];
-    double *part = scratch + (size_t)q * ntiles * kRsCap;
-    for (int chunk = 0; chunk < nchunk; ++chunk) {
-        const int ns = overflow ? min(kRsCap, nc - chunk * kRsCap) : total;
-        for (int tile = warp; tile < ntiles; tile += NW) {
-            const int row = tile * kDictRows + lane;
-            double r[SP];
-#pragma unroll
-            for (int s2 = 0; s2 < SP; ++s2) r[s2] = (s2 < S && row < E) ? R[(size_t)s2 * E + row] : 0.0;
-            for (int i = 0; i < ns; ++i) {
-                const int c = overflow ? chunk * kRsCap + i : s_list[i];
-                const uint32_t mycol = lane < S ? cand_cols[((size_t)q * maxc + c) * 32 + lane] : 0u;
-                double best = -INFINITY;
-                for (int j = 0; j < S; ++j) {
-                    const double w = col_sum<SP>(r, __shfl_sync(kFull, mycol, j));
-                    best = w > best ? w : best;             // NaN never wins
-                }
-                double val = best > 0.0 ? best : 0.0;       // rowMaxs(cbind(0, score))
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
-                if (lane == 0) part[(size_t)tile * kRsCap + i] = val;
-            }
-        }
-        __syncthreads();
-        if (tid < ns) {
-            double t = 0.0;
-            for (int et = 0; et < ntiles; ++et) t += part[(size_t)et * kRsCap + tid];
-            sc[overflow ? chunk * kRsCap + tid : s_list[tid]] = t;
-        }
         __syncthreads();
     }
 }
@@ -897,30 +798,10 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
         return 0;
     }
     dim3 grid(sb->G, n);
-    const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
-    dim3 rgrid((sb->maxc + 255) / 256, n);
-#define MN_ARGS sb->E, S, sb->maxc, sb->dcap, sb->G, sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p,  \
-                sb->base_id.p, sb->pair_id.p, sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p
-    if (sb->exact_only) {
-#define MN_SCORE(SPV) MN_LAUNCH((score_dict_kernel<SPV, double, kDictThreads, 1>), grid, kDictThreads, sb->dict_smem, st, MN_ARGS)
-        if (S <= 8) MN_SCORE(8);
-        else if (S <= 16) MN_SCORE(16);
-        else if (S <= 24) MN_SCORE(24);
-        else if (S <= 28) MN_SCORE(28);
-        else if (S <= 30) MN_SCORE(30);
-        else MN_SCORE(32);
-#undef MN_SCORE
-        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p);
-        return 0;
-    }
-    // filter pass in FP32, then the exact FP64 scores of the candidates it cannot separate from the best
 #define MN_SCORE(SPV)                                                                                              \
-    do {                                                                                                           \
-        MN_LAUNCH((score_dict_kernel<SPV, float, kFiltThreads, 2>), grid, kFiltThreads, sb->filt_smem, st, MN_ARGS);  \
-        MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p); \
-        MN_LAUNCH(rescore_kernel<SPV>, n, kRsThreads, 0, st, sb->E, S, sb->maxc, sb->Rptr.p, sb->ncand.p,           \
-                  sb->cand_cols.p, sb->scores.p, sb->rs_scratch.p, sb->rs_stats.p);                                \
-    } while (0)
+    MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, sb->G,   \
+              sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->pair_id.p,       \
+              sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
     else if (S <= 24) MN_SCORE(24);
@@ -928,15 +809,16 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
     else if (S <= 30) MN_SCORE(30);
     else MN_SCORE(32);
 #undef MN_SCORE
-#undef MN_ARGS
+    const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
+    dim3 rgrid((sb->maxc + 255) / 256, n);
+    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p);
     return 0;
 }
 
 constexpr int kGcap = 32;          // most row groups per search (partial sums kept per group)
 
-// `sms` CTA slots are resident at a time (one per SM for the FP64 table, two for the FP32 one), so the launch runs in
-// ceil(G*n/slots) rounds of ceil(tiles/G) tiles each: pick the G that minimises the product for the current number of
-// active searches.
+// One CTA fits per SM (the table fills shared memory), so the launch runs in ceil(G*n/SMs) rounds of ceil(tiles/G)
+// tiles each: pick the G that minimises the product for the current number of active searches.
 static int pick_groups(int n_active, int ntiles, int sms)
 {
     int best = 1;
@@ -960,17 +842,12 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         const int fit = (int)((232448 - 4096 - 512) / (kDictRows * 8 + 4));
         sb->dcap = std::max(1, std::min(need, fit));
         sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
-        sb->filt_smem = (size_t)sb->dcap * kDictRows * 4 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
-        sb->filt_ctas = 2 * (sb->filt_smem + 1024 + 256) <= 233472 ? 2 : 1;      // 228 KB per SM, 1 KB reserved per CTA
-        const char *ex = getenv("MNEMCU_EXACT_SCORES");
-        sb->exact_only = (ex && ex[0] == '1') ? 1 : 0;
-#define MN_ATTR(SPV)                                                                                               \
-        cudaFuncSetAttribute(score_dict_kernel<SPV, double, kDictThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                             (int)sb->dict_smem);                                                                  \
-        cudaFuncSetAttribute(score_dict_kernel<SPV, float, kFiltThreads, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                             (int)sb->filt_smem);
-        MN_ATTR(8) MN_ATTR(16) MN_ATTR(24) MN_ATTR(28) MN_ATTR(30) MN_ATTR(32)
-#undef MN_ATTR
+        cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        cudaFuncSetAttribute(score_dict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
     }
     auto body = [&]() -> int {
         MN_TRY(sb->Rptr.alloc(nmax));
@@ -982,8 +859,6 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->n_active.alloc(2, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
         MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
         MN_TRY(sb->scores.alloc((size_t)nmax * sb->maxc));
-        MN_TRY(sb->rs_scratch.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * kRsCap));
-        MN_TRY(sb->rs_stats.alloc(2, true));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
@@ -1014,8 +889,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
     const int S = sb->S;
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
-    const int slots = 148 * (sb->exact_only || sb->marginal ? 1 : sb->filt_ctas);
-    sb->G = pick_groups(n, ntiles, slots);
+    sb->G = pick_groups(n, ntiles, 148);
     MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
     MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
     // initial score of closure(better), R/mnems.r:135-141
@@ -1045,7 +919,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
             if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
             // iteration 0's finish is the initial score (mode 0): it accepts nothing by design
             if (pending > 0 && sb->h_n_active[ps] == 0) done = true;
-            else if (pending > 0) sb->G = pick_groups(sb->h_n_active[ps], ntiles, slots);
+            else if (pending > 0) sb->G = pick_groups(sb->h_n_active[ps], ntiles, 148);
         }
         pending = it;
     }
@@ -1063,11 +937,6 @@ const double *search_score(const SearchBatch *sb) { return sb->oldscore.p; }
 const double *search_maxtrace(const SearchBatch *sb) { return sb->maxtrace.p; }
 const int32_t *search_niter(const SearchBatch *sb) { return sb->niter.p; }
 const unsigned long long *search_nscored(const SearchBatch *sb) { return sb->nscored.p; }
-int search_rescore_stats(const SearchBatch *sb, unsigned long long out[2])
-{
-    MN_CU(cudaMemcpy(out, sb->rs_stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    return 0;
-}
 
 }  // namespace mn
 
