@@ -23,6 +23,7 @@ constexpr int kRows = 128;     // E-gene rows per score CTA (= threads)
 constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionary (power of two)
 constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
 constexpr int kDictThreads = 512;
+constexpr int kChains = 2;         // independent iteration chains per search_run (see SearchBatch)
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
@@ -36,8 +37,14 @@ struct SearchBatch {
     DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow;
     DevBuf<double> partial, scores, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored;
-    int32_t *h_n_active = nullptr;   // pinned: [0], [1] moves accepted in even / odd iterations, [2] dictionary overflow
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    // Chains: the searches are dealt round-robin (by pair) to kChains groups that iterate independently on their own
+    // streams, so that one chain's single-CTA-per-search phases (argmax + candidate generation), launch gaps and
+    // scoring tails are filled by the scoring kernels of the others.
+    int32_t *h_n_active = nullptr;   // pinned: [2*h + (it & 1)] moves accepted by chain h in iteration it, [2*kChains] overflow
+    DevBuf<int32_t> qlist;            // [nmax] search ids, chain by chain
+    cudaStream_t cst[kChains] = {};   // streams of chains 1.. (chain 0 runs on the caller's stream)
+    cudaEvent_t ev[kChains][2] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kChains] = {};
 };
 
 // ---- candidate generation + mask dictionary ----------------------------------------------------------------
@@ -53,7 +60,7 @@ struct SearchBatch {
 // For insertions the "changed" set written to cand_J is the whole row of v (the columns the one-step closure may
 // touch): candidates that share v then share the set, and the scoring kernel reuses their unchanged-column maximum.
 template <int NT>
-__device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, const uint32_t *Prow,
+__device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int mode, const uint32_t *Prow,
                                                   const int32_t *active, uint32_t *__restrict__ Pcol,
                                                   uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
                                                   int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind,
@@ -68,7 +75,7 @@ __device__ __forceinline__ void gen_body(int S, int maxc, int dcap, int mode, co
     __shared__ int s_warp[NT / 32];
     constexpr int kPer = kDictHash / NT;          // hash slots per thread in the dense-id scan
     static_assert(kPer * NT == kDictHash, "thread count must divide the hash size");
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
     if (!active[q]) {
         if (tid == 0) { ncand[q] = 0; if (nd) { nd[q] = 0; nins[q] = 0; } }
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int
                                                   uint32_t *dict_masks, int32_t *nd, uint16_t *cand_id,
                                                   uint16_t *base_id, uint16_t *pair_id, int32_t *nins, int32_t *overflow)
 {
-    gen_body<256>(S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id,
+    gen_body<256>(blockIdx.x, S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id,
                   base_id, pair_id, nins, overflow);
 }
 
@@ -348,10 +355,11 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
     const int32_t *__restrict__ nins, const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks,
     const uint16_t *__restrict__ base_id, const uint16_t *__restrict__ pair_id, const uint32_t *__restrict__ Pcol,
-    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial)
+    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial,
+    const int32_t *__restrict__ qlist)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int q = blockIdx.y, g = blockIdx.x;
+    const int q = qlist ? qlist[blockIdx.y] : blockIdx.y, g = blockIdx.x;
     const int nc = ncand[q];
     if (nc == 0) return;
     const int ni = nins[q];
@@ -408,7 +416,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     const int nv = s_nv;
     int parity = 0;
     const int ntiles = (E + kDictRows - 1) / kDictRows;
-    for (int tile = g; tile < ntiles; tile += G) {
+    for (int tile = g; tile < ntiles; tile += (int)gridDim.x) {       // G row groups = gridDim.x
         const int row = tile * kDictRows + lane;
         double *ptile = partial + ((size_t)q * ntiles + tile) * maxc;   // this tile's per-candidate sums
         {
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
 
 // ---- argmax, accept rule, graph update -------------------------------------------------------------------
 template <int NT>
-__device__ __forceinline__ void finish_body(int S, int maxc, int etiles, int mode, const int32_t *ncand,
+__device__ __forceinline__ void finish_body(int q, int S, int maxc, int etiles, int mode, const int32_t *ncand,
                                             const double *__restrict__ partial, const uint32_t *cand_cols,
                                             const uint32_t *Pcol, uint32_t *Prow, int32_t *active, double *oldscore,
                                             double *maxtrace, int32_t *niter, unsigned long long *nscored,
@@ -553,7 +561,7 @@ __device__ __forceinline__ void finish_body(int S, int maxc, int etiles, int mod
 {
     __shared__ double s_best[NT];
     __shared__ int s_idx[NT];
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     if (!active[q]) return;
     const int nc = ncand[q];
     double best = -INFINITY;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles
                                                      double *oldscore, double *maxtrace, int32_t *niter,
                                                      unsigned long long *nscored, int32_t *n_active)
 {
-    finish_body<128>(S, maxc, etiles, mode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter, nscored,
+    finish_body<128>(blockIdx.x, S, maxc, etiles, mode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter, nscored,
                      n_active);
 }
 
@@ -632,12 +640,14 @@ __global__ void __launch_bounds__(kFgThreads) finish_gen_kernel(int S, int maxc,
                                                          double *maxtrace, int32_t *niter, unsigned long long *nscored,
                                                          int32_t *n_active, uint32_t *cand_J, uint32_t *dict_masks,
                                                          int32_t *nd, uint16_t *cand_id, uint16_t *base_id,
-                                                         uint16_t *pair_id, int32_t *nins, int32_t *overflow)
+                                                         uint16_t *pair_id, int32_t *nins, int32_t *overflow,
+                                                         const int32_t *__restrict__ qlist)
 {
-    finish_body<kFgThreads>(S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
+    const int q = qlist[blockIdx.x];                 // the searches of one chain (see search_run)
+    finish_body<kFgThreads>(q, S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
                      nscored, n_active);
     __syncthreads();       // the accepted graph (Prow) and the active flag are visible to the whole CTA
-    gen_body<kFgThreads>(S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd,
+    gen_body<kFgThreads>(q, S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd,
                          cand_id, base_id, pair_id, nins, overflow);
 }
 
@@ -769,9 +779,10 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
 // scores[q][c] = sum over the row tiles, ascending -- fully parallel over candidates, so the single-CTA finish step
 // reads one value per candidate instead of one per (candidate, tile)
 __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles, const int32_t *__restrict__ ncand,
-                                                           const double *__restrict__ partial, double *__restrict__ scores)
+                                                           const double *__restrict__ partial, double *__restrict__ scores,
+                                                           const int32_t *__restrict__ qlist)
 {
-    const int q = blockIdx.y;
+    const int q = qlist ? qlist[blockIdx.y] : blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand[q]) return;
     double sc = 0.0;
@@ -788,20 +799,22 @@ static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
     return 0;
 }
 
-static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
+// scores of the `n` searches listed in qlist (device; nullptr = searches 0..n-1) with G row groups each
+static int launch_score_dict(SearchBatch *sb, int n, int G, const int32_t *qlist, cudaStream_t st)
 {
     const int S = sb->S;
     if (sb->marginal) {   // the dictionary trick needs a row MAXIMUM; the marginal score re-sums the changed columns per candidate
         MN_TRY(launch_score(sb, n, st));
         dim3 rg((sb->maxc + 255) / 256, n);
-        MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p);
+        MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p,
+                  (const int32_t *)nullptr);
         return 0;
     }
-    dim3 grid(sb->G, n);
+    dim3 grid(G, n);
 #define MN_SCORE(SPV)                                                                                              \
-    MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, sb->G,   \
+    MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, G,       \
               sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->pair_id.p,       \
-              sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p)
+              sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p, qlist)
     if (S <= 8) MN_SCORE(8);
     else if (S <= 16) MN_SCORE(16);
     else if (S <= 24) MN_SCORE(24);
@@ -811,7 +824,7 @@ static int launch_score_dict(SearchBatch *sb, int n, cudaStream_t st)
 #undef MN_SCORE
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
     dim3 rgrid((sb->maxc + 255) / 256, n);
-    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p);
+    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p, qlist);
     return 0;
 }
 
@@ -856,7 +869,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->adj_rows.alloc((size_t)nmax * 32)); MN_TRY(sb->closed_rows.alloc((size_t)nmax * 32));
         MN_TRY(sb->closed_cols.alloc((size_t)nmax * 32));
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
-        MN_TRY(sb->n_active.alloc(2, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
+        MN_TRY(sb->n_active.alloc(2 * kChains, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
+        MN_TRY(sb->qlist.alloc(nmax, true));
         MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
         MN_TRY(sb->scores.alloc((size_t)nmax * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
@@ -864,10 +878,15 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
         MN_TRY(sb->nins.alloc(nmax, true));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
-        MN_CU(cudaMallocHost((void **)&sb->h_n_active, 4 * sizeof(int32_t)));
-        sb->h_n_active[0] = sb->h_n_active[1] = sb->h_n_active[2] = 0;
-        MN_CU(cudaEventCreateWithFlags(&sb->ev[0], cudaEventDisableTiming));
-        MN_CU(cudaEventCreateWithFlags(&sb->ev[1], cudaEventDisableTiming));
+        MN_CU(cudaMallocHost((void **)&sb->h_n_active, (2 * kChains + 1) * sizeof(int32_t)));
+        for (int i = 0; i <= 2 * kChains; ++i) sb->h_n_active[i] = 0;
+        for (int h = 0; h < kChains; ++h) {
+            MN_CU(cudaEventCreateWithFlags(&sb->ev[h][0], cudaEventDisableTiming));
+            MN_CU(cudaEventCreateWithFlags(&sb->ev[h][1], cudaEventDisableTiming));
+            MN_CU(cudaEventCreateWithFlags(&sb->ev_join[h], cudaEventDisableTiming));
+            if (h > 0) MN_CU(cudaStreamCreateWithFlags(&sb->cst[h], cudaStreamNonBlocking));
+        }
+        MN_CU(cudaEventCreateWithFlags(&sb->ev_fork, cudaEventDisableTiming));
         return 0;
     };
     int rc = body();
@@ -880,7 +899,12 @@ void search_destroy(SearchBatch *sb)
 {
     if (!sb) return;
     if (sb->h_n_active) cudaFreeHost(sb->h_n_active);
-    for (int i = 0; i < 2; ++i) if (sb->ev[i]) cudaEventDestroy(sb->ev[i]);
+    for (int h = 0; h < kChains; ++h) {
+        for (int i = 0; i < 2; ++i) if (sb->ev[h][i]) cudaEventDestroy(sb->ev[h][i]);
+        if (sb->ev_join[h]) cudaEventDestroy(sb->ev_join[h]);
+        if (sb->cst[h]) cudaStreamDestroy(sb->cst[h]);
+    }
+    if (sb->ev_fork) cudaEventDestroy(sb->ev_fork);
     delete sb;
 }
 
@@ -889,42 +913,76 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
     const int S = sb->S;
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
-    sb->G = pick_groups(n, ntiles, 148);
     MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
     MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
     // initial score of closure(better), R/mnems.r:135-141
     MN_TRY(launch_gen(sb, n, 0, st));
-    MN_TRY(launch_score_dict(sb, n, st));
-    // iteration it: [finish(it-1) + gen(it)] -> score(it).  The host learns the number of searches that accepted a move
-    // one iteration late (the copy of iteration it is awaited while iteration it+1 is already queued), so the GPU never
-    // idles on a host round trip; the one surplus iteration at the end finds every search inactive and does nothing.
-    const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
-    int pending = -1;                      // iteration whose n_active copy is in flight
-    bool done = false;
-    for (int it = 0; it < hard_cap && !done; ++it) {
-        const int slot = it & 1;
-        MN_CU(cudaMemsetAsync(sb->n_active.p + slot, 0, sizeof(int32_t), st));
-        // n_active[slot] counts the searches that accept a move in this fused finish
-        MN_LAUNCH(finish_gen_kernel, n, kFgThreads, 0, st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
-                  sb->scores.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
-                  sb->niter.p, sb->nscored.p, sb->n_active.p + slot, sb->cand_J.p, sb->dict_masks.p, sb->nd.p,
-                  sb->cand_id.p, sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);
-        MN_TRY(launch_score_dict(sb, n, st));
-        MN_CU(cudaMemcpyAsync(sb->h_n_active + slot, sb->n_active.p + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        MN_CU(cudaMemcpyAsync(sb->h_n_active + 2, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        MN_CU(cudaEventRecord(sb->ev[slot], st));
-        if (pending >= 0) {
-            const int ps = pending & 1;
-            MN_CU(cudaEventSynchronize(sb->ev[ps]));
-            if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
-            // iteration 0's finish is the initial score (mode 0): it accepts nothing by design
-            if (pending > 0 && sb->h_n_active[ps] == 0) done = true;
-            else if (pending > 0) sb->G = pick_groups(sb->h_n_active[ps], ntiles, 148);
+    MN_TRY(launch_score_dict(sb, n, pick_groups(n, ntiles, 148), nullptr, st));
+    // Chains.  Searches come in pairs (2p: empty start, 2p+1: previous graph, R/mnems.r:2036-2073) with very different
+    // lengths, so pairs -- not single searches -- are dealt round-robin.
+    const int nch = (sb->marginal || n < 4) ? 1 : kChains;
+    struct Chain { int n = 0, off = 0, pending = -1, G = 1; bool done = false; cudaStream_t st = nullptr; };
+    Chain ch[kChains];
+    {
+        std::vector<int32_t> ql;
+        for (int h = 0; h < nch; ++h) {
+            ch[h].off = (int)ql.size();
+            for (int q = 0; q < n; ++q)
+                if ((q >> 1) % nch == h) ql.push_back(q);
+            ch[h].n = (int)ql.size() - ch[h].off;
+            ch[h].st = h == 0 ? st : sb->cst[h];
+            ch[h].G = pick_groups(ch[h].n, ntiles, 148);
+            ch[h].done = ch[h].n == 0;
         }
-        pending = it;
+        MN_CU(cudaMemcpyAsync(sb->qlist.p, ql.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        MN_CU(cudaStreamSynchronize(st));              // ql is a stack vector; also: the initial scores are complete
+    }
+    for (int h = 1; h < nch; ++h) {                   // fork (the sync above already ordered everything before it)
+        MN_CU(cudaEventRecord(sb->ev_fork, st));
+        MN_CU(cudaStreamWaitEvent(ch[h].st, sb->ev_fork, 0));
+    }
+    // iteration it of a chain: [finish(it-1) + gen(it)] -> score(it).  The host learns the number of searches that
+    // accepted a move one iteration late (the copy of iteration it is awaited while iteration it+1 is already queued), so
+    // the GPU never idles on a host round trip; the one surplus iteration at the end finds every search of the chain
+    // inactive and does nothing.
+    const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
+    int32_t *h_over = sb->h_n_active + 2 * kChains;
+    auto all_done = [&]() { for (int h = 0; h < nch; ++h) if (!ch[h].done) return false; return true; };
+    for (int it = 0; it < hard_cap && !all_done(); ++it) {
+        const int slot = it & 1;
+        for (int h = 0; h < nch; ++h) {
+            Chain &c = ch[h];
+            if (c.done) continue;
+            int32_t *na = sb->n_active.p + 2 * h + slot;
+            const int32_t *ql = sb->qlist.p + c.off;
+            MN_CU(cudaMemsetAsync(na, 0, sizeof(int32_t), c.st));
+            // *na counts the searches of the chain that accept a move in this fused finish
+            MN_LAUNCH(finish_gen_kernel, c.n, kFgThreads, 0, c.st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
+                      sb->scores.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
+                      sb->niter.p, sb->nscored.p, na, sb->cand_J.p, sb->dict_masks.p, sb->nd.p, sb->cand_id.p,
+                      sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p, ql);
+            MN_TRY(launch_score_dict(sb, c.n, c.G, ql, c.st));
+            MN_CU(cudaMemcpyAsync(sb->h_n_active + 2 * h + slot, na, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+            MN_CU(cudaMemcpyAsync(h_over, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
+            MN_CU(cudaEventRecord(sb->ev[h][slot], c.st));
+            if (c.pending >= 0) {
+                const int ps = c.pending & 1;
+                MN_CU(cudaEventSynchronize(sb->ev[h][ps]));
+                if (*h_over) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+                // iteration 0's finish is the initial score (mode 0): it accepts nothing by design
+                const int acc = sb->h_n_active[2 * h + ps];
+                if (c.pending > 0 && acc == 0) c.done = true;
+                else if (c.pending > 0) c.G = pick_groups(acc, ntiles, 148);
+            }
+            c.pending = it;
+        }
+    }
+    for (int h = 1; h < nch; ++h) {                   // join
+        MN_CU(cudaEventRecord(sb->ev_join[h], ch[h].st));
+        MN_CU(cudaStreamWaitEvent(st, sb->ev_join[h], 0));
     }
     MN_CU(cudaStreamSynchronize(st));
-    if (sb->h_n_active[2]) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+    if (*h_over) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
     return 0;
