@@ -23,7 +23,7 @@ constexpr int kRows = 128;     // E-gene rows per score CTA (= threads)
 constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionary (power of two)
 constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
 constexpr int kDictThreads = 512;
-constexpr int kChains = 2;         // independent iteration chains per search_run (see SearchBatch)
+constexpr int kChains = 4;         // most independent iteration chains per search_run (see SearchBatch)
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
@@ -920,7 +920,9 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     MN_TRY(launch_score_dict(sb, n, pick_groups(n, ntiles, 148), nullptr, st));
     // Chains.  Searches come in pairs (2p: empty start, 2p+1: previous graph, R/mnems.r:2036-2073) with very different
     // lengths, so pairs -- not single searches -- are dealt round-robin.
-    const int nch = (sb->marginal || n < 4) ? 1 : kChains;
+    int want = 2;                                      // default number of chains
+    if (const char *e = getenv("MNEMCU_CHAINS")) want = std::max(1, std::min(kChains, atoi(e)));
+    const int nch = (sb->marginal || n < 2 * want) ? 1 : want;
     struct Chain { int n = 0, off = 0, pending = -1, G = 1; bool done = false; cudaStream_t st = nullptr; };
     Chain ch[kChains];
     {
