@@ -162,14 +162,11 @@ int launch_build_masks(const mnemcu_ctx *cx, const uint32_t *clo, const int32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// M-step sufficient statistics.  Layout Dcol[cp][Epad]: a cell's E-genes are contiguous, thread t owns the
-// E-gene pair (2t, 2t+1) and walks the cells of one chunk of one segment in ascending order, so loads are
-// coalesced 16-byte reads and the responsibility gamma[m][cp] is warp-uniform (broadcast from shared memory).
-// Chunk partials are combined in ascending chunk order by mstats_reduce_kernel: no atomics, bit-reproducible.
-//
-// grid = (E-gene tiles, chunks, groups of MT pairs), block = tpb threads.
+// M-step sufficient statistics.  Layout Dcol[cp][Epad]: a cell's E-genes are contiguous, so a CTA streams its
+// slice of D with coalesced 16-byte copies; the cells of one chunk of one segment are contracted against the
+// responsibilities gamma[m][cp] on the FP64 tensor cores (see mstats_kernel).  Chunk partials are combined in
+// ascending chunk order by mstats_reduce_kernel: no atomics, bit-reproducible.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSub = 64;   // cells whose weights are staged in shared memory at a time (chunks are multiples of 64 cells)
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
@@ -184,47 +181,68 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
 
-constexpr int kStCells = 8;    // cells per pipeline stage
+constexpr int kStCells = 8;    // cells per pipeline stage (two k-steps of the FP64 MMA)
 constexpr int kStages = 3;     // stages in flight: 2 ahead of the one being consumed
+constexpr int kMsWarpE = 64;   // E-genes per warp: 8 n-tiles of 8
+constexpr int kMsThreads = 128;
 
-// grid = (groups of MT pairs, E-gene tiles, chunks), block = tpb threads.  A 3-stage cp.async ring keeps 16 cells
-// (64 KB per CTA at 256 threads) in flight ahead of the FMAs: each stage holds, for 8 cells, the CTA's slice of D
-// (16 bytes per thread and cell, straight from HBM to shared memory, L1 bypassed) and the 8 x MT weights.
-template <int MT>
-__global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict__ Dcol, int Epad,
-                                                        const double *__restrict__ gam, int M, int Cp,
-                                                        const int32_t *__restrict__ chunk_cp0,
-                                                        const int32_t *__restrict__ chunk_n, double *__restrict__ partial)
+// D += A * B on the FP64 tensor cores, m8n8k4: A 8x4 row-major (a = A[lane/4][lane%4]), B 4x8 column-major
+// (b = B[lane%4][lane/4]), C/D 8x8 (c0, c1 = C[lane/4][2*(lane%4) + {0, 1}]).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
 {
-    constexpr int MTP = (MT + 1) & ~1;                 // even row length: weights are fetched as double2
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// grid = (groups of pairs, E-gene tiles, chunks), block = tpb threads (a multiple of 32, <= 128); warp w owns the 64
+// E-genes [tile0 + 64 w, +64).  The contraction over the cells of the chunk is a GEMM
+//     Rt[pair][e] += gamma[pair][cell] * D[cell][e]          (M = pairs in 8-row tiles, N = E-genes, K = cells)
+// issued as m8n8k4 FP64 MMAs: one instruction does 256 FMAs, so the FP64 pipe runs at its peak rate with an eighth
+// of the issue slots the scalar DFMA form needs (ncu on the DFMA form: FP64 pipe 53 %, issue-bound).  A 3-stage
+// cp.async ring keeps 16 cells (32 KB per CTA) in flight ahead of the MMAs: each stage holds, for 8 cells, the CTA's
+// slice of D (16 bytes per thread and cell, straight from HBM to shared memory, L1 bypassed) and the 8 x MT8*8 weights.
+// Row strides are padded to 8 mod 16 doubles so that the 4 x 8 fragment loads are conflict-free (2 wavefronts).
+template <int MT8>
+__global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__restrict__ Dcol, int Epad,
+                                                               const double *__restrict__ gam, int M, int MT, int Cp,
+                                                               const int32_t *__restrict__ chunk_cp0,
+                                                               const int32_t *__restrict__ chunk_n,
+                                                               double *__restrict__ partial)
+{
+    constexpr int GSTR = (MT8 * 8) % 16 == 0 ? MT8 * 8 + 8 : MT8 * 8;      // == 8 (mod 16)
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    const int tpb = blockDim.x, tid = threadIdx.x;
-    double2 *sD = reinterpret_cast<double2 *>(s_dyn);                                   // [kStages][kStCells][tpb]
-    double *sG = reinterpret_cast<double *>(sD + (size_t)kStages * kStCells * tpb);     // [kStages][kStCells][MTP]
+    const int tpb = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ESTR = 2 * tpb + 8;                                           // == 8 (mod 16): tpb is a multiple of 32
+    double *sD = reinterpret_cast<double *>(s_dyn);                         // [kStages][kStCells][ESTR]
+    double *sG = sD + (size_t)kStages * kStCells * ESTR;                    // [kStages][kStCells][GSTR]
     const int chunk = blockIdx.z;
     const int m0 = blockIdx.x * MT;                     // groups vary fastest: the CTAs that re-read a tile run together
-    const int e = 2 * (blockIdx.y * tpb + tid);
+    const int etile0 = 2 * blockIdx.y * tpb;
+    const int e = etile0 + 2 * tid;                     // the pair of E-genes this thread stages
     const bool live = e < Epad;
     const int cp0 = chunk_cp0[chunk];
     const int n = chunk_n[chunk];                       // multiple of 64
-    double ax[MT], ay[MT];
+    double acc[8][MT8][2];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) { ax[m] = 0.0; ay[m] = 0.0; }
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int mt = 0; mt < MT8; ++mt) { acc[nt][mt][0] = 0.0; acc[nt][mt][1] = 0.0; }
     const double2 *p = reinterpret_cast<const double2 *>(Dcol + (size_t)cp0 * Epad + (live ? e : 0));
     const size_t stride = (size_t)Epad / 2;
 
     auto issue = [&](int st, int c0) {
         if (c0 < n) {
 #pragma unroll
-            for (int j = 0; j < kStCells; ++j) cp_async16(&sD[(st * kStCells + j) * tpb + tid], p + (size_t)(c0 + j) * stride);
-            for (int i = tid; i < kStCells * MTP; i += tpb) {
+            for (int j = 0; j < kStCells; ++j)
+                cp_async16(&sD[(size_t)(st * kStCells + j) * ESTR + 2 * tid], p + (size_t)(c0 + j) * stride);
+            for (int i = tid; i < kStCells * MT8 * 8; i += tpb) {
                 const int m = i / kStCells, c = i - m * kStCells;
-                double *dst = &sG[(st * kStCells + c) * MTP + m];
+                double *dst = &sG[(st * kStCells + c) * GSTR + m];
                 if (m < MT && m0 + m < M) {
                     if (gam) cp_async8(dst, gam + (size_t)(m0 + m) * Cp + cp0 + c0 + c);
                     else *dst = 1.0;
                 } else {
-                    *dst = 0.0;
+                    *dst = 0.0;                          // padding rows of the last 8-pair tile
                 }
             }
         }
@@ -234,33 +252,38 @@ __global__ void __launch_bounds__(256, 2) mstats_kernel(const double *__restrict
     issue(0, 0);
     issue(1, kStCells);
     int st = 0;
+    const int kq = lane & 3, gq = lane >> 2;            // k index / row-or-column index of this lane's fragment element
     for (int c0 = 0; c0 < n; c0 += kStCells) {
         issue(st == 0 ? 2 : st - 1, c0 + 2 * kStCells);     // (st + 2) % 3
         cp_async_wait<2>();
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < kStCells; ++j) {
-            const double2 d = sD[(st * kStCells + j) * tpb + tid];
-            const double *g = &sG[(st * kStCells + j) * MTP];
+        for (int ks = 0; ks < kStCells / 4; ++ks) {
+            const double *gd = sG + (st * kStCells + ks * 4 + kq) * GSTR + gq;
+            const double *dd = sD + (size_t)(st * kStCells + ks * 4 + kq) * ESTR + warp * kMsWarpE + gq;
+            double a[MT8];
 #pragma unroll
-            for (int m = 0; m < MT; m += 2) {
-                const double2 gg = *reinterpret_cast<const double2 *>(g + m);       // broadcast LDS.128
-                ax[m] = fma(d.x, gg.x, ax[m]);
-                ay[m] = fma(d.y, gg.x, ay[m]);
-                if (m + 1 < MT) {
-                    ax[m + 1] = fma(d.x, gg.y, ax[m + 1]);
-                    ay[m + 1] = fma(d.y, gg.y, ay[m + 1]);
-                }
+            for (int mt = 0; mt < MT8; ++mt) a[mt] = gd[mt * 8];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const double b = dd[nt * 8];
+#pragma unroll
+                for (int mt = 0; mt < MT8; ++mt) dmma884(acc[nt][mt][0], acc[nt][mt][1], a[mt], b);
             }
         }
         __syncthreads();
         st = st == 2 ? 0 : st + 1;
     }
-    if (live) {
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
-            if (m0 + m < M)
-                *reinterpret_cast<double2 *>(partial + ((size_t)chunk * M + m0 + m) * Epad + e) = make_double2(ax[m], ay[m]);
+    for (int nt = 0; nt < 8; ++nt) {
+        const int eo = etile0 + warp * kMsWarpE + nt * 8 + 2 * kq;
+#pragma unroll
+        for (int mt = 0; mt < MT8; ++mt) {
+            const int m = mt * 8 + gq;
+            if (eo < Epad && m < MT && m0 + m < M)
+                *reinterpret_cast<double2 *>(partial + ((size_t)chunk * M + m0 + m) * Epad + eo) =
+                    make_double2(acc[nt][mt][0], acc[nt][mt][1]);
+        }
     }
 }
 
@@ -344,21 +367,21 @@ int launch_theta_groups(const mnemcu_ctx *cx, const double *Rg, int M, const uin
 
 size_t mstats_partial_elems(const mnemcu_ctx *cx, int M) { return (size_t)cx->nchunk * M * cx->Epad; }
 
-template <int MT>
-static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, double *partial, cudaStream_t st)
+template <int MT8>
+static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, int MT, double *partial, cudaStream_t st)
 {
-    const int pairs = cx->Epad / 2;
-    int tpb = 256;
+    const int pairs = cx->Epad / 2;                    // E-gene pairs: one per staging thread
+    int tpb = kMsThreads;
     while (tpb > 32 && tpb / 2 >= pairs) tpb /= 2;
     dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
-    constexpr int MTP = (MT + 1) & ~1;
-    const size_t smem = (size_t)kStages * kStCells * ((size_t)tpb * sizeof(double2) + MTP * sizeof(double));
+    constexpr int GSTR = (MT8 * 8) % 16 == 0 ? MT8 * 8 + 8 : MT8 * 8;
+    const size_t smem = (size_t)kStages * kStCells * ((size_t)(2 * tpb + 8) + GSTR) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
-        MN_CU(cudaFuncSetAttribute(mstats_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        MN_CU(cudaFuncSetAttribute(mstats_kernel<MT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr_set = true;
     }
-    MN_LAUNCH(mstats_kernel<MT>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, M, cx->Cp, cx->chunk_cp0, cx->chunk_n,
+    MN_LAUNCH(mstats_kernel<MT8>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, M, MT, cx->Cp, cx->chunk_cp0, cx->chunk_n,
               partial);
     return 0;
 }
@@ -366,15 +389,14 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, doubl
 int launch_mstats(const mnemcu_ctx *cx, const double *gam, int M, double *partial, double *R, cudaStream_t st)
 {
     MN_ARG(M >= 1 && M <= 32, "M-step statistics serve 1..32 pairs per launch");
-    const int groups = (M + 19) / 20;
+    // pairs per CTA: up to 24 (three 8-pair MMA tiles; 48 FP64 accumulators per lane)
+    const int groups = (M + 23) / 24;
     const int MT = (M + groups - 1) / groups;
     int rc;
-    switch (MT) {
-#define MN_CASE(v) case v: rc = launch_mstats_t<v>(cx, gam, M, partial, st); break;
-        MN_CASE(1) MN_CASE(2) MN_CASE(3) MN_CASE(4) MN_CASE(5) MN_CASE(6) MN_CASE(7) MN_CASE(8) MN_CASE(9) MN_CASE(10)
-        MN_CASE(11) MN_CASE(12) MN_CASE(13) MN_CASE(14) MN_CASE(15) MN_CASE(16) MN_CASE(17) MN_CASE(18) MN_CASE(19)
-#undef MN_CASE
-        default: rc = launch_mstats_t<20>(cx, gam, M, partial, st); break;
+    switch ((MT + 7) / 8) {
+        case 1: rc = launch_mstats_t<1>(cx, gam, M, MT, partial, st); break;
+        case 2: rc = launch_mstats_t<2>(cx, gam, M, MT, partial, st); break;
+        default: rc = launch_mstats_t<3>(cx, gam, M, MT, partial, st); break;
     }
     if (rc) return rc;
     dim3 grid((cx->E + 127) / 128, cx->S, M);
