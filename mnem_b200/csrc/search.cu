@@ -828,7 +828,7 @@ static int launch_score_dict(SearchBatch *sb, int n, int G, const int32_t *qlist
     return 0;
 }
 
-constexpr int kGcap = 32;          // most row groups per search (partial sums kept per group)
+constexpr int kGcap = 64;          // most row groups (CTAs) per search
 
 // One CTA fits per SM (the table fills shared memory), so the launch runs in ceil(G*n/SMs) rounds of ceil(tiles/G)
 // tiles each: pick the G that minimises the product for the current number of active searches.
@@ -836,7 +836,8 @@ static int pick_groups(int n_active, int ntiles, int sms)
 {
     int best = 1;
     long best_cost = -1;
-    for (int G = 1; G <= std::min(kGcap, ntiles); ++G) {
+    static const int gcap = getenv("MNEMCU_GCAP") ? std::max(1, std::min(kGcap, atoi(getenv("MNEMCU_GCAP")))) : kGcap;
+    for (int G = 1; G <= std::min(gcap, ntiles); ++G) {
         const long cost = (long)((G * (long)n_active + sms - 1) / sms) * ((ntiles + G - 1) / G);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
     }
