@@ -23,17 +23,21 @@ __device__ __forceinline__ double pow_b(double b, double lb, double y)
 }
 
 // One cell: y_i = mw_i * b^(L_i - shift); returns column sum; xs[] receives y_i.
-template <bool kComplete>
-__device__ __forceinline__ double cell_terms(const double *L, long long si, int k, const double *mw, bool shift_on,
+// KT > 0: k known at compile time (loops unroll, the small per-cell arrays stay in registers); KT = 0: runtime k.
+template <bool kComplete, int KT = 0>
+__device__ __forceinline__ double cell_terms(const double *L, long long si, int k_rt, const double *mw, bool shift_on,
                                              double shrink_k, double b, double lb, double *xs, double *xraw)
 {
+    const int k = KT > 0 ? KT : k_rt;
     double xmax = -INFINITY;
+#pragma unroll
     for (int i = 0; i < k; ++i) {
         const double x = L[i * si];
         xraw[i] = x;
         if (x > xmax) xmax = x;
     }
     double cs = 0.0;
+#pragma unroll
     for (int i = 0; i < k; ++i) {
         double v = xraw[i];
         if (kComplete && shift_on) v = v - (xmax - shrink_k);      // R/mnems.r:1427
@@ -97,13 +101,16 @@ __device__ __forceinline__ double block_sum_256(double v, double *sm)
 }
 
 // partial[(slot*nb + blockIdx.x)*(k+1) + i] : i < k row sums of gamma, i == k log-likelihood
-template <bool kComplete>
-__global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, int k, double b, double lb,
+template <bool kComplete, int KT>
+__global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, int k_rt, double b, double lb,
                                                         double shrink_k, double *__restrict__ partial)
 {
     __shared__ double sm[8];
     const int slot = blockIdx.y;
-    double mw[MNEMCU_MAX_K], lmw[MNEMCU_MAX_K], xs[MNEMCU_MAX_K], xraw[MNEMCU_MAX_K], rs[MNEMCU_MAX_K];
+    constexpr int KA = KT > 0 ? KT : MNEMCU_MAX_K;
+    const int k = KT > 0 ? KT : k_rt;
+    double mw[KA], lmw[KA], xs[KA], xraw[KA], rs[KA];
+#pragma unroll
     for (int i = 0; i < k; ++i) {
         mw[i] = s.mw[slot] ? s.mw[slot][i] : 1.0 / k;
         lmw[i] = log(mw[i]) / lb;                                   // R/mnems_low.r:545
@@ -118,8 +125,9 @@ __global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, i
             // getLL(complete = TRUE): sum_i Z_ic * (L_ic + log_b mw_i), Z = getAffinity(complete = TRUE)
             double cs;
             if (k == 1) { xraw[0] = L[0]; xs[0] = 1.0; cs = 1.0; }
-            else cs = cell_terms<true>(L, g.si, k, mw, shift_on, shrink_k, b, lb, xs, xraw);
+            else cs = cell_terms<true, KT>(L, g.si, k, mw, shift_on, shrink_k, b, lb, xs, xraw);
             double t = 0.0;
+#pragma unroll
             for (int i = 0; i < k; ++i) {
                 double z = xs[i] / cs;
                 if (isnan(z)) z = 0.0;
@@ -129,8 +137,9 @@ __global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, i
             ll += t;
         } else {
             // getLL: log(sum_i mw_i b^L_ic)/log(b), un-stabilised (R/mnems_low.r:547-549)
-            const double cs = cell_terms<false>(L, g.si, k, mw, false, 0.0, b, lb, xs, xraw);
+            const double cs = cell_terms<false, KT>(L, g.si, k, mw, false, 0.0, b, lb, xs, xraw);
             ll += log(cs) / lb;
+#pragma unroll
             for (int i = 0; i < k; ++i) {
                 double z = k == 1 ? 1.0 : xs[i] / cs;
                 if (isnan(z)) z = 0.0;
@@ -139,26 +148,42 @@ __global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, i
         }
     }
     double *out = partial + ((size_t)slot * gridDim.x + blockIdx.x) * (k + 1);
-    for (int i = 0; i <= k; ++i) {
-        const double t = block_sum_256(i < k ? rs[i] : ll, sm);
+#pragma unroll
+    for (int i = 0; i < k; ++i) {
+        const double t = block_sum_256(rs[i], sm);
         if (threadIdx.x == 0) out[i] = t;
     }
+    const double t = block_sum_256(ll, sm);
+    if (threadIdx.x == 0) out[k] = t;
 }
 
-// one warp per slot: block partials in ascending order, then mw <- rs / sum(rs), NA guard, ll
-__global__ void mix_finalize_kernel(MixSlots s, int k, int nb, const double *__restrict__ partial)
+// one CTA per slot: block partials in ascending order (staged through shared memory a chunk at a time, so the
+// sequential sums read from shared memory instead of chasing nb dependent global loads), then mw <- rs / sum(rs),
+// NA guard, ll
+constexpr int kFinThreads = 256;
+constexpr int kFinStage = 3072;          // doubles staged per chunk
+__global__ void __launch_bounds__(kFinThreads) mix_finalize_kernel(MixSlots s, int k, int nb, const double *__restrict__ partial)
 {
+    __shared__ double sp[kFinStage];
     const int slot = blockIdx.x;
-    const int lane = threadIdx.x;
-    double v = 0.0, ll = 0.0;
-    if (lane < k) {
-        const double *p = partial + (size_t)slot * nb * (k + 1) + lane;
-        for (int bb = 0; bb < nb; ++bb) v += p[(size_t)bb * (k + 1)];
+    const int tid = threadIdx.x, lane = tid;
+    const int w = k + 1;                                       // k row sums + the log-likelihood per block
+    const int rows_per = kFinStage / w;
+    const double *p = partial + (size_t)slot * nb * w;
+    double v = 0.0;                                            // thread i <= k: running sum of column i
+    for (int b0 = 0; b0 < nb; b0 += rows_per) {
+        const int nr = min(rows_per, nb - b0);
+        for (int i = tid; i < nr * w; i += kFinThreads) sp[i] = p[(size_t)b0 * w + i];
+        __syncthreads();
+        if (tid < w)
+            for (int r = 0; r < nr; ++r) v += sp[r * w + tid];
+        __syncthreads();
     }
-    if (lane == 0) {
-        const double *p = partial + (size_t)slot * nb * (k + 1) + k;
-        for (int bb = 0; bb < nb; ++bb) ll += p[(size_t)bb * (k + 1)];
-    }
+    if (tid < w) sp[tid] = v;                                  // k may be 32: column k (the ll) then lives in warp 1
+    __syncthreads();
+    if (tid >= 32) return;
+    v = lane < k ? sp[lane] : 0.0;
+    const double ll = sp[k];
     double tot = 0.0;
     for (int i = 0; i < k; ++i) tot += __shfl_sync(kFull, v, i);
     double m = v / tot;
@@ -199,9 +224,24 @@ int launch_mix_stats_geom(const MixSlots &s, const MixGeom &g, int k, int comple
     double lb, sk;
     consts(logtype, k, &lb, &sk);
     dim3 grid(kMixBlocks, s.n);
-    if (complete) MN_LAUNCH(mix_stats_kernel<true>, grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch);
-    else MN_LAUNCH(mix_stats_kernel<false>, grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch);
-    MN_LAUNCH(mix_finalize_kernel, s.n, 32, 0, st, s, k, kMixBlocks, scratch);
+#define MN_MIX(KT)                                                                                                 \
+    do {                                                                                                           \
+        if (complete) MN_LAUNCH((mix_stats_kernel<true, KT>), grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch); \
+        else MN_LAUNCH((mix_stats_kernel<false, KT>), grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch);         \
+    } while (0)
+    switch (k) {       // the common mixture sizes get a compile-time k (registers instead of local-memory arrays)
+        case 1: MN_MIX(1); break;
+        case 2: MN_MIX(2); break;
+        case 3: MN_MIX(3); break;
+        case 4: MN_MIX(4); break;
+        case 5: MN_MIX(5); break;
+        case 6: MN_MIX(6); break;
+        case 7: MN_MIX(7); break;
+        case 8: MN_MIX(8); break;
+        default: MN_MIX(0); break;
+    }
+#undef MN_MIX
+    MN_LAUNCH(mix_finalize_kernel, s.n, kFinThreads, 0, st, s, k, kMixBlocks, scratch);
     return 0;
 }
 
