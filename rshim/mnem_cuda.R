@@ -8,11 +8,18 @@
 mnem_cuda_enabled <- function() identical(getOption("mnem.backend", "r"), "cuda")
 
 ## replaces the `lapply(seq_len(starts), do_inits)` of R/mnems.r:2166-2170 for inference = "em", search = "greedy",
-## marginal = FALSE, single-knock-down columns; `init` is mnem()'s phi list (R/mnems.r:1790-1793)
-mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0) {
-    pert <- as.integer(colnames(data))                       # after modData(): "1".."S"
-    S <- length(unique(pert))
-    ctx <- mnemcu_context(data, pert, S, device)
+## marginal = FALSE; `init` is mnem()'s phi list (R/mnems.r:1790-1793).  Multi-knock-down columns ("1_3") or an
+## explicit Rho take the Rho path (R/mnems_low.r:613-616, 896-904).
+mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0, Rho = NULL) {
+    if (is.null(Rho) && any(grepl("_", colnames(data)))) Rho <- getRho(data)
+    if (is.null(Rho)) {
+        pert <- as.integer(colnames(data))                   # after modData(): "1".."S"
+        S <- length(unique(pert))
+        ctx <- mnemcu_context(data, pert, S, device)
+    } else {
+        S <- nrow(Rho)
+        ctx <- mnemcu_context_rho(data, Rho, device)
+    }
     out <- mnemcu_em(ctx, init, complete, logtype)
     for (s in seq_along(out$limits)) {                       # names the rest of mnem() expects (R/mnems.r:2153-2163)
         out$limits[[s]]$k <- length(init[[s]])
@@ -33,7 +40,7 @@ mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0) {
 ## In getAffinity() (R/mnems.r:1390), soft path with norm = TRUE:
 ##   if (mnem_cuda_enabled()) return(mnemcu_getAffinity(x, if (is.null(mw)) rep(1, nrow(x))/nrow(x) else mw,
 ##                                                      affinity, complete, logtype))
-## In scoreAdj() (R/mnems.r:416) for method = "llr", marginal = FALSE, weights = NULL, D already collapsed:
-##   if (mnem_cuda_enabled()) return(mnemcu_scoreAdj(D, adj, trans.close))
+## In scoreAdj() (R/mnems.r:416) for method = "llr", weights = NULL, D already collapsed:
+##   if (mnem_cuda_enabled()) return(mnemcu_scoreAdj(D, adj, trans.close, marginal, logtype))
 ## In nem() (R/mnems.r:52) after doMean (line 107), search = "greedy", runs = 1:
-##   if (mnem_cuda_enabled()) { fit <- mnemcu_nem(D, start); ... assemble list(adj, score, scores, subtopo, ...) }
+##   if (mnem_cuda_enabled()) { fit <- mnemcu_nem(D, start, marginal, logtype); ... assemble list(adj, score, ...) }

@@ -97,6 +97,18 @@ SEXP mnemcu_context(NumericMatrix data, IntegerVector pert, int S, int device = 
     UNPROTECT(1);
     return p;
 }
+// Rho = getRho(data) (R/mnems_low.r:308-324): S x C, several knock-downs per column allowed
+// [[Rcpp::export]]
+SEXP mnemcu_context_rho(NumericMatrix data, NumericMatrix Rho, int device = 0)
+{
+    if (Rho.ncol() != data.ncol()) stop("Rho must have one column per column of data");
+    mnemcu_ctx *cx = nullptr;
+    chk(mnemcu_ctx_create_rho(data.begin(), data.nrow(), data.ncol(), Rho.begin(), Rho.nrow(), device, &cx));
+    SEXP p = PROTECT(R_MakeExternalPtr(cx, R_NilValue, R_NilValue));
+    R_RegisterCFinalizerEx(p, ctx_finalizer, TRUE);
+    UNPROTECT(1);
+    return p;
+}
 static mnemcu_ctx *ctx_of(SEXP p)
 {
     mnemcu_ctx *cx = static_cast<mnemcu_ctx *>(R_ExternalPtrAddr(p));
@@ -134,19 +146,22 @@ SEXP mnemcu_doMean(SEXP ctx, Nullable<NumericVector> weights)
 }
 
 // [[Rcpp::export]]
-List mnemcu_scoreAdj(NumericMatrix R, NumericMatrix adj, bool trans_close)
+List mnemcu_scoreAdj(NumericMatrix R, NumericMatrix adj, bool trans_close, bool marginal = false, double logtype = 2.0)
 {
     const int E = R.nrow(), S = R.ncol();
     std::vector<uint8_t> g = to_u8(adj);
     double score = 0;
     IntegerVector theta(E);
     NumericMatrix W(E, S);
-    chk(mnemcu_score_adj(R.begin(), E, S, g.data(), 1, trans_close, &score, theta.begin(), W.begin()));
+    if (marginal)
+        chk(mnemcu_score_adj_marginal(R.begin(), E, S, g.data(), 1, trans_close, logtype, &score, theta.begin(), W.begin()));
+    else
+        chk(mnemcu_score_adj(R.begin(), E, S, g.data(), 1, trans_close, &score, theta.begin(), W.begin()));
     return List::create(_["score"] = score, _["subtopo"] = theta, _["subweights"] = W);
 }
 
 // [[Rcpp::export]]
-List mnemcu_nem(NumericMatrix R, Nullable<NumericMatrix> start)
+List mnemcu_nem(NumericMatrix R, Nullable<NumericMatrix> start, bool marginal = false, double logtype = 2.0)
 {
     const int E = R.nrow(), S = R.ncol();
     std::vector<uint8_t> st, adj((size_t)S * S);
@@ -155,8 +170,12 @@ List mnemcu_nem(NumericMatrix R, Nullable<NumericMatrix> start)
     double score = 0, mtr = 0;
     int32_t nit = 0;
     int64_t nsc = 0;
-    chk(mnemcu_nem_greedy(R.begin(), E, S, start.isNotNull() ? st.data() : nullptr, 1, adj.data(), theta.begin(), &score,
-                          &mtr, &nit, &nsc));
+    if (marginal)
+        chk(mnemcu_nem_greedy_marginal(R.begin(), E, S, start.isNotNull() ? st.data() : nullptr, 1, logtype, adj.data(),
+                                       theta.begin(), &score, &mtr, &nit, &nsc));
+    else
+        chk(mnemcu_nem_greedy(R.begin(), E, S, start.isNotNull() ? st.data() : nullptr, 1, adj.data(), theta.begin(),
+                              &score, &mtr, &nit, &nsc));
     NumericMatrix A(S, S);
     from_u8(adj, A);
     return List::create(_["adj"] = A, _["score"] = score, _["scores"] = NumericVector::create(mtr), _["subtopo"] = theta);
