@@ -836,8 +836,7 @@ static int pick_groups(int n_active, int ntiles, int sms)
 {
     int best = 1;
     long best_cost = -1;
-    static const int gcap = getenv("MNEMCU_GCAP") ? std::max(1, std::min(kGcap, atoi(getenv("MNEMCU_GCAP")))) : kGcap;
-    for (int G = 1; G <= std::min(gcap, ntiles); ++G) {
+    for (int G = 1; G <= std::min(kGcap, ntiles); ++G) {
         const long cost = (long)((G * (long)n_active + sms - 1) / sms) * ((ntiles + G - 1) / G);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = G; }
     }

@@ -106,7 +106,8 @@ def test_getll_app_rda_known_answers(key):
 
 
 @pytest.mark.parametrize("k,complete,logtype", [(1, False, 2), (2, False, 2), (3, True, 2), (5, True, 2), (4, False, np.e),
-                                                (3, True, 10)])
+                                                (3, True, 10), (8, True, 2), (9, False, 2), (13, True, 2), (32, True, 2),
+                                                (32, False, 2)])
 def test_affinity_and_ll_random(k, complete, logtype):
     rng = np.random.default_rng(k)
     L = rng.normal(size=(k, 3001)) * 40

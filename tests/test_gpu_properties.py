@@ -130,3 +130,58 @@ def test_greedy_search_at_config5_shape():
     assert np.array_equal(got["adj"], want["adj"]) and np.array_equal(got["subtopo"], want["theta"])
     assert got["n_iter"] == want["n_iter"] and got["n_scored"] == want["n_raw"]
     assert abs(got["score"] - want["score"]) <= 1e-12 * abs(want["score"])
+
+
+def test_config5_full_size_properties():
+    """BASELINE config 5 at full size (30 S-genes x 2000 E-genes x 1 000 020 cells, k = 5; 2 x 16 GB in HBM), 3 starts:
+    run-to-run determinism, monotone accepted likelihood, the winner's probs reproduced by getProbs from its
+    (phi, theta), doMean linearity, and the E-step checked against the oracle on a 2000-cell slice."""
+    sim = simdata.make_config(5)
+    init = simdata.init_phi(sim["S"], sim["k"], 3, seed=2005)
+    with mb.Context.synthetic(sim) as cx:
+        a = mb.em_run(cx, init, complete=True)
+        b = mb.em_run(cx, init, complete=True, batch=2)
+        for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
+            assert np.array_equal(a[key], b[key]), key
+        for s in range(3):
+            assert (np.diff(a["lls"][s]) >= 0).all() and a["ll"][s] == a["lls"][s].max()
+            for g in a["adj"][s]:
+                assert np.array_equal(mb.transitive_reduction(g), g)
+        w = a["best"]
+        res = [dict(adj=a["adj"][w][i], subtopo=a["theta"][w][i]) for i in range(5)]
+        pr = mb.getProbs(a["probs"][w], 5, cx, res, mw=a["mw"][w], complete=True)
+        assert np.array_equal(pr["probs"], a["probs"][w])
+        n = 2000
+        D = cx.read_data(500000, n)
+        assert np.array_equal(D, simdata.host_data(sim, 500000, n))
+        want = orc.get_probs(D, sim["pert"][500000:500000 + n], sim["S"], a["adj"][w], a["theta"][w], np.zeros((5, n)), None,
+                             complete=True)
+        np.testing.assert_allclose(a["probs"][w][:, 500000:500000 + n], want["probs"], rtol=1e-12, atol=1e-12)
+        rng = np.random.default_rng(1)
+        w1, w2 = rng.random(sim["C"]), rng.random(sim["C"])
+        R1, R2, R12 = mb.doMean(cx, w1), mb.doMean(cx, w2), mb.doMean(cx, w1 + 3.0 * w2)
+        np.testing.assert_allclose(R12, R1 + 3.0 * R2, rtol=1e-10, atol=1e-7)
+        # the planted mixture is recovered: hard assignments are far purer than chance
+        post = mb.getAffinity(a["probs"][w], mw=a["mw"][w], complete=True)
+        hard = post.argmax(0)
+        purity = sum(np.bincount(hard[sim["comp"] == t], minlength=5).max() for t in range(5)) / sim["C"]
+        assert purity > 0.35
+
+
+def test_config4_shape_model_selection():
+    """BASELINE config 4 shape (24 S-genes, 41 E-genes each + 16 uninformative = 1000, three planted components), fewer
+    cells: mnemk() over k = 1..4 with getIC() (R/mnems.r:1477-1529, 1560-1574) -- the criterion is finite for every k,
+    its arithmetic matches the formula recomputed from the fits, and the chosen k minimises it."""
+    cfg = dict(simdata.CONFIGS[4])
+    cfg["C"] = 30000
+    sim = simdata.make_config(cfg, seed=1004)
+    with mb.Context.synthetic(sim) as cx:
+        out = mb.mnemk(cx, ks=(1, 2, 3, 4), starts=2, complete=True, seed=3)
+    assert set(out["ics"]) == {1, 2, 3, 4} and all(np.isfinite(v) for v in out["ics"].values())
+    assert out["k"] == min(out["ics"], key=lambda q: out["ics"][q])
+    assert out["lls"][3] > out["lls"][1]                           # three planted components beat a single network
+    fit = out["best"]
+    k = out["k"]
+    fpar = sum(int((orc.mytc(c["phi"]) - np.eye(24, dtype=int) != 0).sum()) for c in fit["comp"]) + k * sim["E"] + (k - 1)
+    ic = np.log(sim["C"]) * fpar - 2 * np.max(fit["ll"]) * np.log(2)
+    assert abs(ic - out["ics"][k]) <= 1e-9 * abs(ic)
