@@ -293,6 +293,28 @@ def test_em_small_gaussian(batch):
     check_em(sim, D, init, complete=False, batch=batch)
 
 
+def test_em_many_pairs_few_cells():
+    """20 and 30 (start, component) pairs per pass on a small matrix: the E-step then splits the E-gene range over up to
+    8 warps of a CTA and combines their partial sums through shared memory (up to 112 KB).  With k = 5 on 1200 cells the
+    greedy decisions are rounding-level ties (oracle margin 1e-16), so the fit is pinned against the one-start-per-pass
+    run (bit-identical: a start's result does not depend on what shares its passes) and the E-step against the oracle."""
+    sim = simdata.make_config(dict(S=8, Egenes=40, C=1200, mw=[0.2] * 5, k=5, starts=6, uninform=0), seed=31)
+    D = simdata.host_data(sim) + np.random.default_rng(7).normal(size=(sim["E"], sim["C"])) * 0.5
+    init = simdata.init_phi(8, 5, 6, seed=8)
+    with mb.Context(D, sim["pert"]) as cx:
+        one = mb.em_run(cx, init, complete=True, batch=1, max_iter_guard=12)
+        for batch in (4, 6):
+            r = mb.em_run(cx, init, complete=True, batch=batch, max_iter_guard=12)
+            for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
+                assert np.array_equal(r[key], one[key]), (batch, key)
+        s = 2
+        want = orc.get_probs(D, sim["pert"], 8, one["adj"][s], one["theta"][s], one["probs"][s], one["mw"][s], complete=True)
+        res = [dict(adj=one["adj"][s][i], subtopo=one["theta"][s][i]) for i in range(5)]
+        got = mb.getProbs(one["probs"][s], 5, cx, res, mw=one["mw"][s], complete=True)
+        close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
+        close(one["probs"][s], want["probs"], rtol=1e-11, atol=1e-11)
+
+
 def test_em_config2_shape_complete():
     """BASELINE config 2 shape (S=10, E=100, ~10k cells, k=3), 6 starts, complete = TRUE."""
     sim = simdata.make_config(2)

@@ -26,9 +26,11 @@ def test_em_is_deterministic_and_batch_independent(big):
     a = mb.em_run(cx, init, complete=True, batch=4)
     b = mb.em_run(cx, init, complete=True, batch=4)
     c = mb.em_run(cx, init, complete=True, batch=1)
+    d = mb.em_run(cx, init, complete=True, batch=6)           # 30 (start, component) pairs per pass
     for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
         assert np.array_equal(a[key], b[key]), key            # bit-reproducible run to run
         assert np.array_equal(a[key], c[key]), key            # sharing passes between starts changes nothing
+        assert np.array_equal(a[key], d[key]), key
     assert a["best"] == b["best"] == c["best"]
     for s in range(init.shape[0]):
         lls = a["lls"][s]
