@@ -107,8 +107,8 @@ static int launch_estep_t(const mnemcu_ctx *cx, const uint32_t *maskT, int M, co
     const int eper = ((cx->E + esplit - 1) / esplit + 31) / 32 * 32;
     size_t smem = esplit > 1 ? (size_t)groups * (esplit - 1) * MT * 32 * sizeof(double2) : 0;
     static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {     // small C: up to 7 partial-sum slabs of MT x 32 double2 (112 KB at MT = 32)
-        MN_CU(cudaFuncSetAttribute(estep_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 32 * 32 * 16));
+    if (!attr_set && smem > 48 * 1024) {     // small C: up to 7 partial-sum slabs of MT x 32 double2 (70 KB at MT = 20)
+        MN_CU(cudaFuncSetAttribute(estep_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 20 * 32 * 16));
         attr_set = true;
     }
     MN_LAUNCH(estep_kernel<MT>, cx->nblk, 32 * groups * esplit, smem, st, cx->Dblk, cx->E, maskT, cx->blk_seg, M, eper,
@@ -119,9 +119,10 @@ static int launch_estep_t(const mnemcu_ctx *cx, const uint32_t *maskT, int M, co
 int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairPtrs &out, cudaStream_t st)
 {
     MN_ARG(M >= 1 && M <= 32, "E-step serves 1..32 (start, component) pairs per launch");
-    // Pairs per warp: all of them, up to 32 (64 FP64 accumulators per lane: 125 registers up to 20 pairs, 167 at 30),
-    // so D is read once whatever the number of pairs.
-    const int groups = (M + 31) / 32;
+    // Pairs per warp: up to 20 (40 FP64 accumulators per lane, 125 registers); above that two warps of the same CTA
+    // split the pairs and the second one re-reads the block from L1/L2, not from HBM.  (Measured at 30 pairs, cfg5: one
+    // warp with 60 accumulators needs 167 registers -> 12 warps per SM and 4.58 ms per pass; two warps of 15: 4.26 ms.)
+    const int groups = (M + 19) / 20;
     const int MT = (M + groups - 1) / groups;
     // Few blocks (small C): split the E-gene range over up to 8 warps so that every SM still has loads in flight.
     int esplit = 1;
@@ -131,10 +132,8 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
 #define MN_CASE(v) case v: return launch_estep_t<v>(cx, maskT, M, out, esplit, st);
         MN_CASE(1) MN_CASE(2) MN_CASE(3) MN_CASE(4) MN_CASE(5) MN_CASE(6) MN_CASE(7) MN_CASE(8) MN_CASE(9) MN_CASE(10)
         MN_CASE(11) MN_CASE(12) MN_CASE(13) MN_CASE(14) MN_CASE(15) MN_CASE(16) MN_CASE(17) MN_CASE(18) MN_CASE(19)
-        MN_CASE(20) MN_CASE(21) MN_CASE(22) MN_CASE(23) MN_CASE(24) MN_CASE(25) MN_CASE(26) MN_CASE(27) MN_CASE(28)
-        MN_CASE(29) MN_CASE(30) MN_CASE(31)
 #undef MN_CASE
-        default: return launch_estep_t<32>(cx, maskT, M, out, esplit, st);
+        default: return launch_estep_t<20>(cx, maskT, M, out, esplit, st);
     }
 }
 
