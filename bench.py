@@ -24,6 +24,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# EM loop iterations per start of the seeded benchmark fits (measured on the GPU path, which the oracle matches iteration
+# for iteration at the sizes it can run): the CPU arm cannot afford to run a fit to convergence, so it evaluates its
+# fitted cost model at this many iterations per start
+MEAN_EM_ITERS = {1: 4.0, 2: 6.0, 3: 10.0, 4: 10.0, 5: 12.96}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -102,10 +107,10 @@ def make_workload(args):
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference (R cannot be installed in this image)
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_sample(sim, init, n_threads, cells):
-    """EM iterations/s of the CPU restatement on a bounded sample: the first `cells` cells of the same data, one EM
-    start per thread, INIT phase + exactly one EM loop iteration each (max_iter_guard = 1), with the reference's
-    redundant recomputation switched on (faithful_cost)."""
+def cpu_sample(sim, init, n_threads, cells, guard=1):
+    """One bounded run of the CPU restatement: the first `cells` cells of the same data, one EM start per thread, INIT
+    phase + exactly `guard` EM loop iterations each (max_iter_guard), with the reference's redundant recomputation
+    switched on (faithful_cost).  Returns wall seconds and counts."""
     import oracle as orc
     from mnem_b200 import simdata
     cells = min(cells, sim["C"])
@@ -114,10 +119,42 @@ def cpu_sample(sim, init, n_threads, cells):
     ph = init[:n_threads]
     t0 = time.time()
     r = orc.mnem_em(D, pert, sim["S"], ph, complete=sim["complete"], nthreads=n_threads, faithful_cost=True,
-                    max_iter_guard=1)
+                    max_iter_guard=guard)
     dt = time.time() - t0
-    return dict(value=float(r["n_iter"].sum() / dt), seconds=dt, em_iters=int(r["n_iter"].sum()),
-                cand_scored=int(r["n_scored"].sum()), cells=cells, starts=len(ph))
+    return dict(seconds=dt, em_iters=int(r["n_iter"].sum()), cand_scored=int(r["n_scored"].sum()), cells=cells,
+                starts=len(ph))
+
+
+def cpu_extrapolated(sim, init, n_threads, cells, mean_iters):
+    """EM iterations/s of the CPU restatement for the FULL workload, from three bounded samples.
+
+    Per start the reference spends  T(C) = INIT(C) + n * EM(C)  with INIT(C) = aI*C (theta-free E-step: passes over the
+    cells only) and EM(C) = aE*C + b (passes over the cells plus 2k greedy searches, whose cost does not depend on C).
+    Samples: (C/2, 1 EM iteration), (C', 1), (C', 2) with C' = `cells` give aI, aE, b; the value reported is
+    n_threads * n / T(C_full) for n = `mean_iters` EM iterations per start."""
+    c2 = min(cells, sim["C"])
+    c1 = max(1, c2 // 2)
+    r11 = cpu_sample(sim, init, n_threads, c1, 1)
+    r21 = cpu_sample(sim, init, n_threads, c2, 1)
+    r22 = cpu_sample(sim, init, n_threads, c2, 2)
+    t11, t21, t22 = r11["seconds"], r21["seconds"], r22["seconds"]
+    slope = max(0.0, (t21 - t11) / max(1, c2 - c1))                 # aI + aE
+    b = max(0.0, t21 - slope * c2)
+    em2 = max(1e-9, t22 - t21)                                      # EM(c2) = aE*c2 + b
+    aE = max(0.0, (em2 - b) / c2)
+    aI = max(0.0, slope - aE)
+    Cf = sim["C"]
+    t_init, t_em = aI * Cf, aE * Cf + b
+    T = t_init + mean_iters * t_em
+    value = r21["starts"] * mean_iters / T
+    return dict(value=float(value), seconds=t11 + t21 + t22, t_init_full=t_init, t_em_full=t_em, b_search=b,
+                cells=(c1, c2), starts=r21["starts"], mean_iters=mean_iters,
+                cand_scores_per_s=r22["cand_scored"] / max(1e-9, t22),
+                sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) in parallel: three bounded "
+                        "samples -- first %d cells with 1 EM iteration (%.1f s), first %d cells with 1 (%.1f s) and 2 (%.1f s) "
+                        "EM iterations, redundant passes kept -- fitted to T = INIT(C) + n*EM(C), INIT = aI*C, EM = aE*C + b "
+                        "(b: the searches), and evaluated at C = %d cells, n = %.2f EM iterations per start: INIT %.3g s, "
+                        "EM iteration %.3g s per start" % (r21["starts"], c1, t11, c2, t21, t22, Cf, mean_iters, t_init, t_em)))
 
 
 def run_reference(args):
@@ -127,22 +164,21 @@ def run_reference(args):
     sim, init, name = make_workload(args)
     import oracle as orc
     nthr = min(os.cpu_count() or 1, sim["starts"], orc.lib().orc_max_threads())
-    cells = args.cpu_cells or max(2000, sim["C"] // 64)
+    cells = args.cpu_cells or max(2000, sim["C"] // 128)
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_sample(sim, init, nthr, cells)
+        r = cpu_extrapolated(sim, init, nthr, cells, MEAN_EM_ITERS.get(args.config, 10.0))
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
-    sample = ("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R): %d starts in parallel, first %d of %d cells, "
-              "INIT + 1 EM iteration each, redundant passes kept" % (vals[0]["starts"], vals[0]["cells"], sim["C"]))
+    sample = vals[-1]["sample"]
     line = {"impl": "reference", "metric": "em_iterations_per_s", "value": v, "unit": "EM iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean([x["seconds"] for x in vals])), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "EM iterations/s", "cores": nthr, "kind": "port", "sample": sample},
-            "cand_scores_per_s": float(np.mean([x["cand_scored"] / x["seconds"] for x in vals])),
+            "cand_scores_per_s": float(np.mean([x["cand_scores_per_s"] for x in vals])),
             "e2e": {"value": v, "unit": "EM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -284,12 +320,10 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cells = args.cpu_cells or max(2000, Cn // 64)
-        c = cpu_sample(sim, init, 1, cells)
-        cpu = {"value": c["value"], "unit": "EM iterations/s", "cores": 1, "kind": "port",
-               "sample": "oracle port (C restatement, not R): 1 start, first %d of %d cells, INIT + 1 EM iteration, "
-                         "redundant passes kept; %.1f s" % (c["cells"], Cn, c["seconds"]),
-               "cand_scores_per_s": c["cand_scored"] / c["seconds"]}
+        cells = args.cpu_cells or max(2000, Cn // 128)
+        c = cpu_extrapolated(sim, init, 1, cells, em_iters / max(1, sim["starts"]))
+        cpu = {"value": c["value"], "unit": "EM iterations/s", "cores": 1, "kind": "port", "sample": c["sample"],
+               "cand_scores_per_s": c["cand_scores_per_s"]}
     if rank == 0:
         line = {"metric": "em_iterations_per_s", "value": value, "unit": "EM iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
