@@ -115,7 +115,12 @@ struct Engine {
     int32_t *h_chg = nullptr;
     unsigned long long *h_counters = nullptr;
     size_t kCp = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // phase timers: event pairs recorded on the stream and read back at the next point where the host waits for the
+    // device anyway (no extra synchronisation on the critical path)
+    static constexpr int kTimers = 16;
+    cudaEvent_t tev[kTimers][2] = {};
+    double *tacc[kTimers] = {};
+    int ntimer = 0;
     mnemcu_em_stats stats{};
 
     ~Engine()
@@ -125,8 +130,9 @@ struct Engine {
         if (h_mw) cudaFreeHost(h_mw);
         if (h_chg) cudaFreeHost(h_chg);
         if (h_counters) cudaFreeHost(h_counters);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < kTimers; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (tev[i][j]) cudaEventDestroy(tev[i][j]);
     }
 
     double *buf(int slot, int which) { return Lbuf.p + ((size_t)slot * 3 + which) * kCp; }
@@ -177,20 +183,33 @@ struct Engine {
         MN_CU(cudaMallocHost((void **)&h_mw, sizeof(double) * B * 32));
         MN_CU(cudaMallocHost((void **)&h_chg, sizeof(int32_t) * 2 * M));
         MN_CU(cudaMallocHost((void **)&h_counters, sizeof(unsigned long long) * 2));
-        MN_CU(cudaEventCreate(&ev0)); MN_CU(cudaEventCreate(&ev1));
+        for (int i = 0; i < kTimers; ++i) { MN_CU(cudaEventCreate(&tev[i][0])); MN_CU(cudaEventCreate(&tev[i][1])); }
         for (int b = 0; b < B; ++b) slots[b].best_rows.assign((size_t)k * 32, 0u);
         return 0;
     }
 
     // ---- timing helpers ---------------------------------------------------------------------------------
-    int tic() { MN_CU(cudaEventRecord(ev0, st)); return 0; }
+    int tic()
+    {
+        if (ntimer == kTimers) MN_TRY(flush_timers());
+        MN_CU(cudaEventRecord(tev[ntimer][0], st));
+        return 0;
+    }
     int toc(double *acc)
     {
-        MN_CU(cudaEventRecord(ev1, st));
-        MN_CU(cudaEventSynchronize(ev1));
-        float ms = 0.f;
-        MN_CU(cudaEventElapsedTime(&ms, ev0, ev1));
-        *acc += ms;
+        MN_CU(cudaEventRecord(tev[ntimer][1], st));
+        tacc[ntimer++] = acc;
+        return 0;
+    }
+    int flush_timers()          // waits for the last recorded event: call where the host synchronises anyway
+    {
+        for (int i = 0; i < ntimer; ++i) {
+            MN_CU(cudaEventSynchronize(tev[i][1]));
+            float ms = 0.f;
+            MN_CU(cudaEventElapsedTime(&ms, tev[i][0], tev[i][1]));
+            *tacc[i] += ms;
+        }
+        ntimer = 0;
         return 0;
     }
 
@@ -309,7 +328,7 @@ struct Engine {
         MN_LAUNCH(build_starts_kernel, np, 32, 0, st, d_pairs.p, d_res1.p, d_start.p);
         std::vector<const double *> rp(2 * np);
         for (int p = 0; p < np; ++p) rp[2 * p] = rp[2 * p + 1] = R.p + (size_t)pairs[p] * cx->S * cx->E;
-        MN_CU(cudaStreamSynchronize(st));   // pairs / ht are stack vectors
+        // (pairs / ht are stack vectors: copies from pageable memory are staged before the call returns)
         MN_TRY(tic());
         MN_TRY(search_run(sb, 2 * np, rp.data(), d_start.p, st));
         MN_LAUNCH(pick_kernel, np, 128, 0, st, cx->E, cx->S, d_pairs.p, d_have_theta.p, search_maxtrace(sb),
@@ -649,6 +668,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             }
             MN_CU(cudaMemcpyAsync(en.h_mw, en.d_mw.p, sizeof(double) * B * 32, cudaMemcpyDeviceToHost, st));
             MN_CU(cudaStreamSynchronize(st));
+            MN_TRY(en.flush_timers());
             for (int b : act)
                 for (int i = 0; i < k; ++i) en.slots[b].mw[i] = en.h_mw[b * 32 + i];
             for (int b : outer_guard)
@@ -684,6 +704,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         return 0;
     };
     int rc = body();
+    if (!rc) rc = en.flush_timers();
     if (!rc) {
         cudaEventRecord(evB, st);
         cudaEventSynchronize(evB);
@@ -720,6 +741,7 @@ extern "C" int mnemcu_bench_estep(mnemcu_ctx *cx, int batch, int k, const uint8_
         double ms = 0.0;
         en.stats.ms_estep = 0.0;
         MN_TRY(en.op_estep());
+        MN_TRY(en.flush_timers());
         ms = en.stats.ms_estep;
         ms_out[r] = ms;
     }
@@ -736,6 +758,7 @@ extern "C" int mnemcu_bench_mstats(mnemcu_ctx *cx, int batch, int k, int n_rep, 
     for (int r = 0; r < n_rep; ++r) {
         en.stats.ms_mstats = 0.0;
         MN_TRY(en.op_mstats());
+        MN_TRY(en.flush_timers());
         ms_out[r] = en.stats.ms_mstats;
     }
     if (bytes_per_launch)

@@ -936,10 +936,10 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
             ch[h].G = pick_groups(ch[h].n, ntiles, 148);
             ch[h].done = ch[h].n == 0;
         }
+        // pageable source: the call returns once the bytes are staged, so the stack vector may go out of scope
         MN_CU(cudaMemcpyAsync(sb->qlist.p, ql.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-        MN_CU(cudaStreamSynchronize(st));              // ql is a stack vector; also: the initial scores are complete
     }
-    for (int h = 1; h < nch; ++h) {                   // fork (the sync above already ordered everything before it)
+    for (int h = 1; h < nch; ++h) {                   // fork: the other chains start after the list and the initial scores
         MN_CU(cudaEventRecord(sb->ev_fork, st));
         MN_CU(cudaStreamWaitEvent(ch[h].st, sb->ev_fork, 0));
     }
