@@ -624,6 +624,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             MN_CU(cudaMemcpyAsync(en.h_chg, en.d_edge.p, sizeof(int32_t) * en.M, cudaMemcpyDeviceToHost, st));
             MN_CU(cudaMemcpyAsync(en.h_chg + en.M, en.d_thch.p, sizeof(int32_t) * en.M, cudaMemcpyDeviceToHost, st));
             MN_TRY(en.toc(&en.stats.ms_mixture));
+            MN_CU(cudaStreamSynchronize(st));                   // h_ll / h_chg are read below
             // ---- host logic, INIT slots: R/mnems_low.r:643-659 ----
             std::vector<int> outer, outer_guard;
             for (int b : ini) {
