@@ -126,35 +126,65 @@ def cpu_sample(sim, init, n_threads, cells, guard=1):
 
 
 def cpu_extrapolated(sim, init, n_threads, cells, mean_iters):
-    """EM iterations/s of the CPU restatement for the FULL workload, from three bounded samples.
+    """EM iterations/s of the CPU restatement for the FULL workload, from bounded component timings.
 
-    Per start the reference spends  T(C) = INIT(C) + n * EM(C)  with INIT(C) = aI*C (theta-free E-step: passes over the
-    cells only) and EM(C) = aE*C + b (passes over the cells plus 2k greedy searches, whose cost does not depend on C).
-    Samples: (C/2, 1 EM iteration), (C', 1), (C', 2) with C' = `cells` give aI, aE, b; the value reported is
-    n_threads * n / T(C_full) for n = `mean_iters` EM iterations per start."""
-    c2 = min(cells, sim["C"])
-    c1 = max(1, c2 // 2)
-    r11 = cpu_sample(sim, init, n_threads, c1, 1)
-    r21 = cpu_sample(sim, init, n_threads, c2, 1)
-    r22 = cpu_sample(sim, init, n_threads, c2, 2)
-    t11, t21, t22 = r11["seconds"], r21["seconds"], r22["seconds"]
-    slope = max(0.0, (t21 - t11) / max(1, c2 - c1))                 # aI + aE
-    b = max(0.0, t21 - slope * c2)
-    em2 = max(1e-9, t22 - t21)                                      # EM(c2) = aE*c2 + b
-    aE = max(0.0, (em2 - b) / c2)
-    aI = max(0.0, slope - aE)
-    Cf = sim["C"]
-    t_init, t_em = aI * Cf, aE * Cf + b
+    Per start the reference spends (R/mnems.r:1905-1915, 1976-2108; the oracle's orc_em_start with faithful_cost):
+        T(C) = getProbs(theta = NULL)(C)  +  n * [ 2k * doMean(C)  +  2k * nem_greedy  +  getProbs(theta given)(C) ]
+    The three data passes are timed on the first `cells` cells of the same matrix and scale linearly with the number of
+    cells (they are plain loops over the columns); the greedy searches work on the collapsed E x S matrix and do not
+    depend on C.  Every thread times its own start (the threads run concurrently, so memory-bandwidth contention is in
+    the numbers); the value reported is  n_threads * n / T(C_full)  with n = `mean_iters` EM iterations per start."""
+    import concurrent.futures
+
+    import oracle as orc
+    from mnem_b200 import simdata
+    c = min(cells, sim["C"])
+    k, S, E = sim["k"], sim["S"], sim["E"]
+    D = simdata.host_data_native(sim, 0, c, nthreads=max(1, n_threads))
+    pert = sim["pert"][:c]
+    n_threads = max(1, min(n_threads, len(init)))
+
+    def one(s):
+        phi = init[s]
+        t = {}
+        t0 = time.time()
+        g0 = orc.get_probs(D, pert, S, phi, None, np.zeros((k, c)), None, complete=sim["complete"], faithful_cost=True)
+        t["init"] = time.time() - t0
+        post = orc.get_affinity(g0["probs"], g0["mw"], complete=sim["complete"])
+        t0 = time.time()
+        R = [orc.do_mean(D, pert, S, post[i]) for i in range(k)]
+        t["domean"] = (time.time() - t0) / k
+        t0 = time.time()
+        fits = [orc.nem_greedy(R[i], None) for i in range(k)] + [orc.nem_greedy(R[i], phi[i]) for i in range(k)]
+        t["greedy"] = (time.time() - t0) / (2 * k)
+        nsc = sum(f["n_scored"] for f in fits)
+        adj = np.stack([f["adj"] for f in fits[:k]])
+        th = np.stack([f["theta"] for f in fits[:k]])
+        t0 = time.time()
+        orc.get_probs(D, pert, S, adj, th, g0["probs"], g0["mw"], complete=sim["complete"], faithful_cost=True)
+        t["estep"] = time.time() - t0
+        t["scored"] = nsc
+        return t
+
+    t0 = time.time()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=n_threads) as ex:      # ctypes releases the GIL
+        ts = list(ex.map(one, range(n_threads)))
+    wall = time.time() - t0
+    m = {key: float(np.mean([t[key] for t in ts])) for key in ("init", "domean", "greedy", "estep")}
+    scale = sim["C"] / float(c)
+    t_init = m["init"] * scale
+    t_em = 2 * k * m["domean"] * scale + 2 * k * m["greedy"] + m["estep"] * scale
     T = t_init + mean_iters * t_em
-    value = r21["starts"] * mean_iters / T
-    return dict(value=float(value), seconds=t11 + t21 + t22, t_init_full=t_init, t_em_full=t_em, b_search=b,
-                cells=(c1, c2), starts=r21["starts"], mean_iters=mean_iters,
-                cand_scores_per_s=r22["cand_scored"] / max(1e-9, t22),
-                sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) in parallel: three bounded "
-                        "samples -- first %d cells with 1 EM iteration (%.1f s), first %d cells with 1 (%.1f s) and 2 (%.1f s) "
-                        "EM iterations, redundant passes kept -- fitted to T = INIT(C) + n*EM(C), INIT = aI*C, EM = aE*C + b "
-                        "(b: the searches), and evaluated at C = %d cells, n = %.2f EM iterations per start: INIT %.3g s, "
-                        "EM iteration %.3g s per start" % (r21["starts"], c1, t11, c2, t21, t22, Cf, mean_iters, t_init, t_em)))
+    value = n_threads * mean_iters / T
+    return dict(value=float(value), seconds=wall, t_init_full=t_init, t_em_full=t_em, cells=c, starts=n_threads,
+                mean_iters=mean_iters,
+                cand_scores_per_s=float(sum(t["scored"] for t in ts) / max(1e-9, sum(2 * k * t["greedy"] for t in ts)) * n_threads),
+                sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) concurrently, first %d of %d cells "
+                        "(%.1f s): per start getProbs(theta=NULL) %.2f s, doMean %.3f s, getProbs(theta) %.2f s (each scaled by "
+                        "%d/%d cells), nem_greedy %.2f s per search (independent of the cell count); redundant passes kept; "
+                        "T = init + n*(2k*doMean + 2k*greedy + getProbs) at n = %.2f EM iterations per start: init %.3g s, "
+                        "EM iteration %.3g s per start" % (n_threads, c, sim["C"], wall, m["init"], m["domean"], m["estep"],
+                                                          sim["C"], c, m["greedy"], mean_iters, t_init, t_em)))
 
 
 def run_reference(args):
