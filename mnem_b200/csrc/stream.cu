@@ -192,6 +192,34 @@ constexpr int kStages = 3;     // stages in flight: 2 ahead of the one being con
 constexpr int kMsWarpE = 64;   // E-genes per warp: 8 n-tiles of 8
 constexpr int kMsThreads = 128;
 
+// ---- TMA (1-D bulk copy) + mbarrier helpers: one thread arms the stage's barrier with the byte count and issues the
+// copies; the copy engine writes shared memory and completes the transaction count; everybody waits on the phase bit.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // D += A * B on the FP64 tensor cores, m8n8k4: A 8x4 row-major (a = A[lane/4][lane%4]), B 4x8 column-major
 // (b = B[lane%4][lane/4]), C/D 8x8 (c0, c1 = C[lane/4][2*(lane%4) + {0, 1}]).
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
@@ -200,14 +228,18 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+constexpr int kGP = 12;        // doubles per staged weight row (8 cells + padding: rows gq and gq + 4 share a bank pair only)
+
 // grid = (groups of pairs, E-gene tiles, chunks), block = tpb threads (a multiple of 32, <= 128); warp w owns the 64
 // E-genes [tile0 + 64 w, +64).  The contraction over the cells of the chunk is a GEMM
 //     Rt[pair][e] += gamma[pair][cell] * D[cell][e]          (M = pairs in 8-row tiles, N = E-genes, K = cells)
 // issued as m8n8k4 FP64 MMAs: one instruction does 256 FMAs, so the FP64 pipe runs at its peak rate with an eighth
-// of the issue slots the scalar DFMA form needs (ncu on the DFMA form: FP64 pipe 53 %, issue-bound).  A 3-stage
-// cp.async ring keeps 16 cells (32 KB per CTA) in flight ahead of the MMAs: each stage holds, for 8 cells, the CTA's
-// slice of D (16 bytes per thread and cell, straight from HBM to shared memory, L1 bypassed) and the 8 x MT8*8 weights.
-// Row strides are padded to 8 mod 16 doubles so that the 4 x 8 fragment loads are conflict-free (2 wavefronts).
+// of the issue slots the scalar DFMA form needs (ncu on the DFMA form: FP64 pipe 53 %, issue-bound).
+// Staging: a 3-stage ring filled by TMA 1-D bulk copies (cp.async.bulk, one elected thread): per stage 8 cells, i.e. 8
+// rows of the CTA's D slice (2 KB each, contiguous in Dcol) and, per pair, its 8 responsibilities (64 B, contiguous in
+// gamma[m][.]); completion is signalled on the stage's mbarrier, so no thread spends issue slots on address arithmetic
+// or per-thread copies.  Row strides are padded (D rows to 8 mod 16 doubles, weight rows to 12) so that the 4 x 8
+// fragment loads take the minimum of two shared-memory wavefronts.
 template <int MT8>
 __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__restrict__ Dcol, int Epad,
                                                                const double *__restrict__ gam, int M, int MT, int Cp,
@@ -215,61 +247,64 @@ __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__r
                                                                const int32_t *__restrict__ chunk_n,
                                                                double *__restrict__ partial)
 {
-    constexpr int GSTR = (MT8 * 8) % 16 == 0 ? MT8 * 8 + 8 : MT8 * 8;      // == 8 (mod 16)
     extern __shared__ __align__(16) unsigned char s_dyn[];
+    __shared__ __align__(8) uint64_t s_full[kStages];
     const int tpb = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ESTR = 2 * tpb + 8;                                           // == 8 (mod 16): tpb is a multiple of 32
     double *sD = reinterpret_cast<double *>(s_dyn);                         // [kStages][kStCells][ESTR]
-    double *sG = sD + (size_t)kStages * kStCells * ESTR;                    // [kStages][kStCells][GSTR]
+    double *sG = sD + (size_t)kStages * kStCells * ESTR;                    // [kStages][MT8 * 8][kGP]
     const int chunk = blockIdx.z;
     const int m0 = blockIdx.x * MT;                     // groups vary fastest: the CTAs that re-read a tile run together
     const int etile0 = 2 * blockIdx.y * tpb;
-    const int e = etile0 + 2 * tid;                     // the pair of E-genes this thread stages
-    const bool live = e < Epad;
     const int cp0 = chunk_cp0[chunk];
     const int n = chunk_n[chunk];                       // multiple of 64
+    const int nlive = max(0, min(MT, M - m0));          // pairs of this CTA; rows nlive .. MT8*8-1 are padding
+    const uint32_t row_bytes = (uint32_t)(min(2 * tpb, Epad - etile0) * (int)sizeof(double));   // multiple of 16 (Epad even)
+    const uint32_t stage_bytes = kStCells * row_bytes + (gam ? (uint32_t)nlive * kStCells * (uint32_t)sizeof(double) : 0u);
     double acc[8][MT8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int mt = 0; mt < MT8; ++mt) { acc[nt][mt][0] = 0.0; acc[nt][mt][1] = 0.0; }
-    const double2 *p = reinterpret_cast<const double2 *>(Dcol + (size_t)cp0 * Epad + (live ? e : 0));
-    const size_t stride = (size_t)Epad / 2;
+    // constant weight rows are written once (generic proxy) and never touched by the copies: padding rows 0, and all
+    // live rows 1 when there are no weights (unweighted doMean)
+    for (int i = tid; i < kStages * MT8 * 8 * kGP; i += tpb) {
+        const int m = (i / kGP) % (MT8 * 8);
+        sG[i] = (m < nlive && !gam) ? 1.0 : 0.0;
+    }
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kStages; ++s2) mbar_init(&s_full[s2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const double *Dsrc = Dcol + (size_t)cp0 * Epad + etile0;
 
-    auto issue = [&](int st, int c0) {
-        if (c0 < n) {
-#pragma unroll
-            for (int j = 0; j < kStCells; ++j)
-                cp_async16(&sD[(size_t)(st * kStCells + j) * ESTR + 2 * tid], p + (size_t)(c0 + j) * stride);
-            for (int i = tid; i < kStCells * MT8 * 8; i += tpb) {
-                const int m = i / kStCells, c = i - m * kStCells;
-                double *dst = &sG[(st * kStCells + c) * GSTR + m];
-                if (m < MT && m0 + m < M) {
-                    if (gam) cp_async8(dst, gam + (size_t)(m0 + m) * Cp + cp0 + c0 + c);
-                    else *dst = 1.0;
-                } else {
-                    *dst = 0.0;                          // padding rows of the last 8-pair tile
-                }
-            }
-        }
-        cp_async_commit();                              // always: keeps the group count uniform
+    auto issue = [&](int st, int c0) {                  // called by thread 0 only
+        if (c0 >= n) return;
+        mbar_expect_tx(&s_full[st], stage_bytes);
+        for (int j = 0; j < kStCells; ++j)
+            tma_load_1d(&sD[(size_t)(st * kStCells + j) * ESTR], Dsrc + (size_t)(c0 + j) * Epad, row_bytes, &s_full[st]);
+        if (gam)
+            for (int m = 0; m < nlive; ++m)
+                tma_load_1d(&sG[(st * MT8 * 8 + m) * kGP], gam + (size_t)(m0 + m) * Cp + cp0 + c0,
+                            kStCells * (uint32_t)sizeof(double), &s_full[st]);
     };
 
-    issue(0, 0);
-    issue(1, kStCells);
+    if (tid == 0) { issue(0, 0); issue(1, kStCells); }
     int st = 0;
+    uint32_t parity = 0;                                // phase of the barrier of stage `st`: flips each time the ring wraps
     const int kq = lane & 3, gq = lane >> 2;            // k index / row-or-column index of this lane's fragment element
     for (int c0 = 0; c0 < n; c0 += kStCells) {
-        issue(st == 0 ? 2 : st - 1, c0 + 2 * kStCells);     // (st + 2) % 3
-        cp_async_wait<2>();
-        __syncthreads();
+        // stage (st + 2) % 3 was consumed in the previous iteration (everyone passed the barrier at its end)
+        if (tid == 0) issue(st == 0 ? 2 : st - 1, c0 + 2 * kStCells);
+        mbar_wait(&s_full[st], parity);
 #pragma unroll
         for (int ks = 0; ks < kStCells / 4; ++ks) {
-            const double *gd = sG + (st * kStCells + ks * 4 + kq) * GSTR + gq;
+            const double *gd = sG + (st * MT8 * 8 + gq) * kGP + ks * 4 + kq;
             const double *dd = sD + (size_t)(st * kStCells + ks * 4 + kq) * ESTR + warp * kMsWarpE + gq;
             double a[MT8];
 #pragma unroll
-            for (int mt = 0; mt < MT8; ++mt) a[mt] = gd[mt * 8];
+            for (int mt = 0; mt < MT8; ++mt) a[mt] = gd[mt * 8 * kGP];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 const double b = dd[nt * 8];
@@ -277,8 +312,8 @@ __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__r
                 for (int mt = 0; mt < MT8; ++mt) dmma884(acc[nt][mt][0], acc[nt][mt][1], a[mt], b);
             }
         }
-        __syncthreads();
-        st = st == 2 ? 0 : st + 1;
+        __syncthreads();                                // the stage may be refilled
+        if (st == 2) { st = 0; parity ^= 1u; } else ++st;
     }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -380,8 +415,7 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, int M
     int tpb = kMsThreads;
     while (tpb > 32 && tpb / 2 >= pairs) tpb /= 2;
     dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
-    constexpr int GSTR = (MT8 * 8) % 16 == 0 ? MT8 * 8 + 8 : MT8 * 8;
-    const size_t smem = (size_t)kStages * kStCells * ((size_t)(2 * tpb + 8) + GSTR) * sizeof(double);
+    const size_t smem = (size_t)kStages * ((size_t)kStCells * (2 * tpb + 8) + (size_t)MT8 * 8 * kGP) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         MN_CU(cudaFuncSetAttribute(mstats_kernel<MT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
