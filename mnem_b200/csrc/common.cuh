@@ -188,7 +188,9 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
 // maskT[s][e] bit m = closure_m[s][theta_m[e] - 1] (theta 0 -> 0).  clo: [M][32] row masks, theta: [M][E].
 int launch_build_masks(const mnemcu_ctx *cx, const uint32_t *clo, const int32_t *theta, int M, uint32_t *maskT,
                        cudaStream_t st);
-// M-step statistics: R[m][s][e] = sum_{cp in segment s} Dcol[cp][e] * gam[m][cp]; gam == nullptr: weights 1.
+// M-step statistics: R[m][s][e] = sum_{cp in segment s} Dcol[cp][e] * gam[cp][m]; gam == nullptr: weights 1.
+// gam is cell-major [Cp][gamma_stride(M)], columns M.. zero (one TMA bulk copy per pipeline stage).
+inline int gamma_stride(int M) { return M <= 8 ? 8 : (M <= 24 ? 24 : 40); }    // == 8 (mod 16): conflict-free fragments
 int launch_mstats(const mnemcu_ctx *cx, const double *gam, int M, double *partial, double *R, cudaStream_t st);
 size_t mstats_partial_elems(const mnemcu_ctx *cx, int M);
 // Rho path only (ctx->multi): per-group sums Rg[m][g][e] from the chunk partials of the last launch_mstats, and the
@@ -204,7 +206,7 @@ int launch_L_from_internal(const mnemcu_ctx *cx, const double *L_int, int k, dou
 constexpr int kMaxSlots = 32;
 struct MixSlots {             // by-value kernel argument: one entry per mixture in the launch
     const double *L[kMaxSlots];     // [k][Cp]
-    double *gam[kMaxSlots];         // [k][Cp] output of the affinity kernel (may alias nothing)
+    double *gam[kMaxSlots];         // output of the affinity kernel: first column of the mixture in [Cp][gw]
     const double *mw[kMaxSlots];    // [k] device
     const int32_t *anypos[kMaxSlots];   // device flag: any(L > 0)
     double *ll_out[kMaxSlots];      // device scalar receiving ll
@@ -214,7 +216,7 @@ struct MixSlots {             // by-value kernel argument: one entry per mixture
 };
 constexpr int kMixBlocks = 296;    // blocks per mixture in the statistics kernel (2 per SM)
 // gamma = getAffinity(L, mw) for every slot (pad cells get 0)
-int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, cudaStream_t st);
+int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int complete, double logtype, cudaStream_t st);
 // ll = getLL(L, mw), mw_out = normalise(rowSums(getAffinity(L, mw))) for every slot; scratch: n*kMixBlocks*(k+1)
 int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, double *scratch,
                      cudaStream_t st);

@@ -17,14 +17,14 @@
 
 namespace mn {
 
-// weights given as n row blocks of C (caller's cell order) -> [n][Cp] sorted, padding 0
-__global__ void weights_to_internal_kernel(const double *__restrict__ w, int n, int C, int Cp,
+// weights given as n row blocks of C (caller's cell order) -> [Cp][gw] sorted, padding cells and columns n.. 0
+__global__ void weights_to_internal_kernel(const double *__restrict__ w, int n, int gw, int C, int Cp,
                                            const int32_t *__restrict__ orig, double *__restrict__ out)
 {
     const int cp = blockIdx.x * blockDim.x + threadIdx.x;
     if (cp >= Cp) return;
     const int c = orig[cp];
-    for (int j = 0; j < n; ++j) out[(size_t)j * Cp + cp] = c >= 0 ? w[(size_t)j * C + c] : 0.0;
+    for (int j = 0; j < gw; ++j) out[(size_t)cp * gw + j] = (c >= 0 && j < n) ? w[(size_t)j * C + c] : 0.0;
 }
 
 // After the two greedy searches of every (slot, component) pair: keep the better one (R/mnems.r:2069-2073, tie ->
@@ -155,7 +155,7 @@ struct Engine {
         kCp = (size_t)k * cx->Cp;
         slots.assign(B, Slot());
         MN_TRY(Lbuf.alloc((size_t)B * 3 * kCp, true));
-        MN_TRY(gam.alloc((size_t)M * cx->Cp, true));
+        MN_TRY(gam.alloc((size_t)gamma_stride(M) * cx->Cp, true));     // [Cp][gw], columns M.. stay 0
         MN_TRY(R.alloc((size_t)M * cx->S * cx->E, true));
         MN_TRY(partial.alloc(mstats_partial_elems(cx, M)));
         MN_TRY(mixscratch.alloc((size_t)B * kMixBlocks * (k + 1)));
@@ -261,11 +261,11 @@ struct Engine {
         for (int j = 0; j < ms.n; ++j) {
             const int b = list[j];
             ms.L[j] = buf(b, slots[b].cur);
-            ms.gam[j] = gam.p + (size_t)b * kCp;
+            ms.gam[j] = gam.p + (size_t)b * k;
             ms.mw[j] = d_mw.p + b * 32;
             ms.anypos[j] = flag(b, slots[b].cur);
         }
-        return launch_affinity(cx, ms, k, complete, logtype, st);
+        return launch_affinity(cx, ms, k, gamma_stride(M), complete, logtype, st);
     }
 
     int op_mstats(bool unweighted = false)
@@ -356,7 +356,7 @@ extern "C" int mnemcu_do_mean(mnemcu_ctx *cx, const double *weights, int n, doub
     const size_t ES = (size_t)cx->E * cx->S;
     DevBuf<double> dw, dgam, dpart, dR;
     const int G = std::min(n, 20);
-    MN_TRY(dgam.alloc((size_t)G * cx->Cp));
+    MN_TRY(dgam.alloc((size_t)gamma_stride(G) * cx->Cp));
     MN_TRY(dpart.alloc(mstats_partial_elems(cx, G)));
     MN_TRY(dR.alloc((size_t)G * ES));
     if (weights) MN_TRY(dw.alloc((size_t)G * cx->C));
@@ -365,8 +365,8 @@ extern "C" int mnemcu_do_mean(mnemcu_ctx *cx, const double *weights, int n, doub
         if (weights) {
             MN_CU(cudaMemcpyAsync(dw.p, weights + (size_t)j0 * cx->C, sizeof(double) * (size_t)g * cx->C,
                                   cudaMemcpyHostToDevice, st));
-            MN_LAUNCH(weights_to_internal_kernel, (cx->Cp + 255) / 256, 256, 0, st, dw.p, g, cx->C, cx->Cp, cx->orig,
-                      dgam.p);
+            MN_LAUNCH(weights_to_internal_kernel, (cx->Cp + 255) / 256, 256, 0, st, dw.p, g, gamma_stride(g), cx->C, cx->Cp,
+                      cx->orig, dgam.p);
         }
         MN_TRY(launch_mstats(cx, weights ? dgam.p : nullptr, g, dpart.p, dR.p, st));
         MN_CU(cudaMemcpyAsync(R_out + (size_t)j0 * ES, dR.p, sizeof(double) * (size_t)g * ES, cudaMemcpyDeviceToHost, st));

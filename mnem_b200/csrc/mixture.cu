@@ -13,8 +13,9 @@ namespace mn {
 
 struct MixGeom {
     int ncell;              // cells (columns) to visit
-    long long si, sc;       // strides of L / gamma
+    long long si, sc;       // strides of L (component, cell)
     const int32_t *valid;   // optional [ncell]: < 0 marks padding that must not enter any sum
+    long long gsi, gsc;     // strides of the gamma output of affinity_kernel (0, 0: same as L)
 };
 
 __device__ __forceinline__ double pow_b(double b, double lb, double y)
@@ -55,9 +56,10 @@ __global__ void __launch_bounds__(256) affinity_kernel(MixSlots s, MixGeom g, in
     const int slot = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.ncell) return;
-    double *out = s.gam[slot] + c * g.sc;
+    const long long osi = g.gsi ? g.gsi : g.si, osc = g.gsc ? g.gsc : g.sc;
+    double *out = s.gam[slot] + c * osc;
     if (g.valid && g.valid[c] < 0) {
-        for (int i = 0; i < k; ++i) out[i * g.si] = 0.0;
+        for (int i = 0; i < k; ++i) out[i * osi] = 0.0;
         return;
     }
     double mw[MNEMCU_MAX_K], xs[MNEMCU_MAX_K], xraw[MNEMCU_MAX_K];
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256) affinity_kernel(MixSlots s, MixGeom g, in
             double y = xs[i] < mx ? 0.0 : xs[i];
             if (y != 0.0) y = 1.0;
             if (isnan(y)) y = 0.0;
-            out[i * g.si] = y;
+            out[i * osi] = y;
         }
         return;
     }
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(256) affinity_kernel(MixSlots s, MixGeom g, in
     for (int i = 0; i < k; ++i) {
         double v = xs[i] / cs;
         if (isnan(v)) v = 0.0;                                      // :1439
-        out[i * g.si] = v;
+        out[i * osi] = v;
     }
 }
 
@@ -245,16 +247,18 @@ int launch_mix_stats_geom(const MixSlots &s, const MixGeom &g, int k, int comple
     return 0;
 }
 
-int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, cudaStream_t st)
+int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int complete, double logtype, cudaStream_t st)
 {
-    MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig};
+    // L is [k][Cp]; gamma goes to the cell-major [Cp][gw] layout the M-step statistics kernel stages (s.gam[j] points at
+    // the mixture's first column)
+    MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig, 1, (long long)gw};
     return launch_affinity_geom(s, g, k, 0, complete, logtype, st);
 }
 
 int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, double *scratch,
                      cudaStream_t st)
 {
-    MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig};
+    MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig, 0, 0};
     return launch_mix_stats_geom(s, g, k, complete, logtype, scratch, st);
 }
 
@@ -291,7 +295,7 @@ static int mix_api(const double *L, int k, int C, const double *mw, int affinity
     s.L[0] = dL.p;
     s.mw[0] = mw ? dmw.p : nullptr;
     s.anypos[0] = dflag.p;
-    MixGeom g{C, 1, (long long)k, nullptr};
+    MixGeom g{C, 1, (long long)k, nullptr, 0, 0};
     if (complete) MN_LAUNCH(anypos_kernel, 296, 256, 0, 0, dL.p, n, dflag.p);
     if (gam_out) {
         MN_TRY(dG.alloc(n));

@@ -228,7 +228,6 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int kGP = 12;        // doubles per staged weight row (8 cells + padding: rows gq and gq + 4 share a bank pair only)
 
 // grid = (groups of pairs, E-gene tiles, chunks), block = tpb threads (a multiple of 32, <= 128); warp w owns the 64
 // E-genes [tile0 + 64 w, +64).  The contraction over the cells of the chunk is a GEMM
@@ -236,13 +235,13 @@ constexpr int kGP = 12;        // doubles per staged weight row (8 cells + paddi
 // issued as m8n8k4 FP64 MMAs: one instruction does 256 FMAs, so the FP64 pipe runs at its peak rate with an eighth
 // of the issue slots the scalar DFMA form needs (ncu on the DFMA form: FP64 pipe 53 %, issue-bound).
 // Staging: a 3-stage ring filled by TMA 1-D bulk copies (cp.async.bulk, one elected thread): per stage 8 cells, i.e. 8
-// rows of the CTA's D slice (2 KB each, contiguous in Dcol) and, per pair, its 8 responsibilities (64 B, contiguous in
-// gamma[m][.]); completion is signalled on the stage's mbarrier, so no thread spends issue slots on address arithmetic
-// or per-thread copies.  Row strides are padded (D rows to 8 mod 16 doubles, weight rows to 12) so that the 4 x 8
-// fragment loads take the minimum of two shared-memory wavefronts.
+// rows of the CTA's D slice (2 KB each, contiguous in Dcol) and ONE block of responsibilities (gamma is kept cell-major
+// [Cp][gw], so the 8 cells x gw weights of a stage are contiguous); completion is signalled on the stage's mbarrier, so
+// no thread spends issue slots on address arithmetic or per-thread copies.  Row strides (D rows in shared memory, gw)
+// are 8 mod 16 doubles so that the 4 x 8 fragment loads take the minimum of two shared-memory wavefronts.
 template <int MT8>
 __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__restrict__ Dcol, int Epad,
-                                                               const double *__restrict__ gam, int M, int MT, int Cp,
+                                                               const double *__restrict__ gam, int gw, int M, int MT,
                                                                const int32_t *__restrict__ chunk_cp0,
                                                                const int32_t *__restrict__ chunk_n,
                                                                double *__restrict__ partial)
@@ -252,26 +251,23 @@ __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__r
     const int tpb = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ESTR = 2 * tpb + 8;                                           // == 8 (mod 16): tpb is a multiple of 32
     double *sD = reinterpret_cast<double *>(s_dyn);                         // [kStages][kStCells][ESTR]
-    double *sG = sD + (size_t)kStages * kStCells * ESTR;                    // [kStages][MT8 * 8][kGP]
+    double *sG = sD + (size_t)kStages * kStCells * ESTR;                    // [kStages][kStCells][gw]
     const int chunk = blockIdx.z;
     const int m0 = blockIdx.x * MT;                     // groups vary fastest: the CTAs that re-read a tile run together
     const int etile0 = 2 * blockIdx.y * tpb;
     const int cp0 = chunk_cp0[chunk];
     const int n = chunk_n[chunk];                       // multiple of 64
-    const int nlive = max(0, min(MT, M - m0));          // pairs of this CTA; rows nlive .. MT8*8-1 are padding
     const uint32_t row_bytes = (uint32_t)(min(2 * tpb, Epad - etile0) * (int)sizeof(double));   // multiple of 16 (Epad even)
-    const uint32_t stage_bytes = kStCells * row_bytes + (gam ? (uint32_t)nlive * kStCells * (uint32_t)sizeof(double) : 0u);
+    const uint32_t gam_bytes = (uint32_t)(kStCells * gw) * (uint32_t)sizeof(double);
+    const uint32_t stage_bytes = kStCells * row_bytes + (gam ? gam_bytes : 0u);
     double acc[8][MT8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int mt = 0; mt < MT8; ++mt) { acc[nt][mt][0] = 0.0; acc[nt][mt][1] = 0.0; }
-    // constant weight rows are written once (generic proxy) and never touched by the copies: padding rows 0, and all
-    // live rows 1 when there are no weights (unweighted doMean)
-    for (int i = tid; i < kStages * MT8 * 8 * kGP; i += tpb) {
-        const int m = (i / kGP) % (MT8 * 8);
-        sG[i] = (m < nlive && !gam) ? 1.0 : 0.0;
-    }
+    // no weights (unweighted doMean): constant rows, written once (generic proxy) and never touched by the copies
+    if (!gam)
+        for (int i = tid; i < kStages * kStCells * gw; i += tpb) sG[i] = (i % gw) < M ? 1.0 : 0.0;
     if (tid == 0) {
         for (int s2 = 0; s2 < kStages; ++s2) mbar_init(&s_full[s2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -284,10 +280,7 @@ __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__r
         mbar_expect_tx(&s_full[st], stage_bytes);
         for (int j = 0; j < kStCells; ++j)
             tma_load_1d(&sD[(size_t)(st * kStCells + j) * ESTR], Dsrc + (size_t)(c0 + j) * Epad, row_bytes, &s_full[st]);
-        if (gam)
-            for (int m = 0; m < nlive; ++m)
-                tma_load_1d(&sG[(st * MT8 * 8 + m) * kGP], gam + (size_t)(m0 + m) * Cp + cp0 + c0,
-                            kStCells * (uint32_t)sizeof(double), &s_full[st]);
+        if (gam) tma_load_1d(&sG[st * kStCells * gw], gam + (size_t)(cp0 + c0) * gw, gam_bytes, &s_full[st]);
     };
 
     if (tid == 0) { issue(0, 0); issue(1, kStCells); }
@@ -300,11 +293,11 @@ __global__ void __launch_bounds__(kMsThreads, 3) mstats_kernel(const double *__r
         mbar_wait(&s_full[st], parity);
 #pragma unroll
         for (int ks = 0; ks < kStCells / 4; ++ks) {
-            const double *gd = sG + (st * MT8 * 8 + gq) * kGP + ks * 4 + kq;
+            const double *gd = sG + (st * kStCells + ks * 4 + kq) * gw + m0 + gq;
             const double *dd = sD + (size_t)(st * kStCells + ks * 4 + kq) * ESTR + warp * kMsWarpE + gq;
             double a[MT8];
 #pragma unroll
-            for (int mt = 0; mt < MT8; ++mt) a[mt] = gd[mt * 8 * kGP];
+            for (int mt = 0; mt < MT8; ++mt) a[mt] = gd[mt * 8];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 const double b = dd[nt * 8];
@@ -415,13 +408,14 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, int M
     int tpb = kMsThreads;
     while (tpb > 32 && tpb / 2 >= pairs) tpb /= 2;
     dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
-    const size_t smem = (size_t)kStages * ((size_t)kStCells * (2 * tpb + 8) + (size_t)MT8 * 8 * kGP) * sizeof(double);
+    const int gw = gamma_stride(M);
+    const size_t smem = (size_t)kStages * kStCells * ((size_t)(2 * tpb + 8) + gw) * sizeof(double);
     static bool attr_set = false;
     if (!attr_set) {
         MN_CU(cudaFuncSetAttribute(mstats_kernel<MT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr_set = true;
     }
-    MN_LAUNCH(mstats_kernel<MT8>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, M, MT, cx->Cp, cx->chunk_cp0, cx->chunk_n,
+    MN_LAUNCH(mstats_kernel<MT8>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, gw, M, MT, cx->chunk_cp0, cx->chunk_n,
               partial);
     return 0;
 }
