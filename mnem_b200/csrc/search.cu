@@ -27,7 +27,7 @@ constexpr int kChains = 4;         // most independent iteration chains per sear
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
-    int dcap = 0, G = 1;              // dictionary capacity (entries), row groups per search
+    int dcap = 0;                     // dictionary capacity (entries)
     int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
     double logtype = 2.0;
     size_t dict_smem = 0;
