@@ -208,7 +208,7 @@ __device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int m
     for (int i = 0; i < kPer; ++i) {
         const uint32_t k = keys[tid * kPer + i];
         if (k != 0u) {
-            ids[tid * kPer + i] = (uint16_t)base;
+            ids[tid * kPer + i] = (uint16_t)min(base, dcap - 1);   // overflow: stay inside the table (the host reports it)
             if (base < dcap) dict_masks[(size_t)q * dcap + base] = k;
             ++base;
         }
@@ -853,7 +853,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     {   // dictionary capacity: pairwise unions + deletion masks + slack, limited by the 227 KB of shared memory
         const int need = S * (S + 1) / 2 + S * S / 4 + 2 * S + 8;
         const int fit = (int)((232448 - 4096 - 512) / (kDictRows * 8 + 4));
-        sb->dcap = std::max(1, std::min(need, fit));
+        sb->dcap = std::max(1, std::min(need + need / 2, fit));     // 50 % slack where shared memory allows (S <= 26)
         sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
         cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
         cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
