@@ -325,11 +325,24 @@ def run_ours(args):
             with mb.Context.synthetic(sim, device=local) as c0:
                 mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
             times, iters = [], []
+            # N > 1: every rank uploads 1/N of the columns from ITS host copy and the slices are exchanged over NVLink
+            # (NCCL broadcast per slice) instead of pushing N full copies of D through PCIe and the host memory bus
+            bounds = [Cn * r // world for r in range(world + 1)]
             for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
                 queue = mdist.StartQueue(sim["starts"])
                 barrier()
                 t0 = time.time()
-                with mb.Context(Dh, sim["pert"], device=local) as cxe:
+                if world == 1:
+                    cxe = mb.Context(Dh, sim["pert"], device=local)
+                else:
+                    Dd = torch.empty((Cn, E), dtype=torch.float64, device=dev)
+                    Dd[bounds[rank]:bounds[rank + 1]].copy_(host[bounds[rank]:bounds[rank + 1]], non_blocking=True)
+                    for r in range(world):
+                        dist.broadcast(Dd[bounds[r]:bounds[r + 1]], src=r)
+                    torch.cuda.synchronize()
+                    cxe = mb.Context.from_device(Dd.data_ptr(), E, Cn, sim["pert"], device=local)
+                    del Dd
+                with cxe:
                     r = mb.em_run(cxe, init, complete=sim["complete"], batch=args.batch, want_probs=False, next_start=queue)
                 my = sorted(queue.taken)
                 mdist.gather_winner(my, r["ll"][my], sim["starts"], device=dev)     # the winner is part of the result
@@ -341,7 +354,8 @@ def run_ours(args):
                     iters.append(reduce_sum([r["stats"]["em_iters"]])[0])
             per_start = k * S * S + 4 * k * E + 8 * k + 8 + 4 + 4 * 8 * 256          # adj, theta, mw, ll, n_iter, traces
             e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
-                   "h2d_bytes_per_step": int(world * (8 * E * Cn + 4 * Cn + sim["starts"] * k * S * S)),
+                   "h2d_bytes_per_step": int(8 * E * Cn + world * (4 * Cn + sim["starts"] * k * S * S)),
+                   "nvlink_bytes_per_step": int(8 * E * Cn * (world - 1)),
                    "d2h_bytes_per_step": int(sim["starts"] * per_start),
                    "seconds_per_step": float(np.mean(times)), "steps": len(times)}
             del hnp, Dh

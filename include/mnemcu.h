@@ -97,6 +97,11 @@ int mnemcu_nem_greedy_marginal(const double *R, int E, int S, const uint8_t *sta
 /* ---- device-resident data context -------------------------------------------------------------------- */
 /* Uploads D (E x C) once, sorted by perturbation, in the two HBM layouts the kernels stream. */
 int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *pert, int S, int device, mnemcu_ctx **out);
+/* Same as mnemcu_ctx_create, but D is ALREADY in the memory of `device` (column-major E x C, the caller's cell
+ * order; the buffer is only read and may be freed after the call).  For N-GPU jobs: every rank uploads 1/N of the
+ * columns and the ranks all-gather over NVLink instead of pushing N full copies through PCIe (bench.py e2e). */
+int mnemcu_ctx_create_device(const double *D_dev, int E, int C, const int32_t *pert, int S, int device,
+                             mnemcu_ctx **out);
 /* The Rho path of the reference (mnem(), nem(), getProbs(), doMean() called with Rho != NULL): Rho is S x C
  * column-major, Rho[s,c] != 0 <=> S-gene s is knocked down in cell c (any number per cell, also none).  Every
  * entry point that takes the context then follows the reference's Rho branches: effect of a cell =

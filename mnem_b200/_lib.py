@@ -58,6 +58,7 @@ SIGNATURES = {
                                              c_i32p, c_i64p]),
     "mnemcu_nem_greedy": (C.c_int, [c_dp, C.c_int, C.c_int, c_u8p, C.c_int, c_u8p, c_i32p, c_dp, c_dp, c_i32p, c_i64p]),
     "mnemcu_ctx_create": (C.c_int, [c_dp, C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(c_ctx)]),
+    "mnemcu_ctx_create_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(c_ctx)]),
     "mnemcu_ctx_create_rho": (C.c_int, [c_dp, C.c_int, C.c_int, c_dp, C.c_int, C.c_int, C.POINTER(c_ctx)]),
     "mnemcu_ctx_create_synthetic": (C.c_int, [C.c_int, C.c_int, c_i32p, C.c_int, c_u8p, C.c_int, c_u8p, c_i32p,
                                               C.c_uint64, C.c_int, C.POINTER(c_ctx)]),

@@ -139,6 +139,18 @@ class Context:
                                               C.c_uint64(sim["seed"]), int(device), C.byref(h)))
         return cls(_handle=h, _dims=(sim["E"], len(pert), S))
 
+    @classmethod
+    def from_device(cls, ptr, E, C_, pert, device=0):
+        """D already resident on `device` at address `ptr` (column-major E x C FP64, e.g. a torch tensor's
+        data_ptr() of shape [C, E]); the buffer is only read."""
+        lib = load_library()
+        h = _lib.c_ctx()
+        pert, S, _ = mod_data(pert)
+        if len(pert) != C_:
+            raise ValueError("pert must have one entry per column of D")
+        check(lib.mnemcu_ctx_create_device(C.c_void_p(int(ptr)), int(E), int(C_), i32p(pert), S, int(device), C.byref(h)))
+        return cls(_handle=h, _dims=(int(E), int(C_), S))
+
     def read_data(self, c0=0, nc=None):
         nc = self.C - c0 if nc is None else nc
         out = np.zeros((self.E, nc), order="F")

@@ -253,6 +253,29 @@ static int pert_to_masks(const int32_t *pert, int C, int S, std::vector<uint32_t
     return 0;
 }
 
+// D on the device already (column-major E x C, caller's cell order): one scatter pass, no staging
+static int ctx_from_device(const double *D_dev, int E, int C, const std::vector<uint32_t> &cellmask, int S, int device,
+                           mnemcu_ctx **out)
+{
+    mnemcu_ctx *cx = new mnemcu_ctx();
+    int rc = ctx_layout(cx, E, C, cellmask, S, device);
+    if (rc) { ctx_free(cx); return rc; }
+    auto body = [&]() -> int {
+        MN_CU(cudaMemsetAsync(cx->Dcol, 0, sizeof(double) * (size_t)cx->Cp * cx->Epad, cx->stream));
+        for (int c0 = 0; c0 < C; c0 += 32768) {
+            const int nc = std::min(32768, C - c0);
+            dim3 grid((E + 127) / 128, nc);
+            MN_LAUNCH(scatter_cols_kernel, grid, 128, 0, cx->stream, D_dev + (size_t)c0 * E, E, cx->Epad, c0, nc, cx->pos,
+                      cx->Dcol);
+        }
+        return ctx_finish(cx);
+    };
+    rc = body();
+    if (rc) { ctx_free(cx); return rc; }
+    *out = cx;
+    return 0;
+}
+
 static int ctx_upload(const double *D, int E, int C, const std::vector<uint32_t> &cellmask, int S, int device,
                       mnemcu_ctx **out)
 {
@@ -299,6 +322,19 @@ extern "C" int mnemcu_ctx_create(const double *D, int E, int C, const int32_t *p
     std::vector<uint32_t> cm;
     MN_TRY(pert_to_masks(pert, C, S, cm));
     return ctx_upload(D, E, C, cm, S, device, out);
+}
+
+extern "C" int mnemcu_ctx_create_device(const double *D_dev, int E, int C, const int32_t *pert, int S, int device,
+                                        mnemcu_ctx **out)
+{
+    MN_ARG(out != nullptr && D_dev != nullptr, "NULL pointer");
+    *out = nullptr;
+    cudaPointerAttributes at;
+    MN_CU(cudaPointerGetAttributes(&at, D_dev));
+    MN_ARG(at.type == cudaMemoryTypeDevice && at.device == device, "D_dev must be device memory of `device`");
+    std::vector<uint32_t> cm;
+    MN_TRY(pert_to_masks(pert, C, S, cm));
+    return ctx_from_device(D_dev, E, C, cm, S, device, out);
 }
 
 extern "C" int mnemcu_ctx_create_rho(const double *D, int E, int C, const double *Rho, int S, int device,

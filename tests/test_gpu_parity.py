@@ -357,6 +357,20 @@ def test_device_generator_matches_host_generator():
         assert np.array_equal(cx.read_data(), D)
 
 
+def test_context_from_device_resident_data():
+    """mnemcu_ctx_create_device: D already in device memory (a torch tensor here) gives the same context as the host path."""
+    import torch
+    sim = simdata.make_config(dict(S=6, Egenes=7, C=2500, mw=[0.5, 0.5], k=2, starts=1, uninform=3), seed=41)
+    D = simdata.host_data(sim)
+    Dd = torch.from_numpy(np.ascontiguousarray(D.T)).cuda()            # [C, E] row-major == E x C column-major
+    with mb.Context.from_device(Dd.data_ptr(), sim["E"], sim["C"], sim["pert"]) as cx, mb.Context(D, sim["pert"]) as cy:
+        assert np.array_equal(cx.read_data(), D)
+        w = np.random.default_rng(0).random(sim["C"])
+        assert np.array_equal(mb.doMean(cx, w), mb.doMean(cy, w))
+    with pytest.raises(mb.MnemcuError):
+        mb.Context.from_device(D.ctypes.data, sim["E"], sim["C"], sim["pert"])      # a host pointer is refused
+
+
 def test_ragged_segments_and_missing_padding():
     """Segments of very different sizes (1 cell, 63, 64, 65, 1000 cells) exercise the 64-cell padding."""
     rng = np.random.default_rng(9)
