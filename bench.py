@@ -317,6 +317,11 @@ def run_ours(args):
             host = torch.empty((Cn, E), dtype=torch.float64, pin_memory=True)       # column-major E x C
         except Exception as ex:                                                    # noqa: BLE001
             err = ex
+        if err is None:
+            free_dev = torch.cuda.mem_get_info(dev)[0]
+            want_dev = 8.0 * E * Cn * (3.2 if world > 1 else 2.2)       # two layouts (+ the gathered copy for N > 1)
+            if free_dev < want_dev:
+                err = MemoryError("not enough device memory for the end-to-end run: %.1f GB free" % (free_dev / 1e9))
         if -reduce_max(-(1.0 if err is None else 0.0)) < 1.0:
             e2e = {"value": None, "unit": "EM iterations/s", "error": repr(err)[:200] if err else "another rank failed"}
         else:
