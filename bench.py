@@ -192,8 +192,13 @@ def run_reference(args):
     if rank != 0:
         return
     sim, init, name = make_workload(args)
-    import oracle as orc
-    nthr = min(os.cpu_count() or 1, sim["starts"], orc.lib().orc_max_threads())
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so OpenMP's own count is not asked;
+    # the samples run in a Python thread pool, ctypes releases the GIL)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    nthr = max(1, min(ncpu, sim["starts"]))
     cells = args.cpu_cells or max(2000, sim["C"] // 128)
     vals = []
     for i in range(args.warmup + args.steps):
