@@ -70,7 +70,10 @@ struct DevBuf {
         cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
         if (e != cudaSuccess) {
             p = nullptr;
-            return set_err(MNEMCU_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            // only a genuine out-of-memory is NOMEM; no device / no driver is a CUDA failure like everywhere else
+            return set_err(e == cudaErrorMemoryAllocation ? MNEMCU_ERR_NOMEM : MNEMCU_ERR_CUDA, "cudaMalloc(%zu bytes): %s",
+                           count * sizeof(T), cudaGetErrorString(e));
         }
         n = count;
         if (zero) {

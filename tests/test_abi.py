@@ -80,3 +80,38 @@ def test_get_rho_follows_getRho():
     Rho, sg = mb.get_rho(["2", "10_2", "1", "10", "1_2_10"])
     assert sg == ["1", "2", "10"]
     assert Rho.tolist() == [[0, 0, 1, 0, 1], [1, 1, 0, 0, 1], [0, 1, 0, 1, 1]]
+
+
+# ---- a compiled C++ consumer of the ABI (tests/cabi/cabi_check.cpp, built by __graft_entry__.build()) ---------------
+CABI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cabi", "cabi_check")
+
+
+def _cabi(*args):
+    import subprocess
+    if not os.path.exists(CABI):
+        import __graft_entry__ as ge
+        ge.build()
+    return subprocess.run([CABI] + list(args), capture_output=True, text=True, timeout=300)
+
+
+def test_struct_layouts_agree_between_c_and_ctypes():
+    """sizeof / offsetof as the C++ compiler sees include/mnemcu.h == what the ctypes binding declares."""
+    import ctypes as C
+    from mnem_b200 import _lib
+    out = dict(line.split(None, 1) for line in _cabi("layout").stdout.strip().splitlines())
+    o = [int(x) for x in out["em_opts"].split()]
+    f = _lib.EmOpts
+    assert o == [C.sizeof(f), f.complete.offset, f.logtype.offset, f.batch.offset, f.max_trace.offset, f.max_iter_guard.offset,
+                 f.next_start.offset, f.next_start_user.offset]
+    s = [int(x) for x in out["em_stats"].split()]
+    g = _lib.EmStats
+    assert s == [C.sizeof(g), g.em_iters.offset, g.ms_total.offset, g.estep_bytes.offset]
+    assert int(out["version"]) == mb.load_library().mnemcu_version()
+
+
+def test_cpp_consumer_sees_clean_errors_without_a_device():
+    """No CPU fallback: from C++ too, every compute entry fails with MNEMCU_ERR_CUDA and a message; argument errors come
+    first.  (On a GPU box the program reports the device instead.)"""
+    r = _cabi("nogpu")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "has_gpu" in r.stdout or ("ctx_create rc=2" in r.stdout and "get_ll rc=2" in r.stdout and "null_pert rc=1" in r.stdout)

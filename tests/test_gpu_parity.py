@@ -505,3 +505,35 @@ def test_nem_greedy_marginal(S, E, n, logtype):
         assert np.array_equal(got["subtopo"][i], want["theta"])
         assert got["n_iter"][i] == want["n_iter"] and got["n_scored"][i] == want["n_raw"]
         assert abs(got["score"][i] - want["score"]) <= RTOL * abs(want["score"])
+
+
+# ---- the boundary from a compiled C++ program -------------------------------------------------------------------------
+def test_cpp_consumer_fit_matches_the_python_binding(tmp_path):
+    """tests/cabi/cabi_check.cpp (plain g++, links libmnemcu.so) runs mnemcu_em_run on column-major buffers read from a
+    file, as the Rcpp shim would pass them; winner, likelihood, iteration count and graphs equal the ctypes path."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "cabi", "cabi_check")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build()
+    sim = simdata.make_config(dict(S=5, Egenes=6, C=1500, mw=[0.4, 0.6], k=2, starts=3, uninform=1), seed=51)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(5, 2, 3, seed=6)
+    path = str(tmp_path / "problem.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([sim["E"], sim["C"], 5, 2, 3, 0], dtype=np.int32).tobytes())
+        f.write(np.asfortranarray(D).tobytes(order="F"))
+        f.write(np.ascontiguousarray(sim["pert"], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(np.transpose(init.reshape(6, 5, 5), (0, 2, 1))).astype(np.uint8).tobytes())
+    r = subprocess.run([exe, "fit", path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tok = r.stdout.split()
+    best, ll, iters, digest = int(tok[1]), float(tok[3]), int(tok[5]), int(tok[7])
+    fit = mb.mnem(D, sim["pert"], phi=init)
+    assert best == fit["best_start"] and ll == fit["ll"] and iters == int(fit["n_iter"].sum())
+    dig = 1469598103934665603
+    adj = np.ascontiguousarray(np.transpose(fit["limits"][best]["adj"], (0, 2, 1))).astype(np.uint8).ravel()
+    th = fit["limits"][best]["theta"].astype(np.uint32).ravel()
+    for v in list(adj) + list(th):
+        dig = ((dig ^ int(v)) * 1099511628211) % (1 << 64)
+    assert dig == digest
