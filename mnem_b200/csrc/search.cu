@@ -1,16 +1,22 @@
 // Batched greedy structure search: nem(search = "greedy") of the reference, R/mnems.r:111-142, 203-307, 362-379,
-// for many (start, component, restart) searches in lock step.
+// for many (start, component, restart) searches at once.
 //
-// Per greedy iteration three kernels run over ALL active searches:
-//   gen_kernel     c(get.ins.fast, get.rev.tc, get.del.tc)(better)  R/mnems_low.r:1025-1084 as bit-matrix algebra
-//                  (one CTA per search; a candidate is 32 column masks; the one-step closure of src/mm.cpp:50-65
-//                  in column form is  col'_j = col_j | (x[v,j] ? col_u : 0))
-//   score_kernel   scoreAdj(D, model, P, oldadj, trans.close = FALSE)  R/mnems.r:205-217, 439-454: thread = E-gene row,
-//                  only the columns that differ from the current graph are re-summed (ascending S-gene order, exactly
-//                  the order of the Eigen product they replace), row maximum against 0, fixed-shape sum over rows
-//   finish_kernel  which.max (first), accept rule R/mnems.r:279-289, graph update
-// Graphs are 32-bit row/column masks (S <= 32), so closure, reduction and neighbour generation are shuffles,
-// ballots and popcounts.
+// The searches of a call are dealt to (by default two) CHAINS that iterate independently on their own streams; one greedy
+// iteration of a chain is three launches over the chain's searches:
+//   finish_gen_kernel   [finish of iteration i-1] which.max (first), accept rule R/mnems.r:279-289, graph update;
+//                       [generation of iteration i] c(get.ins.fast, get.rev.tc, get.del.tc)(better),
+//                       R/mnems_low.r:1025-1084, as bit-matrix algebra (one CTA of 1024 threads per search; a candidate is
+//                       32 column masks; the one-step closure of src/mm.cpp:50-65 in column form is
+//                       col'_j = col_j | (x[v,j] ? col_u : 0)), plus the per-iteration dictionary of distinct column masks
+//   score_dict_kernel   scoreAdj(D, model, P, oldadj, trans.close = FALSE), R/mnems.r:205-217, 439-454, for every candidate:
+//                       each distinct mask is summed once per E-gene row (ascending S-gene order, the order of the Eigen
+//                       product it replaces), candidates take row maxima over table look-ups, rows are added in a fixed
+//                       shape (exact ties between candidates stay exact)
+//   reduce_tiles_kernel adds the 32-row tiles of every candidate in ascending order
+// score_kernel is the generic scorer (any graph, every changed column re-summed; marginal = TRUE variant) behind
+// mnemcu_score_adj and the marginal search; gen_kernel is the unfused generator used for the initial score and by
+// mnemcu_neighbours.  Graphs are 32-bit row/column masks (S <= 32), so closure, reduction and neighbour generation
+// are shuffles, ballots and popcounts.
 #include <climits>
 
 #include "common.cuh"
@@ -619,16 +625,6 @@ __device__ __forceinline__ void finish_body(int q, int S, int maxc, int etiles, 
     } else if (tid == 0) {
         active[q] = 0;
     }
-}
-
-__global__ void __launch_bounds__(128) finish_kernel(int S, int maxc, int etiles, int mode, const int32_t *ncand,
-                                                     const double *partial, const uint32_t *cand_cols,
-                                                     const uint32_t *Pcol, uint32_t *Prow, int32_t *active,
-                                                     double *oldscore, double *maxtrace, int32_t *niter,
-                                                     unsigned long long *nscored, int32_t *n_active)
-{
-    finish_body<128>(blockIdx.x, S, maxc, etiles, mode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter, nscored,
-                     n_active);
 }
 
 // finish of greedy iteration i fused with the candidate generation of iteration i + 1 (same CTA per search): one
