@@ -1,0 +1,100 @@
+"""Hypothesis-driven properties of the CPU oracle on small random cases (S <= 7, E <= 14): the algebra the reference's
+graph routines must satisfy whatever the input, independent of the NumPy re-reading in test_oracle_selfcheck.py."""
+import numpy as np
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+import oracle as orc
+
+
+@st.composite
+def graphs(draw, dag=False, max_s=7):
+    S = draw(st.integers(1, max_s))
+    bits = draw(st.lists(st.booleans(), min_size=S * S, max_size=S * S))
+    a = np.array(bits, dtype=np.uint8).reshape(S, S)
+    if dag:
+        a = np.triu(a, 1)
+        p = np.array(draw(st.permutations(list(range(S)))))
+        a = a[np.ix_(p, p)]
+    np.fill_diagonal(a, 0)
+    return a
+
+
+@settings(max_examples=120, deadline=None)
+@given(graphs())
+def test_closure_is_reflexive_transitive_and_idempotent(g):
+    c = orc.mytc(g)
+    S = len(g)
+    assert (np.diag(c) == 1).all() and (c >= (g != 0)).all()
+    assert ((c.astype(int) @ c.astype(int) > 0) <= (c > 0)).all()            # transitive
+    assert np.array_equal(orc.mytc(c), c)
+    reach = np.linalg.matrix_power((g != 0).astype(np.int64) + np.eye(S, dtype=np.int64), S) > 0
+    assert np.array_equal(c > 0, reach)
+
+
+@settings(max_examples=120, deadline=None)
+@given(graphs(dag=True))
+def test_reduction_of_a_dag_is_minimal_and_keeps_the_closure(g):
+    r = orc.transitive_reduction(g)
+    assert (np.diag(r) == 0).all()
+    assert np.array_equal(orc.mytc(r), orc.mytc(g))                            # same reachability
+    for i, j in zip(*np.nonzero(r)):                                           # no edge is implied by the others
+        q = r.copy()
+        q[i, j] = 0
+        assert orc.mytc(q)[i, j] == 0
+    assert np.array_equal(orc.transitive_reduction(orc.mytc(g)), r)
+
+
+@settings(max_examples=80, deadline=None)
+@given(graphs(max_s=6), st.data())
+def test_one_step_insert_closure(g, data):
+    """transClose_Ins(u, v) after setting x[u, v]: x[i, j] |= x[i, u] & x[v, j] (src/mm.cpp:50-65); on a closed graph the
+    result is closed again."""
+    S = len(g)
+    x = orc.mytc(g)
+    u = data.draw(st.integers(1, S))
+    v = data.draw(st.integers(1, S))
+    y = x.copy()
+    y[u - 1, v - 1] = 1
+    got = orc.trans_close_ins(y, u, v)
+    want = y | np.outer(y[:, u - 1], y[v - 1, :])
+    assert np.array_equal(got, want)
+    assert np.array_equal(orc.mytc(got), got)
+
+
+@settings(max_examples=60, deadline=None)
+@given(graphs(max_s=6), st.integers(0, 2 ** 31 - 1))
+def test_neighbours_are_unique_ordered_and_single_edge_moves(g, seed):
+    P = (g != 0).astype(np.uint8)
+    if seed % 2:
+        P = orc.mytc(P)
+    np.fill_diagonal(P, 1)
+    models, kind, nraw = orc.neighbours(P)
+    assert len(models) <= nraw
+    assert list(kind) == sorted(kind)                                          # insertions, reversals, deletions
+    seen = set()
+    for m, kd in zip(models, kind):
+        assert (np.diag(m) == 1).all()
+        key = m.tobytes()
+        assert key not in seen                                                 # unique(): keep first
+        seen.add(key)
+        if kd == 0:
+            assert (m >= P).all() and (m != P).any()                           # an insertion only adds edges
+        if kd == 2:
+            # a deletion removes one edge of the transitive reduction -- which is taken of the CLOSURE, so on a
+            # non-closed graph the edge may not exist and the candidate is the graph itself (R/mnems_low.r:1070-1084)
+            assert (m <= P).all() and int((P != m).sum()) <= 1
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(2, 5), st.integers(3, 14), st.integers(0, 2 ** 31 - 1))
+def test_greedy_search_ends_in_a_local_optimum(S, E, seed):
+    """nem(search = 'greedy'): the trace is increasing, and the returned score is the score of the returned graph."""
+    rng = np.random.default_rng(seed)
+    R = np.round(rng.normal(size=(E, S)) * 3, 2)
+    fit = orc.nem_greedy(R, None)
+    sc, th, _ = orc.score_adj(R, fit["adj"], trans_close=True)
+    assert abs(sc - fit["score"]) <= 1e-12 * max(1.0, abs(sc))                 # score of closure(adj) (R/mnems.r:362-369)
+    assert np.array_equal(th, fit["theta"])
+    assert fit["max_trace"] == fit["score"]                                    # hill-climb: the last accepted score is the best
+    assert fit["score"] >= orc.score_adj(R, np.zeros((S, S)), trans_close=True)[0]
