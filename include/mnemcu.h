@@ -150,6 +150,8 @@ typedef struct {
      * is the snowfall worker pool that do_inits is mapped over (R/mnems.r:2166-2170). */
     int32_t (*next_start)(void *user);
     void *next_start_user;
+    int affinity;        /* mnem(affinity =): 0 soft responsibilities (default), 1 hard assignments in every
+                          * getAffinity call of the loop (R/mnems.r:1393-1417); not with complete = TRUE */
 } mnemcu_em_opts;
 
 typedef struct {

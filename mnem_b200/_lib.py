@@ -27,7 +27,8 @@ NEXT_START_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
 
 class EmOpts(C.Structure):
     _fields_ = [("complete", C.c_int), ("logtype", C.c_double), ("batch", C.c_int), ("max_trace", C.c_int),
-                ("max_iter_guard", C.c_int), ("next_start", NEXT_START_FN), ("next_start_user", C.c_void_p)]
+                ("max_iter_guard", C.c_int), ("next_start", NEXT_START_FN), ("next_start_user", C.c_void_p),
+                ("affinity", C.c_int)]
 
 
 class EmStats(C.Structure):

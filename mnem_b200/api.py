@@ -404,7 +404,7 @@ def sample_init(S, k, starts, seed=0):
 
 
 def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, max_iter_guard=0, want_probs=True,
-           next_start=None):
+           next_start=None, affinity=0):
     """mnemcu_em_run on a Context: all starts, returns per-start arrays + winner + stats.
 
     next_start: optional callable returning the next start index to fit (or -1 when none is left) -- the ticket
@@ -433,7 +433,7 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
             return -1
 
     cb = _lib.NEXT_START_FN(_ticket) if next_start is not None else _lib.NEXT_START_FN()
-    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None)
+    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None, int(affinity))
     check(load_library().mnemcu_em_run(cx._h, starts, k, u8p(pb), C.byref(o), u8p(adj), i32p(theta), dp(probs), dp(mw),
                                        dp(ll), i32p(nit), dp(tr[0]), dp(tr[1]), dp(tr[2]), dp(tr[3]), C.byref(best),
                                        C.byref(st)))
@@ -449,7 +449,7 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
 
 
 def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0,
-         Rho=None):
+         Rho=None, affinity=0):
     """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho).
 
     Returns the fields of the reference's `mnem` object that the hot path produces: limits (per start), comp
@@ -466,13 +466,13 @@ def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, se
             phi = sample_init(cx.S, k, starts, seed)
         if k == 1:
             return _mnem_k1(cx, phi[0, 0], complete, logtype)
-        r = em_run(cx, phi, complete=complete, logtype=logtype, batch=batch, max_iter_guard=max_iter_guard)
+        r = em_run(cx, phi, complete=complete, logtype=logtype, batch=batch, max_iter_guard=max_iter_guard, affinity=affinity)
         b = r["best"]
         limits = [dict(adj=r["adj"][s], theta=r["theta"][s], probs=r["probs"][s], mw=r["mw"][s], ll=r["ll"][s],
                        lls=r["lls"][s], phievo=r["phievo"][s], thetaevo=r["thetaevo"][s], mwevo=r["mwevo"][s])
                   for s in range(starts)]
         probs = r["probs"][b]
-        post = getAffinity(probs, mw=r["mw"][b], logtype=logtype, complete=complete)        # R/mnems.r:2298-2303
+        post = getAffinity(probs, mw=r["mw"][b], logtype=logtype, complete=complete, affinity=affinity)   # R/mnems.r:2298-2303
         lam = post.sum(1)
         comp = [dict(phi=r["adj"][b][i], theta=r["theta"][b][i]) for i in range(k)]
         return dict(limits=limits, comp=comp, mw=lam / lam.sum(), probs=probs, lls=r["lls"][b], phievo=r["phievo"][b],

@@ -219,9 +219,10 @@ struct MixSlots {             // by-value kernel argument: one entry per mixture
 };
 constexpr int kMixBlocks = 296;    // blocks per mixture in the statistics kernel (2 per SM)
 // gamma = getAffinity(L, mw) for every slot (pad cells get 0)
-int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int complete, double logtype, cudaStream_t st);
+int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int hard, int complete, double logtype,
+                    cudaStream_t st);
 // ll = getLL(L, mw), mw_out = normalise(rowSums(getAffinity(L, mw))) for every slot; scratch: n*kMixBlocks*(k+1)
-int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, double *scratch,
+int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int hard, int complete, double logtype, double *scratch,
                      cudaStream_t st);
 // any(L > 0) over the valid cells of [k][Cp] into *flag (flag must be zeroed by the caller)
 int launch_anypos(const mnemcu_ctx *cx, const double *L, int k, int32_t *flag, cudaStream_t st);

@@ -99,7 +99,7 @@ struct Slot {
 
 struct Engine {
     mnemcu_ctx *cx = nullptr;
-    int k = 0, B = 0, M = 0, T = 10, complete = 0;
+    int k = 0, B = 0, M = 0, T = 10, complete = 0, affinity = 0;    // affinity: mnem(affinity =), 1 = hard assignments
     double logtype = 2.0;
     cudaStream_t st = nullptr;
     std::vector<Slot> slots;
@@ -250,7 +250,7 @@ struct Engine {
             ms.mw_out[j] = (to_tmp ? d_mwtmp.p : d_mw.p) + b * 32;
             ms.na_guard[j] = guard ? 1 : 0;
         }
-        return launch_mix_stats(cx, ms, k, complete, logtype, mixscratch.p, st);
+        return launch_mix_stats(cx, ms, k, affinity, complete, logtype, mixscratch.p, st);
     }
 
     int op_affinity(const std::vector<int> &list)
@@ -265,7 +265,7 @@ struct Engine {
             ms.mw[j] = d_mw.p + b * 32;
             ms.anypos[j] = flag(b, slots[b].cur);
         }
-        return launch_affinity(cx, ms, k, gamma_stride(M), complete, logtype, st);
+        return launch_affinity(cx, ms, k, gamma_stride(M), affinity, complete, logtype, st);
     }
 
     int op_mstats(bool unweighted = false)
@@ -487,8 +487,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     const int E = cx->E, C = cx->C, S = cx->S;
     int B = opts->batch > 0 ? opts->batch : std::max(1, 20 / k);
     B = std::min(B, std::min(starts, 32 / k));
+    MN_ARG(opts->affinity == 0 || opts->affinity == 1, "affinity must be 0 or 1");
+    MN_ARG(!(opts->affinity && opts->complete), "affinity = 1 with complete = TRUE is an error in the reference too");
     Engine en;
     MN_TRY(en.init(cx, k, B, opts->complete, opts->logtype, true));
+    en.affinity = opts->affinity;
     cudaStream_t st = en.st;
     const int T = en.T;
     const size_t kC = (size_t)k * C, kE = (size_t)k * E, kSS = (size_t)k * S * S;

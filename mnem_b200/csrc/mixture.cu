@@ -103,8 +103,10 @@ __device__ __forceinline__ double block_sum_256(double v, double *sm)
 }
 
 // partial[(slot*nb + blockIdx.x)*(k+1) + i] : i < k row sums of gamma, i == k log-likelihood
+// hard != 0: getAffinity(affinity = 1), R/mnems.r:1393-1417 -- per cell the components whose mw_i b^L_i equals the column
+// maximum count 1, the others 0 (only without `complete`: the reference's hard + complete branch is an error)
 template <bool kComplete, int KT>
-__global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, int k_rt, double b, double lb,
+__global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, int k_rt, int hard, double b, double lb,
                                                         double shrink_k, double *__restrict__ partial)
 {
     __shared__ double sm[8];
@@ -141,11 +143,24 @@ __global__ void __launch_bounds__(256) mix_stats_kernel(MixSlots s, MixGeom g, i
             // getLL: log(sum_i mw_i b^L_ic)/log(b), un-stabilised (R/mnems_low.r:547-549)
             const double cs = cell_terms<false, KT>(L, g.si, k, mw, false, 0.0, b, lb, xs, xraw);
             ll += log(cs) / lb;
+            if (hard) {
+                double mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < k; ++i) {
-                double z = k == 1 ? 1.0 : xs[i] / cs;
-                if (isnan(z)) z = 0.0;
-                rs[i] += z;
+                for (int i = 0; i < k; ++i) if (xs[i] > mx) mx = xs[i];
+#pragma unroll
+                for (int i = 0; i < k; ++i) {
+                    double z = xs[i] < mx ? 0.0 : xs[i];
+                    if (z != 0.0) z = 1.0;
+                    if (isnan(z)) z = 0.0;
+                    rs[i] += z;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < k; ++i) {
+                    double z = k == 1 ? 1.0 : xs[i] / cs;
+                    if (isnan(z)) z = 0.0;
+                    rs[i] += z;
+                }
             }
         }
     }
@@ -220,16 +235,17 @@ int launch_affinity_geom(const MixSlots &s, const MixGeom &g, int k, int hard, i
     return 0;
 }
 
-int launch_mix_stats_geom(const MixSlots &s, const MixGeom &g, int k, int complete, double logtype, double *scratch,
-                          cudaStream_t st)
+int launch_mix_stats_geom(const MixSlots &s, const MixGeom &g, int k, int hard, int complete, double logtype,
+                          double *scratch, cudaStream_t st)
 {
+    MN_ARG(!(hard && complete), "affinity = 1 with complete = TRUE is an error in the reference too");
     double lb, sk;
     consts(logtype, k, &lb, &sk);
     dim3 grid(kMixBlocks, s.n);
 #define MN_MIX(KT)                                                                                                 \
     do {                                                                                                           \
-        if (complete) MN_LAUNCH((mix_stats_kernel<true, KT>), grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch); \
-        else MN_LAUNCH((mix_stats_kernel<false, KT>), grid, 256, 0, st, s, g, k, logtype, lb, sk, scratch);         \
+        if (complete) MN_LAUNCH((mix_stats_kernel<true, KT>), grid, 256, 0, st, s, g, k, 0, logtype, lb, sk, scratch); \
+        else MN_LAUNCH((mix_stats_kernel<false, KT>), grid, 256, 0, st, s, g, k, hard, logtype, lb, sk, scratch);    \
     } while (0)
     switch (k) {       // the common mixture sizes get a compile-time k (registers instead of local-memory arrays)
         case 1: MN_MIX(1); break;
@@ -247,19 +263,21 @@ int launch_mix_stats_geom(const MixSlots &s, const MixGeom &g, int k, int comple
     return 0;
 }
 
-int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int complete, double logtype, cudaStream_t st)
+int launch_affinity(const mnemcu_ctx *cx, const MixSlots &s, int k, int gw, int hard, int complete, double logtype,
+                    cudaStream_t st)
 {
+    MN_ARG(!(hard && complete), "affinity = 1 with complete = TRUE is an error in the reference too");
     // L is [k][Cp]; gamma goes to the cell-major [Cp][gw] layout the M-step statistics kernel stages (s.gam[j] points at
     // the mixture's first column)
     MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig, 1, (long long)gw};
-    return launch_affinity_geom(s, g, k, 0, complete, logtype, st);
+    return launch_affinity_geom(s, g, k, hard, complete, logtype, st);
 }
 
-int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int complete, double logtype, double *scratch,
+int launch_mix_stats(const mnemcu_ctx *cx, const MixSlots &s, int k, int hard, int complete, double logtype, double *scratch,
                      cudaStream_t st)
 {
     MixGeom g{cx->Cp, (long long)cx->Cp, 1, cx->orig, 0, 0};
-    return launch_mix_stats_geom(s, g, k, complete, logtype, scratch, st);
+    return launch_mix_stats_geom(s, g, k, hard, complete, logtype, scratch, st);
 }
 
 int launch_anypos(const mnemcu_ctx *cx, const double *L, int k, int32_t *flag, cudaStream_t st)
@@ -307,7 +325,7 @@ static int mix_api(const double *L, int k, int C, const double *mw, int affinity
         MN_TRY(dscratch.alloc((size_t)kMixBlocks * (k + 1)));
         MN_TRY(dll.alloc(1));
         s.ll_out[0] = dll.p;
-        MN_TRY(launch_mix_stats_geom(s, g, k, complete, logtype, dscratch.p, 0));
+        MN_TRY(launch_mix_stats_geom(s, g, k, 0, complete, logtype, dscratch.p, 0));
         MN_CU(cudaMemcpy(ll_out, dll.p, sizeof(double), cudaMemcpyDeviceToHost));
     }
     MN_CU(cudaDeviceSynchronize());

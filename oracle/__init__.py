@@ -24,7 +24,7 @@ class NemInfo(C.Structure):
 
 class EmOpts(C.Structure):
     _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
-                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int)]
+                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int)]
 
 
 class EmInfo(C.Structure):
@@ -236,7 +236,7 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 
 # ---- EM --------------------------------------------------------------------------------------------------
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
-            max_iter_guard=0, noise_mode=0, acc="ld"):
+            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld"):
     """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
     D = _f(D)
     E, Cn = D.shape
@@ -250,7 +250,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     mw = np.zeros((starts, k))
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     infos = (EmInfo * starts)()
-    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode))
+    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode), int(affinity))
     best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
                                 _i32(theta), _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
     adj = _ungraphs(adj, starts * k, S).reshape(starts, k, S, S)
@@ -267,9 +267,9 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     return res
 
 
-def final_mw(L, mw_best, complete=False, logtype=2.0, acc="ld"):
+def final_mw(L, mw_best, complete=False, logtype=2.0, affinity=0, acc="ld"):
     L = _f(L)
     k, Cn = L.shape
     out = np.zeros(k)
-    lib(acc).orc_final_mw(_d(L), k, Cn, _d(_f(mw_best)), int(bool(complete)), C.c_double(logtype), _d(out))
+    lib(acc).orc_final_mw_a(_d(L), k, Cn, _d(_f(mw_best)), int(affinity), int(bool(complete)), C.c_double(logtype), _d(out))
     return out

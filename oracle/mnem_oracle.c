@@ -242,10 +242,10 @@ double orc_get_ll(const double *L, int k, int C, const double *mw_in, int comple
 
 /* mw <- apply(getAffinity(L, mw), 1, sum); mw <- mw/sum(mw); NA -> 1/k.  R/mnems_low.r:591-595, 653-657,
  * R/mnems.r:1936-1940, 2113-2121 (the NA guard exists only at :595 and :1940, selected by na_guard). */
-static void mw_update(const double *L, int k, int C, double *mw, int complete, double logtype, int na_guard,
+static void mw_update_a(const double *L, int k, int C, double *mw, int affinity, int complete, double logtype, int na_guard,
                       double *scratch)
 {
-    orc_get_affinity(L, k, C, mw, 0, complete, logtype, scratch);
+    orc_get_affinity(L, k, C, mw, affinity, complete, logtype, scratch);
     acc_t tot = 0;
     double rs[256];
     for (int i = 0; i < k; i++) {
@@ -257,6 +257,12 @@ static void mw_update(const double *L, int k, int C, double *mw, int complete, d
     int bad = 0;
     for (int i = 0; i < k; i++) { mw[i] = rs[i] / (double)tot; if (isnan(mw[i])) bad = 1; }
     if (bad && na_guard) for (int i = 0; i < k; i++) mw[i] = 1.0 / k;
+}
+
+static void mw_update(const double *L, int k, int C, double *mw, int complete, double logtype, int na_guard,
+                      double *scratch)
+{
+    mw_update_a(L, k, C, mw, 0, complete, logtype, na_guard, scratch);
 }
 
 void orc_mw_update(const double *L, int k, int C, double *mw, int complete, double logtype, int na_guard)
@@ -538,9 +544,9 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
  * :618-619).  L_in: k x C (the `probs` argument).  Outputs: L_out k x C (bestprobs), mw_out[k], returns ll
  * (llold of the last inner iteration, :661-662).  faithful_cost != 0 recomputes the contraction in every
  * inner iteration as the reference does (identical values when theta is given). */
-double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *phi,
-                     const int32_t *theta, const double *L_in, const double *mw_in, int complete, double logtype,
-                     int faithful_cost, double *L_out, double *mw_out, int32_t *theta_used)
+double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *phi,
+                       const int32_t *theta, const double *L_in, const double *mw_in, int affinity, int complete,
+                       double logtype, int faithful_cost, double *L_out, double *mw_out, int32_t *theta_used)
 {
     const int SS = S * S;
     size_t kc = (size_t)k * C;
@@ -558,13 +564,13 @@ double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, 
     for (int i = 0; i < k; i++) mw[i] = mw_in ? mw_in[i] : 1.0 / k;
     int max_count = C <= 100 ? 100 : 10;                                          /* :584-588 */
     double llold = -INFINITY;
-    mw_update(probs, k, C, mw, complete, logtype, 1, scratch);                   /* :591-595 */
+    mw_update_a(probs, k, C, mw, affinity, complete, logtype, 1, scratch);       /* :591-595 */
     for (int i = 0; i < k; i++) { memcpy(clo + (size_t)i * SS, phi + (size_t)i * SS, SS);
         for (int q = 0; q < SS; q++) clo[(size_t)i * SS + q] = clo[(size_t)i * SS + q] != 0;
         orc_mytc(clo + (size_t)i * SS, S); }                                     /* :610 */
     int have0 = 0;
     for (int count = 0; count < max_count; count++) {                            /* converged = -Inf: never stops early */
-        if (!theta) orc_get_affinity(probs, k, C, mw, 0, complete, logtype, post);   /* :601-603 (probsold = probs) */
+        if (!theta) orc_get_affinity(probs, k, C, mw, affinity, complete, logtype, post);   /* :601-603 (probsold = probs) */
         if (!theta || faithful_cost || !have0) {
             for (int i = 0; i < k; i++) {
                 const uint8_t *A = clo + (size_t)i * SS;
@@ -605,7 +611,7 @@ double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, 
         double ll0 = orc_get_ll(probs0, k, C, mw, complete, logtype);            /* :643 */
         if (ll0 - llold > 0) memcpy(best, probs0, sizeof(double) * kc);          /* :646-648 */
         memcpy(probs, probs0, sizeof(double) * kc);                              /* :649 */
-        mw_update(probs, k, C, mw, complete, logtype, 0, scratch);               /* :653-657 */
+        mw_update_a(probs, k, C, mw, affinity, complete, logtype, 0, scratch);   /* :653-657 */
         llold = ll0;                                                             /* :658 */
     }
     memcpy(L_out, best, sizeof(double) * kc);
@@ -613,6 +619,14 @@ double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, 
     if (theta_used) for (size_t i = 0; i < (size_t)k * E; i++) theta_used[i] = th[i] == S + 1 ? 0 : th[i];
     free(probs); free(probs0); free(best); free(post); free(scratch); free(clo); free(th); free(Wtmp);
     return llold;
+}
+
+double orc_get_probs(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *phi,
+                     const int32_t *theta, const double *L_in, const double *mw_in, int complete, double logtype,
+                     int faithful_cost, double *L_out, double *mw_out, int32_t *theta_used)
+{
+    return orc_get_probs_a(D, E, C, pert, S, k, phi, theta, L_in, mw_in, 0, complete, logtype, faithful_cost, L_out, mw_out,
+                           theta_used);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -628,6 +642,7 @@ typedef struct {
                              * routinely decided by the last bit of ll once the graphs have stopped changing; 1 / 2
                              * resolve such noise-level (<= 1e-12 relative) comparisons as FALSE / TRUE so that both
                              * legitimate outcomes can be enumerated */
+    int affinity;           /* mnem(affinity =): 0 soft responsibilities, 1 hard assignments in every getAffinity call */
 } orc_em_opts;
 
 typedef struct {
@@ -668,11 +683,12 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     memcpy(res1_adj, init_phi, (size_t)k * SS);                                   /* :1885-1893 */
     memset(res1_th, 0, sizeof(int32_t) * (size_t)k * E);
     memset(probs, 0, sizeof(double) * kc);                                        /* :1905 */
-    double probs_ll = orc_get_probs(D, E, C, pert, S, k, res1_adj, NULL, probs, mw, complete, logtype,
-                                    o->faithful_cost, newp, mwnew, NULL);         /* :1906-1911 */
+    const int affinity = o->affinity;
+    double probs_ll = orc_get_probs_a(D, E, C, pert, S, k, res1_adj, NULL, probs, mw, affinity, complete, logtype,
+                                      o->faithful_cost, newp, mwnew, NULL);       /* :1906-1911 */
     memcpy(probs, newp, sizeof(double) * kc);
     for (int i = 0; i < k; i++) mw[i] = mwnew[i];                                  /* :1913 */
-    mw_update(probs, k, C, mw, complete, logtype, 1, scratch);                    /* :1936-1940 */
+    mw_update_a(probs, k, C, mw, affinity, complete, logtype, 1, scratch);        /* :1936-1940 */
     double ll = -INFINITY, llold = -INFINITY, bestll = -INFINITY;                 /* :1945-1948 */
     for (int i = 0; i < k; i++) bestmw[i] = mw[i];
     memcpy(probsold, probs, sizeof(double) * kc);
@@ -697,7 +713,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
             llold = ll;                                                           /* :1964-1965 */
             memcpy(probsold, probs, sizeof(double) * kc); probsold_ll = probs_ll;
         }
-        orc_get_affinity(probs, k, C, mw, 0, complete, logtype, post);            /* :1968-1973 */
+        orc_get_affinity(probs, k, C, mw, affinity, complete, logtype, post);     /* :1968-1973 */
         double edgechange = 0, thetachange = 0;
         for (int i = 0; i < k; i++) {                                             /* :1976-2086 */
             for (int c = 0; c < C; c++) gam[c] = post[i + (size_t)c * k];
@@ -728,8 +744,8 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
         memcpy(res1_th, res_th, sizeof(int32_t) * (size_t)k * E);
         have_res1_theta = 1;
         /* E-step :2095-2108 */
-        double newll = orc_get_probs(D, E, C, pert, S, k, res1_adj, res1_th, probsold, mw, complete, logtype,
-                                     o->faithful_cost, newp, mwnew, NULL);
+        double newll = orc_get_probs_a(D, E, C, pert, S, k, res1_adj, res1_th, probsold, mw, affinity, complete, logtype,
+                                       o->faithful_cost, newp, mwnew, NULL);
         if (isfinite(newll) && isfinite(probsold_ll)) {
             double mg = fabs(newll - probsold_ll) / (fabs(probsold_ll) > 1e-300 ? fabs(probsold_ll) : 1e-300);
             if (mg < acceptmargin) acceptmargin = mg;
@@ -744,7 +760,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
         ll = probs_ll;                                                            /* :2111, evopen = 0 */
         double mwold[256];
         for (int i = 0; i < k; i++) mwold[i] = mw[i];
-        mw_update(probs, k, C, mw, complete, logtype, 0, scratch);                /* :2113-2121 */
+        mw_update_a(probs, k, C, mw, affinity, complete, logtype, 0, scratch);    /* :2113-2121 */
         acc_t dm = 0;
         for (int i = 0; i < k; i++) dm += fabs(mw[i] - mwold[i]);
         if (count < o->max_trace) { lls[count] = ll; phievo[count] = edgechange; thetaevo[count] = thetachange;
@@ -800,12 +816,19 @@ int orc_mnem_em(const double *D, int E, int C, const int32_t *pert, int S, int k
 }
 
 /* Final mixture weights of the returned object: lambda0, R/mnems.r:2298-2303. */
+void orc_final_mw_a(const double *L, int k, int C, const double *mw_best, int affinity, int complete, double logtype,
+                    double *out);
 void orc_final_mw(const double *L, int k, int C, const double *mw_best, int complete, double logtype, double *out)
+{
+    orc_final_mw_a(L, k, C, mw_best, 0, complete, logtype, out);
+}
+void orc_final_mw_a(const double *L, int k, int C, const double *mw_best, int affinity, int complete, double logtype,
+                    double *out)
 {
     for (int i = 0; i < k; i++) out[i] = mw_best[i];
     if (k == 1) { out[0] = 1.0; return; }
     double *scratch = (double *)malloc(sizeof(double) * (size_t)k * C);
-    mw_update(L, k, C, out, complete, logtype, 0, scratch);
+    mw_update_a(L, k, C, out, affinity, complete, logtype, 0, scratch);
     free(scratch);
 }
 

@@ -233,7 +233,7 @@ List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0
     std::vector<double> probs((size_t)starts * k * C), mw((size_t)starts * k), ll(starts);
     std::vector<double> lls((size_t)starts * max_trace), pe(lls.size()), te(lls.size()), me(lls.size());
     int32_t best = -1;
-    mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr};
+    mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr, 0};
     mnemcu_em_stats st;
     chk(mnemcu_em_run(cx, starts, k, phi.data(), &o, adj.data(), theta.data(), probs.data(), mw.data(), ll.data(),
                       nit.data(), lls.data(), pe.data(), te.data(), me.data(), &best, &st));

@@ -241,12 +241,14 @@ def test_get_probs_theta_free(S, E, Cn, k):
 
 
 # ---- the EM loop -------------------------------------------------------------------------------------------------
-def check_em(sim, D, init, complete, batch=0, gpu_pert=None):
+def check_em(sim, D, init, complete, batch=0, gpu_pert=None, affinity=0):
     """gpu_pert: what the CUDA side is given when it differs from the oracle's encoding sim["pert"] (the Rho path:
     "_"-joined labels for the GPU, -mask integers for the oracle)."""
-    refs = [orc.mnem_em(D, sim["pert"], sim["S"], init, complete=complete, nthreads=8, noise_mode=m) for m in (0, 1, 2)]
+    refs = [orc.mnem_em(D, sim["pert"], sim["S"], init, complete=complete, nthreads=8, noise_mode=m, affinity=affinity)
+            for m in (0, 1, 2)]
     ref = refs[0]
-    res = mb.mnem(D, sim["pert"] if gpu_pert is None else gpu_pert, phi=init, complete=complete, batch=batch)
+    res = mb.mnem(D, sim["pert"] if gpu_pert is None else gpu_pert, phi=init, complete=complete, batch=batch,
+                  affinity=affinity)
     starts = init.shape[0]
     # Decision margins (SURVEY section 7): a greedy / restart decision closer than 1e-13 relative is rounding noise
     # in ANY implementation -- such a case cannot pin anything, pick another seed.
@@ -273,7 +275,7 @@ def check_em(sim, D, init, complete, batch=0, gpu_pert=None):
     assert res["stats"]["em_iters"] == ref["n_iter"].sum()
     assert res["stats"]["cand_scored"] == ref["n_raw"].sum()
     b = res["best_start"]
-    lams = [orc.final_mw(r["probs"][b], r["mw"][b], complete=complete) for r in refs]
+    lams = [orc.final_mw(r["probs"][b], r["mw"][b], complete=complete, affinity=affinity) for r in refs]
     assert any(np.allclose(res["mw"], lam, rtol=RTOL, atol=0) for lam in lams), (res["mw"], lams)
     return res, ref
 
@@ -313,6 +315,19 @@ def test_em_many_pairs_few_cells():
         got = mb.getProbs(one["probs"][s], 5, cx, res, mw=one["mw"][s], complete=True)
         close(got["probs"], want["probs"], rtol=1e-11, atol=1e-11)
         close(one["probs"][s], want["probs"], rtol=1e-11, atol=1e-11)
+
+
+def test_em_hard_assignments():
+    """mnem(affinity = 1): every getAffinity call of the loop returns 0/1 assignments (R/mnems.r:1393-1417) -- the
+    M-step weights, the mixture-weight updates and the final lambda."""
+    sim = simdata.make_config(dict(S=6, Egenes=5, C=1500, mw=[0.3, 0.3, 0.4], k=3, starts=5, uninform=2), seed=12)
+    D = simdata.host_data(sim) + np.random.default_rng(3).normal(size=(sim["E"], sim["C"])) * 0.5
+    init = simdata.init_phi(sim["S"], 3, 5, seed=2)
+    res, ref = check_em(sim, D, init, complete=False, affinity=1)
+    soft = mb.mnem(D, sim["pert"], phi=init)
+    assert not np.array_equal(res["n_iter"], soft["n_iter"]) or not np.allclose(res["ll"], soft["ll"])   # a different fit
+    with pytest.raises(mb.MnemcuError):
+        mb.mnem(D, sim["pert"], phi=init, complete=True, affinity=1)     # an error in the reference too
 
 
 def test_em_config2_shape_complete():
