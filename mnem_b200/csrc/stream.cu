@@ -5,6 +5,8 @@
 //
 // Both read the expression matrix exactly once per launch and serve up to 32 (start, component) pairs, so
 // the algorithmic traffic is 8*E*C bytes in plus the small outputs.  FP64 throughout.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mn {
@@ -128,6 +130,13 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
     int esplit = 1;
     const long warps = (long)cx->nblk * groups;
     while (esplit * groups < 8 && warps * esplit < 16L * cx->sm_count && cx->E / (esplit * 2) >= 64) esplit *= 2;
+    // Register-limited residency (about 45 + 4 MT registers per thread): a grid of between one and ~2.5 waves leaves a
+    // long tail, so split once more (cfg3 shape, 20 pairs: 1.32 waves at 2 warps per block, 0.189 -> 0.164 ms at 4).
+    {
+        const long resident = (long)cx->sm_count * std::min(64, 65536 / ((45 + 4 * MT) * 32));
+        const double waves = (double)(warps * esplit) / (double)resident;
+        if (waves > 1.0 && waves < 2.5 && esplit * groups < 8 && cx->E / (esplit * 2) >= 64) esplit *= 2;
+    }
     switch (MT) {
 #define MN_CASE(v) case v: return launch_estep_t<v>(cx, maskT, M, out, esplit, st);
         MN_CASE(1) MN_CASE(2) MN_CASE(3) MN_CASE(4) MN_CASE(5) MN_CASE(6) MN_CASE(7) MN_CASE(8) MN_CASE(9) MN_CASE(10)
