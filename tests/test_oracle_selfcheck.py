@@ -347,3 +347,26 @@ def test_marginal_score_matches_the_formula(logtype):
     r = orc.nem_greedy(R, None, marginal=True, logtype=logtype)
     s0 = orc.score_adj(R, np.zeros((S, S)), marginal=True, logtype=logtype)[0]
     assert r["score"] >= s0 and r["max_trace"] == r["score"]
+
+
+# ---- affinity = 1: hard assignments (R/mnems.r:1393-1417) -----------------------------------------------------------
+def test_hard_assignments_in_the_oracle_em():
+    rng = np.random.default_rng(21)
+    k, Cn = 3, 500
+    L = rng.normal(size=(k, Cn)) * 5
+    mw = np.array([0.2, 0.5, 0.3])
+    post = orc.get_affinity(L, mw, affinity=1)
+    y = 2.0 ** L * mw[:, None]
+    assert np.array_equal(post, (y == y.max(0, keepdims=True)).astype(float))      # one 1 per cell (ties: several)
+    lam = orc.final_mw(L, mw, affinity=1)
+    np.testing.assert_allclose(lam, post.sum(1) / post.sum(), rtol=1e-15)
+    # the EM loop with hard assignments runs, differs from the soft fit, and keeps its invariants
+    sim = simdata.make_config(dict(S=4, Egenes=4, C=400, mw=[0.5, 0.5], k=2, starts=3, uninform=0), seed=9)
+    D = simdata.host_data(sim) + rng.normal(size=(sim["E"], sim["C"])) * 0.5
+    init = simdata.init_phi(4, 2, 3, seed=3)
+    hard = orc.mnem_em(D, sim["pert"], 4, init, affinity=1)
+    soft = orc.mnem_em(D, sim["pert"], 4, init, affinity=0)
+    assert not np.allclose(hard["ll"], soft["ll"])
+    for s in range(3):
+        assert (np.diff(hard["lls"][s]) >= 0).all()
+        np.testing.assert_allclose(hard["mw"][s].sum(), 1.0, rtol=1e-12)
