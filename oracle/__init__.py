@@ -19,7 +19,7 @@ c_i32p = C.POINTER(C.c_int32)
 
 class NemInfo(C.Structure):
     _fields_ = [("score", C.c_double), ("max_trace", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
-                ("min_margin", C.c_double), ("n_raw", C.c_long)]
+                ("min_margin", C.c_double), ("n_raw", C.c_long), ("n_dec", C.c_long), ("n_dec_tight", C.c_long)]
 
 
 class EmOpts(C.Structure):
@@ -30,7 +30,7 @@ class EmOpts(C.Structure):
 class EmInfo(C.Structure):
     _fields_ = [("ll", C.c_double), ("best_ll", C.c_double), ("n_iter", C.c_int), ("n_scored", C.c_long),
                 ("n_greedy_iter", C.c_long), ("min_margin", C.c_double), ("n_raw", C.c_long),
-                ("min_accept_margin", C.c_double)]
+                ("min_accept_margin", C.c_double), ("n_dec", C.c_long), ("n_dec_tight", C.c_long)]
 
 
 def build():
@@ -51,6 +51,12 @@ def lib(acc="ld"):
         _LIBS[acc].orc_score_adj_m.restype = C.c_double
         _LIBS[acc].orc_get_probs.restype = C.c_double
     return _LIBS[acc]
+
+
+def set_inner_threads(n, acc="ld"):
+    """Threads INSIDE one fit (cells / E-gene rows / candidates; bit-identical results for any n).  For fits at
+    BASELINE scale; the default 1 keeps every loop serial.  Do not combine with mnem_em(nthreads > 1)."""
+    lib(acc).orc_set_inner_threads(int(n))
 
 
 def _d(a):
@@ -211,7 +217,8 @@ def nem_greedy(R, start=None, marginal=False, logtype=2.0, acc="ld"):
     lib(acc).orc_nem_greedy_m(_d(R), E, S, _u8(sb) if sb is not None else None, int(bool(marginal)), C.c_double(logtype),
                               _u8(adj), _i32(theta), C.byref(info))
     return dict(adj=_ungraphs(adj, 1, S)[0], theta=theta, score=info.score, max_trace=info.max_trace,
-                n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin, n_raw=info.n_raw)
+                n_iter=info.n_iter, n_scored=info.n_scored, min_margin=info.min_margin, n_raw=info.n_raw,
+                n_dec=info.n_dec, n_dec_tight=info.n_dec_tight)
 
 
 # ---- E-step ----------------------------------------------------------------------------------------------
@@ -260,6 +267,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
                n_scored=np.array([i.n_scored for i in infos]), n_greedy_iter=np.array([i.n_greedy_iter for i in infos]),
                min_margin=np.array([i.min_margin for i in infos]), n_raw=np.array([i.n_raw for i in infos]),
                min_accept_margin=np.array([i.min_accept_margin for i in infos]),
+               n_dec=np.array([i.n_dec for i in infos]), n_dec_tight=np.array([i.n_dec_tight for i in infos]),
                lls=[tr[0][s, :n_iter[s]].copy() for s in range(starts)],
                phievo=[tr[1][s, :n_iter[s]].copy() for s in range(starts)],
                thetaevo=[tr[2][s, :n_iter[s]].copy() for s in range(starts)],
@@ -272,4 +280,57 @@ def final_mw(L, mw_best, complete=False, logtype=2.0, affinity=0, acc="ld"):
     k, Cn = L.shape
     out = np.zeros(k)
     lib(acc).orc_final_mw_a(_d(L), k, Cn, _d(_f(mw_best)), int(affinity), int(bool(complete)), C.c_double(logtype), _d(out))
+    return out
+
+
+# ---- the reference's own src/mm.cpp, compiled unmodified (oracle/_ref/libmm_ref.so) --------------------------
+_REF = {}
+
+
+def ref_lib():
+    """The reference's src/mm.cpp compiled verbatim against the stub headers of oracle/rstub (oracle/Makefile).  Built
+    where /root/reference exists; elsewhere (the GPU box) the prebuilt oracle/_ref/libmm_ref.so is loaded.  Returns
+    None when neither is available."""
+    if "lib" not in _REF:
+        path = os.path.join(_HERE, "_ref", "libmm_ref.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/src/mm.cpp"):
+            build()
+        _REF["lib"] = C.CDLL(path) if os.path.exists(path) else None
+    return _REF["lib"]
+
+
+def _ref_graph(x):
+    return np.asfortranarray(np.asarray(x, dtype=np.float64)).copy(order="F")
+
+
+def ref_trans_close_w(x):
+    """transClose_W(x) of src/mm.cpp:15-30 on an R-style double matrix (returned as uint8 0/1)."""
+    b = _ref_graph(x)
+    ref_lib().mmref_trans_close_w(_d(b), b.shape[0])
+    return b.astype(np.uint8)
+
+
+def ref_trans_close_ins(x, u, v):
+    b = _ref_graph(x)
+    ref_lib().mmref_trans_close_ins(_d(b), b.shape[0], int(u), int(v))
+    return b.astype(np.uint8)
+
+
+def ref_trans_close_del(x, u, v):
+    b = _ref_graph(x)
+    ref_lib().mmref_trans_close_del(_d(b), b.shape[0], int(u), int(v))
+    return b.astype(np.uint8)
+
+
+def ref_max_col_row(x):
+    x = _f(x).copy(order="F")
+    out = np.zeros(x.shape[0], dtype=np.int32)
+    ref_lib().mmref_max_col_row(_d(x), x.shape[0], x.shape[1], _i32(out))
+    return out
+
+
+def ref_matmul(A, B):
+    A, B = _f(A).copy(order="F"), _f(B).copy(order="F")
+    out = np.zeros((A.shape[0], B.shape[1]), order="F")
+    ref_lib().mmref_matmul(_d(A), _d(B), A.shape[0], A.shape[1], B.shape[1], _d(out))
     return out

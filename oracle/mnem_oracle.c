@@ -30,6 +30,7 @@
  * contribution of a cell with n > 1 knock-downs by n (R/mnems_low.r:896-904).  Masks need S <= 31.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,6 +45,19 @@ typedef long double acc_t;
 #endif
 
 #define ORC_MAXS 64
+
+/* Inner parallelism for single fits at BASELINE scale (tests/golden/make_scale_golden.py): OpenMP threads split
+ * INDEPENDENT outputs only -- cells of the E-step, E-gene rows of the two contractions, candidates of a greedy
+ * iteration, rows of the mixture sums -- so every accumulator still receives the same addends in the same order
+ * and results are bit-identical for any thread count (tests/test_oracle_properties.py).  Default 1 (serial). */
+static int g_inner = 1;
+void orc_set_inner_threads(int n) { g_inner = n < 1 ? 1 : n; }
+int orc_get_inner_threads(void) { return g_inner; }
+#ifdef _OPENMP
+#define ORC_PAR_FOR _Pragma("omp parallel for schedule(static) num_threads(g_inner) if (g_inner > 1)")
+#else
+#define ORC_PAR_FOR
+#endif
 
 /* set of knocked-down S-genes of a cell as a bit mask (see the note on `pert` above) */
 static inline uint32_t pert_mask(int32_t p) { return p > 0 ? 1u << (p - 1) : (uint32_t)(-(int64_t)p); }
@@ -166,6 +180,7 @@ void orc_get_affinity(const double *L, int k, int C, const double *mw_in, int af
     const double *mw = mw_in;
     if (!mw) { for (int i = 0; i < k; i++) mwbuf[i] = 1.0 / k; mw = mwbuf; }   /* :1392 */
     if (affinity == 1) {
+        ORC_PAR_FOR
         for (int c = 0; c < C; c++) {
             double mx = -INFINITY;
             for (int i = 0; i < k; i++) {
@@ -188,6 +203,7 @@ void orc_get_affinity(const double *L, int k, int C, const double *mw_in, int af
         for (size_t i = 0; i < (size_t)k * C; i++) if (L[i] > 0) { shift = 1; break; }
     }
     double shrink = log(ldexp(1.0, 1023)) / log(logtype);                                /* :1425-1426 */
+    ORC_PAR_FOR
     for (int c = 0; c < C; c++) {
         const double *x = L + (size_t)c * k;
         double *y = out + (size_t)c * k;
@@ -223,19 +239,27 @@ double orc_get_ll(const double *L, int k, int C, const double *mw_in, int comple
         orc_get_affinity(L, k, C, mw, 0, 1, logtype, Z);
         double lmw[256];
         for (int i = 0; i < k; i++) lmw[i] = log(mw[i]) / log(logtype);
+        double *term = (double *)malloc(sizeof(double) * (size_t)C);
+        ORC_PAR_FOR
         for (int c = 0; c < C; c++) {
             acc_t s = 0;
             for (int i = 0; i < k; i++) s += Z[i + (size_t)c * k] * (L[i + (size_t)c * k] + lmw[i]);
-            l += (double)s;
+            term[c] = (double)s;
         }
+        for (int c = 0; c < C; c++) l += term[c];            /* sum(): one sequential long-double accumulator */
+        free(term);
         free(Z);
     } else {                                                                              /* :547-549 */
         double lb = log(logtype);
+        double *term = (double *)malloc(sizeof(double) * (size_t)C);
+        ORC_PAR_FOR
         for (int c = 0; c < C; c++) {
             double s = 0.0;                                 /* rep(1,k) %*% x : double, ascending k */
             for (int i = 0; i < k; i++) s += 1.0 * (rpow(logtype, L[i + (size_t)c * k]) * mw[i]);
-            l += log(s) / lb;
+            term[c] = log(s) / lb;
         }
+        for (int c = 0; c < C; c++) l += term[c];
+        free(term);
     }
     return (double)l;
 }
@@ -248,6 +272,7 @@ static void mw_update_a(const double *L, int k, int C, double *mw, int affinity,
     orc_get_affinity(L, k, C, mw, affinity, complete, logtype, scratch);
     acc_t tot = 0;
     double rs[256];
+    ORC_PAR_FOR
     for (int i = 0; i < k; i++) {
         acc_t s = 0;
         for (int c = 0; c < C; c++) s += scratch[i + (size_t)c * k];
@@ -279,32 +304,62 @@ void orc_mw_update(const double *L, int k, int C, double *mw, int complete, doub
 /* The caller block R/mnems.r:1986-2006 drops zero-weight cells and appends S all-zero cells: the sums  */
 /* are unchanged.  weights == NULL: plain D (k == 1 path, R/mnems.r:1851).                               */
 /* ------------------------------------------------------------------------------------------------ */
-void orc_do_mean(const double *D, int E, int C, const int32_t *pert, int S, const double *w, double *R)
+/* rows [e0, e1) of nw collapsed matrices at once: weight q of cell c is w[q + c*stride] (w == NULL: plain D), output q
+ * is R + q*E*S.  One pass over D; every R[e,s] still receives its addends in ascending cell order. */
+static void do_mean_slice(const double *D, int E, int C, const int32_t *pert, int S, int nw, const double *w, size_t stride,
+                          double *R, int e0, int e1)
 {
-    memset(R, 0, sizeof(double) * (size_t)E * S);
+    for (int q = 0; q < nw; q++)
+        for (int s = 0; s < S; s++) memset(R + ((size_t)q * S + s) * E + e0, 0, sizeof(double) * (size_t)(e1 - e0));
     for (int c = 0; c < C; c++) {
-        if (w && w[c] == 0.0) continue;
         const double *d = D + (size_t)c * E;
         const uint32_t pm = pert_mask(pert[c]);
         const int n = __builtin_popcount(pm);
-        if (n == 1) {
-            double *r = R + (size_t)__builtin_ctz(pm) * E;
-            if (w) {
-                double wc = w[c];
-                for (int e = 0; e < E; e++) r[e] += d[e] * wc;   /* built with -ffp-contract=off: mul then add */
-            } else {
-                for (int e = 0; e < E; e++) r[e] += d[e];
-            }
-        } else if (n > 1) {
-            /* Rho column normalised to sum 1 (:897-902): each knocked-down S-gene receives (D*w) * (1/n) */
-            const double rho = 1.0 / n;
-            for (int s = 0; s < S; s++)
-                if ((pm >> s) & 1u) {
-                    double *r = R + (size_t)s * E;
-                    for (int e = 0; e < E; e++) r[e] += (w ? d[e] * w[c] : d[e]) * rho;
+        for (int q = 0; q < nw; q++) {
+            const double wc = w ? w[q + (size_t)c * stride] : 1.0;
+            if (w && wc == 0.0) continue;
+            double *Rq = R + (size_t)q * S * E;
+            if (n == 1) {
+                double *r = Rq + (size_t)__builtin_ctz(pm) * E;
+                if (w) {
+                    for (int e = e0; e < e1; e++) r[e] += d[e] * wc;   /* built with -ffp-contract=off: mul then add */
+                } else {
+                    for (int e = e0; e < e1; e++) r[e] += d[e];
                 }
+            } else if (n > 1) {
+                /* Rho column normalised to sum 1 (:897-902): each knocked-down S-gene receives (D*w) * (1/n) */
+                const double rho = 1.0 / n;
+                for (int s = 0; s < S; s++)
+                    if ((pm >> s) & 1u) {
+                        double *r = Rq + (size_t)s * E;
+                        for (int e = e0; e < e1; e++) r[e] += (w ? d[e] * wc : d[e]) * rho;
+                    }
+            }
         }
     }
+}
+
+/* nw weight vectors (rows of a k x C column-major matrix when stride = k), one pass; threads own E-gene row ranges */
+static void do_mean_multi(const double *D, int E, int C, const int32_t *pert, int S, int nw, const double *w, size_t stride,
+                          double *R)
+{
+    int nt = g_inner < 1 ? 1 : g_inner;
+    if (nt > (E + 7) / 8) nt = (E + 7) / 8;
+    if (nt <= 1) { do_mean_slice(D, E, C, pert, S, nw, w, stride, R, 0, E); return; }
+    int t;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+#endif
+    for (t = 0; t < nt; t++) {
+        const int per = ((E + nt - 1) / nt + 7) / 8 * 8;
+        const int e0 = t * per, e1 = e0 + per < E ? e0 + per : E;
+        if (e0 < e1) do_mean_slice(D, E, C, pert, S, nw, w, stride, R, e0, e1);
+    }
+}
+
+void orc_do_mean(const double *D, int E, int C, const int32_t *pert, int S, const double *w, double *R)
+{
+    do_mean_multi(D, E, C, pert, S, 1, w, 1, R);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -455,6 +510,9 @@ typedef struct {
     long n_scored;       /* scoreAdj calls inside the loop (unique candidates) */
     double min_margin;   /* smallest |best - runner-up or old| seen in a decision, relative; diagnostic */
     long n_raw;          /* candidates generated before unique() */
+    long n_dec;          /* greedy decisions taken (one argmax + accept/stop test per iteration) */
+    long n_dec_tight;    /* ... of which the winner beat the runner-up or the old score by less than 1e-13 relative (but not
+                          * by exactly 0): decided by the last bits of the sums, i.e. by the summation order / accumulator width */
 } orc_nem_info;
 
 void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int marginal, double logtype,
@@ -482,7 +540,7 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
     int haveP = 0;
     double oldscore = orc_score_adj_m(R, E, S, better, 1, marginal, logtype, NULL, NULL);   /* :135-141 closes inside */
     double maxtrace = oldscore;
-    long nscored = 0, nraw = 0;
+    long nscored = 0, nraw = 0, ndec = 0, ntight = 0;
     int niter = 0;
     double minmargin = INFINITY;
     for (;;) {
@@ -492,34 +550,72 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
         if (nm == 0) break;
         double bests = -INFINITY, second = -INFINITY;
         int bestidx = -1;
-        for (int m = 0; m < nm; m++) {
-            const uint8_t *cand = models + (size_t)m * SS;
-            double sc;
-            if (!haveP) {                                                        /* :439-440 */
-                score_cols(R, E, S, cand, NULL, Wc);
-            } else {                                                             /* :441-446 */
-                uint8_t chg[ORC_MAXS];
-                for (int j = 0; j < S; j++) {
-                    chg[j] = 0;
-                    for (int s = 0; s < S; s++) if (cand[s + j * S] != better[s + j * S]) { chg[j] = 1; break; }
-                }
-                memcpy(Wc, P, sizeof(double) * (size_t)E * S);
-                score_cols(R, E, S, cand, chg, Wc);
+        /* scoreAdj of one candidate into Wbuf; returns the score (NA -> 0, :235) */
+#define ORC_SCORE_CAND(m_, Wbuf_, sc_)                                                                       \
+        do {                                                                                                 \
+            const uint8_t *cand_ = models + (size_t)(m_) * SS;                                               \
+            if (!haveP) {                                                        /* :439-440 */              \
+                score_cols(R, E, S, cand_, NULL, (Wbuf_));                                                   \
+            } else {                                                             /* :441-446 */              \
+                uint8_t chg_[ORC_MAXS];                                                                      \
+                for (int j = 0; j < S; j++) {                                                                \
+                    chg_[j] = 0;                                                                             \
+                    for (int s_ = 0; s_ < S; s_++) if (cand_[s_ + j * S] != better[s_ + j * S]) { chg_[j] = 1; break; } \
+                }                                                                                            \
+                memcpy((Wbuf_), P, sizeof(double) * (size_t)E * S);                                          \
+                score_cols(R, E, S, cand_, chg_, (Wbuf_));                                                   \
+            }                                                                                                \
+            (sc_) = marginal ? score_total_marginal((Wbuf_), E, S, logtype, NULL) : score_total((Wbuf_), E, S, NULL); \
+            if (isnan(sc_)) (sc_) = 0.0;                                         /* :235 */                  \
+        } while (0)
+        if (g_inner > 1 && nm > 1) {
+            /* candidates are independent: score them on g_inner threads, then take which.max in candidate order */
+            double *scs = (double *)malloc(sizeof(double) * (size_t)nm);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(g_inner)
+#endif
+            {
+                double *Wt = (double *)malloc(sizeof(double) * (size_t)E * S);
+                int m;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 8)
+#endif
+                for (m = 0; m < nm; m++) { double sc; ORC_SCORE_CAND(m, Wt, sc); scs[m] = sc; }
+                free(Wt);
             }
-            sc = marginal ? score_total_marginal(Wc, E, S, logtype, NULL) : score_total(Wc, E, S, NULL);
-            if (isnan(sc)) sc = 0.0;                                             /* :235 */
-            nscored++;
-            if (sc > bests) {                                                    /* which.max: first */
-                second = bests; bests = sc; bestidx = m;
-                memcpy(Pbest, Wc, sizeof(double) * (size_t)E * S);
-            } else if (sc > second && sc < bests) second = sc;
+            for (int m = 0; m < nm; m++) {
+                const double sc = scs[m];
+                nscored++;
+                if (sc > bests) { second = bests; bests = sc; bestidx = m; }     /* which.max: first */
+                else if (sc > second && sc < bests) second = sc;
+            }
+            free(scs);
+            { double sc; ORC_SCORE_CAND(bestidx, Pbest, sc); (void)sc; }          /* subweights of the winner */
+        } else {
+            for (int m = 0; m < nm; m++) {
+                double sc;
+                ORC_SCORE_CAND(m, Wc, sc);
+                nscored++;
+                if (sc > bests) {                                                /* which.max: first */
+                    second = bests; bests = sc; bestidx = m;
+                    memcpy(Pbest, Wc, sizeof(double) * (size_t)E * S);
+                } else if (sc > second && sc < bests) second = sc;
+            }
         }
+#undef ORC_SCORE_CAND
         const uint8_t *best = models + (size_t)bestidx * SS;
         int nb = 0, nc = 0;
         for (int i = 0; i < SS; i++) { nb += better[i] == 1; nc += best[i] == 1; }
         double scale = fabs(bests) > 1e-300 ? fabs(bests) : 1e-300;   /* margins relative to the score itself */
         if (bests != oldscore && fabs(bests - oldscore) / scale < minmargin) minmargin = fabs(bests - oldscore) / scale;
         if (isfinite(second) && (bests - second) / scale < minmargin) minmargin = (bests - second) / scale;
+        ndec++;
+        if ((bests != oldscore && fabs(bests - oldscore) / scale < 1e-13) ||
+            (isfinite(second) && (bests - second) / scale < 1e-13)) ntight++;
+        if (getenv("ORC_TRACE_MARGIN") && ((bests != oldscore && fabs(bests - oldscore) / scale < 1e-13) ||
+                                           (isfinite(second) && (bests - second) / scale < 1e-13)))
+            fprintf(stderr, "near-tie: greedy iter %d nm %d best %.17g (idx %d kind %d) second %.17g old %.17g\n", niter, nm,
+                    bests, bestidx, (int)kind[bestidx], second, oldscore);
         if (bests > oldscore || (bests == oldscore && nb > nc)) {                /* :279-286 */
             memcpy(tmp, best, SS); memcpy(better, tmp, SS);
             oldscore = bests;
@@ -533,7 +629,7 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
     orc_score_adj_m(R, E, S, better, 1, marginal, logtype, theta_out, NULL);
     orc_trans_reduce(better, S, adj_out);
     if (info) { info->score = oldscore; info->max_trace = maxtrace; info->n_iter = niter; info->n_scored = nscored;
-                info->min_margin = minmargin; info->n_raw = nraw; }
+                info->min_margin = minmargin; info->n_raw = nraw; info->n_dec = ndec; info->n_dec_tight = ntight; }
     free(P); free(Wc); free(Pbest); free(models); free(kind);
 }
 
@@ -571,7 +667,66 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
     int have0 = 0;
     for (int count = 0; count < max_count; count++) {                            /* converged = -Inf: never stops early */
         if (!theta) orc_get_affinity(probs, k, C, mw, affinity, complete, logtype, post);   /* :601-603 (probsold = probs) */
-        if (!theta || faithful_cost || !have0) {
+        if ((!theta || !have0) && g_inner > 1 && !faithful_cost && S <= 32) {
+            /* Same arithmetic with ONE pass over D per step and threads over independent outputs (see g_inner):
+             * effect rows as bit masks, eff[i][s] bit j = closure_i[s, j]; a cell's row is the OR over its S-genes. */
+            uint32_t *effrow = (uint32_t *)calloc((size_t)k * S, sizeof(uint32_t));
+            for (int i = 0; i < k; i++)
+                for (int s2 = 0; s2 < S; s2++)
+                    for (int j = 0; j < S; j++)
+                        if (clo[(size_t)i * SS + s2 + j * S]) effrow[i * S + s2] |= 1u << j;
+            if (!theta) {
+                /* :619 for all components: Wall[i][j][e] += d[e] * gamma_i[c] over ascending cells */
+                double *Wall = (double *)calloc((size_t)k * E * (S + 1), sizeof(double));
+                int nt = g_inner;
+                if (nt > (E + 7) / 8) nt = (E + 7) / 8;
+                int t;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+#endif
+                for (t = 0; t < nt; t++) {
+                    const int per = ((E + nt - 1) / nt + 7) / 8 * 8;
+                    const int e0 = t * per, e1 = e0 + per < E ? e0 + per : E;
+                    for (int c = 0; c < C && e0 < e1; c++) {
+                        const double *d = D + (size_t)c * E;
+                        const uint32_t pm = pert_mask(pert[c]);
+                        for (int i = 0; i < k; i++) {
+                            const double g = post[i + (size_t)c * k];
+                            uint32_t em = 0;
+                            for (uint32_t r = pm; r; r &= r - 1) em |= effrow[i * S + __builtin_ctz(r)];
+                            for (; em; em &= em - 1) {
+                                double *w = Wall + ((size_t)i * (S + 1) + __builtin_ctz(em)) * E;
+                                for (int e = e0; e < e1; e++) w[e] += d[e] * g;
+                            }
+                        }
+                    }
+                }
+                for (int i = 0; i < k; i++)
+                    orc_max_col_row(Wall + (size_t)i * (S + 1) * E, E, S + 1, th + (size_t)i * E);   /* values 1..S+1 */
+                free(Wall);
+            } else {
+                for (size_t q = 0; q < (size_t)k * E; q++) th[q] = theta[q] == 0 ? S + 1 : theta[q];     /* :621-622 */
+            }
+            /* :624,631 L[i,c] = colSums(data * t(adj1[, subtopo])) : long-double, ascending e; cells are independent */
+            ORC_PAR_FOR
+            for (int c = 0; c < C; c++) {
+                const double *d = D + (size_t)c * E;
+                const uint32_t pm = pert_mask(pert[c]);
+                for (int i = 0; i < k; i++) {
+                    uint32_t em = 0;
+                    for (uint32_t r = pm; r; r &= r - 1) em |= effrow[i * S + __builtin_ctz(r)];
+                    const int32_t *thi = th + (size_t)i * E;
+                    acc_t sum = 0;
+                    for (int e = 0; e < E; e++) {
+                        const int t2 = thi[e];
+                        if (t2 <= S && ((em >> (t2 - 1)) & 1u)) sum += d[e];
+                    }
+                    probs0[i + (size_t)c * k] = (double)sum;
+                }
+            }
+            free(effrow);
+            have0 = 1;
+        } else if (!theta || faithful_cost || !have0) {
             for (int i = 0; i < k; i++) {
                 const uint8_t *A = clo + (size_t)i * SS;
                 int32_t *thi = th + (size_t)i * E;
@@ -654,6 +809,7 @@ typedef struct {
     double min_margin;
     long n_raw;             /* candidates generated before unique() */
     double min_accept_margin;  /* smallest relative |ll_new - ll_kept| or |trace_a - trace_b| behind an EM-level decision */
+    long n_dec, n_dec_tight;   /* greedy decisions of all searches, and those closer than 1e-13 relative (see orc_nem_info) */
 } orc_em_info;
 
 /* outputs: adj_out k*S*S (reduced, diag 0), theta_out k*E, L_out k*C (bestprobs), mw_out k (bestmw),
@@ -673,6 +829,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     double *scratch = (double *)malloc(sizeof(double) * kc);
     double *gam = (double *)malloc(sizeof(double) * C);
     double *Rk = (double *)malloc(sizeof(double) * (size_t)E * S);
+    double *Rall = NULL;
     uint8_t *res1_adj = (uint8_t *)malloc((size_t)k * SS), *res_adj = (uint8_t *)malloc((size_t)k * SS);
     int32_t *res1_th = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E), *res_th = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E);
     uint8_t *bestadj = (uint8_t *)malloc((size_t)k * SS);
@@ -698,7 +855,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     memcpy(bestadj, res1_adj, (size_t)k * SS);
     memset(bestth, 0, sizeof(int32_t) * (size_t)k * E);
     int count = 0, time0 = 1, stop = 0;
-    long nscored = 0, ngreedy = 0, nraw = 0;
+    long nscored = 0, ngreedy = 0, nraw = 0, ndec = 0, ntight = 0;
     double minmargin = INFINITY, acceptmargin = INFINITY;
     /* :1955-1958 with converged=-Inf, increase=TRUE: (ll - llold > -Inf & |ll - llold| > 0) | time0, & !stop.
      * `count < max_iter` binds only to the !increase arm (operator precedence). */
@@ -715,16 +872,25 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
         }
         orc_get_affinity(probs, k, C, mw, affinity, complete, logtype, post);     /* :1968-1973 */
         double edgechange = 0, thetachange = 0;
+        const int one_pass = g_inner > 1 && !o->faithful_cost;      /* all k collapsed matrices from one pass over D */
+        if (one_pass) {
+            if (!Rall) Rall = (double *)malloc(sizeof(double) * (size_t)k * E * S);
+            do_mean_multi(D, E, C, pert, S, k, post, (size_t)k, Rall);
+        }
         for (int i = 0; i < k; i++) {                                             /* :1976-2086 */
-            for (int c = 0; c < C; c++) gam[c] = post[i + (size_t)c * k];
             uint8_t a0[ORC_MAXS * ORC_MAXS], a1[ORC_MAXS * ORC_MAXS];
             int32_t *t0 = (int32_t *)malloc(sizeof(int32_t) * E), *t1 = (int32_t *)malloc(sizeof(int32_t) * E);
             orc_nem_info i0, i1;
-            orc_do_mean(D, E, C, pert, S, gam, Rk);                               /* nem :101-107 */
+            if (one_pass) memcpy(Rk, Rall + (size_t)i * E * S, sizeof(double) * (size_t)E * S);
+            else {
+                for (int c = 0; c < C; c++) gam[c] = post[i + (size_t)c * k];
+                orc_do_mean(D, E, C, pert, S, gam, Rk);                           /* nem :101-107 */
+            }
             orc_nem_greedy(Rk, E, S, NULL, a0, t0, &i0);                          /* j == 1: start0*0 :2042 */
             if (o->faithful_cost) orc_do_mean(D, E, C, pert, S, gam, Rk);
             orc_nem_greedy(Rk, E, S, res1_adj + (size_t)i * SS, a1, t1, &i1);     /* j == 2: start0 :2040 */
             nscored += i0.n_scored + i1.n_scored; ngreedy += i0.n_iter + i1.n_iter; nraw += i0.n_raw + i1.n_raw;
+            ndec += i0.n_dec + i1.n_dec; ntight += i0.n_dec_tight + i1.n_dec_tight;
             if (i0.min_margin < minmargin) minmargin = i0.min_margin;
             if (i1.min_margin < minmargin) minmargin = i1.min_margin;
             int pick1 = i1.max_trace > i0.max_trace;                              /* which.max: tie -> j == 1 :2072-2073 */
@@ -786,7 +952,8 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     info->ll = mx;                                                                /* limits$ll <- max(lls) :2157 */
     info->best_ll = bestll; info->n_iter = count; info->n_scored = nscored; info->n_greedy_iter = ngreedy;
     info->min_margin = minmargin; info->n_raw = nraw; info->min_accept_margin = acceptmargin;
-    free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk);
+    info->n_dec = ndec; info->n_dec_tight = ntight;
+    free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk); free(Rall);
     free(res1_adj); free(res_adj); free(res1_th); free(res_th); free(bestadj); free(bestth); free(bestprobs);
 }
 

@@ -98,3 +98,29 @@ def test_greedy_search_ends_in_a_local_optimum(S, E, seed):
     assert np.array_equal(th, fit["theta"])
     assert fit["max_trace"] == fit["score"]                                    # hill-climb: the last accepted score is the best
     assert fit["score"] >= orc.score_adj(R, np.zeros((S, S)), trans_close=True)[0]
+
+
+def test_inner_threads_do_not_change_a_single_bit():
+    """The scale goldens (tests/golden/make_scale_golden.py) run one fit on several threads: OpenMP splits independent
+    outputs only, so the whole EM result must be identical to the serial oracle, single and multi knock-down."""
+    from mnem_b200 import simdata
+    sim = simdata.make_config(dict(S=7, Egenes=9, C=2100, mw=[0.3, 0.3, 0.4], k=3, starts=2, uninform=3), seed=41)
+    D = simdata.host_data(sim) + np.random.default_rng(1).normal(size=(sim["E"], sim["C"])) * 0.4
+    init = simdata.init_phi(7, 3, 2, seed=3)
+    m = simdata.make_multi(S=5, Egenes=6, C=700, seed=9)
+    init_m = simdata.init_phi(5, 2, 2, seed=4)
+    for acc in ("ld", "f64"):
+        try:
+            orc.set_inner_threads(1, acc)
+            a = orc.mnem_em(D, sim["pert"], 7, init, complete=True, acc=acc)
+            am = orc.mnem_em(m["D"], m["pert_enc"], 5, init_m, acc=acc)
+            orc.set_inner_threads(5, acc)
+            b = orc.mnem_em(D, sim["pert"], 7, init, complete=True, acc=acc)
+            bm = orc.mnem_em(m["D"], m["pert_enc"], 5, init_m, acc=acc)
+        finally:
+            orc.set_inner_threads(1, acc)
+        for x, y in ((a, b), (am, bm)):
+            for key in ("adj", "theta", "probs", "mw", "ll", "n_iter", "n_scored", "min_margin", "min_accept_margin"):
+                assert np.array_equal(x[key], y[key]), key
+            for key in ("lls", "mwevo"):
+                assert all(np.array_equal(p, q) for p, q in zip(x[key], y[key])), key
