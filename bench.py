@@ -303,7 +303,7 @@ def run_ours(args):
                 "share_of_step": st["ms_estep"] / max(st["ms_total"], 1e-9)}
     breakdown = {"ms_estep": st["ms_estep"], "ms_mstats": st["ms_mstats"], "ms_search": st["ms_search"],
                  "ms_mixture": st["ms_mixture"], "ms_total": st["ms_total"], "passes_estep": st["passes_estep"],
-                 "passes_mstats": st["passes_mstats"]}
+                 "passes_mstats": st["passes_mstats"], "search_sm_busy": st.get("search_sm_busy", 0.0)}
     cand_rate = float(np.mean([x["cand"] for x in recs])) / (ms_step * 1e-3)
     cand_rate_search = float(np.sum(reduce_sum([st["cand_scored"]]))) / max(1e-9, reduce_max(st["ms_search"]) * 1e-3)
     cx.close()

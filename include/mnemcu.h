@@ -162,6 +162,7 @@ typedef struct {
     int64_t passes_mstats;
     double ms_total, ms_estep, ms_mstats, ms_search, ms_mixture;   /* CUDA-event times */
     double estep_bytes;      /* algorithmic bytes moved by all E-step launches */
+    double search_sm_busy;   /* device-resident greedy loop: time its CTAs spent on tasks / time they were resident */
 } mnemcu_em_stats;
 
 /* mnem(D, phi = init) EM phase: do_inits for every start, R/mnems.r:1884-2165 (explicit-phi entry :1792-1793).

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmnemcu.so")
+# MNEMCU_LIB: another build of the same library (A/B timing of kernel changes); never a different implementation
+LIB_PATH = os.environ.get("MNEMCU_LIB") or os.path.join(_HERE, "libmnemcu.so")
 
 c_dp = C.POINTER(C.c_double)
 c_u8p = C.POINTER(C.c_uint8)
@@ -35,7 +36,7 @@ class EmStats(C.Structure):
     _fields_ = [("em_iters", C.c_int64), ("cand_scored", C.c_int64), ("greedy_iters", C.c_int64),
                 ("passes_estep", C.c_int64), ("passes_mstats", C.c_int64), ("ms_total", C.c_double),
                 ("ms_estep", C.c_double), ("ms_mstats", C.c_double), ("ms_search", C.c_double),
-                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double)]
+                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double), ("search_sm_busy", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol of include/mnemcu.h

@@ -719,6 +719,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         en.stats.cand_scored = (int64_t)en.h_counters[0];
         en.stats.greedy_iters = (int64_t)en.h_counters[1];
         *best_out = winner;
+        en.stats.search_sm_busy = en.sb ? search_sm_busy(en.sb) : 0.0;
         if (stats_out) *stats_out = en.stats;
     }
     cudaEventDestroy(evA); cudaEventDestroy(evB);

@@ -23,13 +23,37 @@
 
 namespace mn {
 
-constexpr int kCT = 32;        // candidates per score CTA
-constexpr int kRows = 128;     // E-gene rows per score CTA (= threads)
+constexpr int kCT = 32;        // candidates per score CTA (generic scorer)
+constexpr int kRows = 128;     // E-gene rows per score CTA (= threads, generic scorer)
 
 constexpr int kDictHash = 2048;   // hash slots of the per-search mask dictionary (power of two)
 constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scoring kernel
 constexpr int kDictThreads = 512;
-constexpr int kChains = 4;         // most independent iteration chains per search_run (see SearchBatch)
+constexpr int kChains = 4;         // most independent iteration chains of the host-driven loop (see search_run_host)
+constexpr int kUP = 8;             // insertion sources per work item of the dictionary scorer
+constexpr int kMaxChunk = 4;       // most row tiles per task of the device-resident loop
+
+// Device view of a search workspace: one by-value kernel argument instead of twenty pointers.
+struct SearchDev {
+    int E = 0, S = 0, maxc = 0, dcap = 0, ntiles = 0, nsm = 0, hard_cap = 0;
+    const double *const *Rptr = nullptr;
+    uint32_t *Prow = nullptr, *Pcol = nullptr, *cand_cols = nullptr, *cand_J = nullptr, *dict_masks = nullptr, *rowm = nullptr;
+    uint16_t *cand_id = nullptr, *base_id = nullptr, *pair_id = nullptr;
+    uint8_t *chain_v = nullptr, *chain_start = nullptr;      // [q][32] targets chain after chain (bottom-up), [q][33] offsets
+    int32_t *ncand = nullptr, *active = nullptr, *niter = nullptr, *nd = nullptr, *nins = nullptr, *overflow = nullptr,
+            *nchain = nullptr;
+    int8_t *cand_kind = nullptr;
+    double *partial = nullptr, *scores = nullptr, *oldscore = nullptr, *maxtrace = nullptr;
+    unsigned long long *nscored = nullptr;
+    // the device-resident loop: a ring of tasks (search, first tile, tiles) and its counters
+    unsigned long long *ring = nullptr;
+    unsigned ring_mask = 0;
+    unsigned *qctl = nullptr;         // [0] head (next ticket), [1] reserved, [2] committed, [3] done flag
+    int32_t *live = nullptr;          // searches still climbing
+    int32_t *tiles_done = nullptr;    // [q] tiles of the current iteration already scored
+    int32_t *stage = nullptr;         // [q] 0: the pending scores are the initial score of closure(start); 1: neighbours
+    unsigned long long *busy_ns = nullptr;   // [0] ns the CTAs spent on tasks, [1] ns they were resident (utilisation of the loop)
+};
 
 struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
@@ -37,21 +61,51 @@ struct SearchBatch {
     int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
     double logtype = 2.0;
     size_t dict_smem = 0;
+    int sm_count = 148;
     DevBuf<const double *> Rptr;
-    DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks;
+    DevBuf<uint32_t> Prow, Pcol, cand_cols, cand_J, adj_rows, closed_rows, closed_cols, dict_masks, rowm;
     DevBuf<uint16_t> cand_id, base_id, pair_id;
-    DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow;
+    DevBuf<uint8_t> chain_v, chain_start;
+    DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow, nchain, live, tiles_done, stage;
     DevBuf<double> partial, scores, oldscore, maxtrace;
-    DevBuf<unsigned long long> nscored;
-    // Chains: the searches are dealt round-robin (by pair) to kChains groups that iterate independently on their own
-    // streams, so that one chain's single-CTA-per-search phases (argmax + candidate generation), launch gaps and
-    // scoring tails are filled by the scoring kernels of the others.
+    DevBuf<unsigned long long> nscored, ring, busy_ns;
+    unsigned long long *h_busy = nullptr;     // pinned copy of busy_ns
+    double busy_acc = 0.0, resident_acc = 0.0;   // accumulated over the search_run calls of this workspace
+    DevBuf<unsigned> qctl;
+    unsigned ring_cap = 0;
+    // Host-driven loop only.  Chains: the searches are dealt round-robin (by pair) to kChains groups that iterate
+    // independently on their own streams, so that one chain's single-CTA-per-search phases (argmax + candidate
+    // generation), launch gaps and scoring tails are filled by the scoring kernels of the others.
     int32_t *h_n_active = nullptr;   // pinned: [2*h + (it & 1)] moves accepted by chain h in iteration it, [2*kChains] overflow
     DevBuf<int32_t> qlist;            // [nmax] search ids, chain by chain
     cudaStream_t cst[kChains] = {};   // streams of chains 1.. (chain 0 runs on the caller's stream)
     cudaEvent_t ev[kChains][2] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kChains] = {};
+
+    SearchDev dev() const
+    {
+        SearchDev d;
+        d.E = E; d.S = S; d.maxc = maxc; d.dcap = dcap; d.ntiles = (E + kDictRows - 1) / kDictRows; d.nsm = sm_count;
+        d.hard_cap = 4 * S * S + 16;      // a strict hill-climb cannot take more moves than this in practice
+        d.Rptr = Rptr.p; d.Prow = Prow.p; d.Pcol = Pcol.p; d.cand_cols = cand_cols.p; d.cand_J = cand_J.p;
+        d.dict_masks = dict_masks.p; d.rowm = rowm.p; d.cand_id = cand_id.p; d.base_id = base_id.p; d.pair_id = pair_id.p;
+        d.chain_v = chain_v.p; d.chain_start = chain_start.p; d.ncand = ncand.p; d.active = active.p; d.niter = niter.p;
+        d.nd = nd.p; d.nins = nins.p; d.overflow = overflow.p; d.nchain = nchain.p; d.partial = partial.p;
+        d.scores = scores.p; d.oldscore = oldscore.p; d.maxtrace = maxtrace.p; d.nscored = nscored.p; d.ring = ring.p;
+        d.ring_mask = ring_cap ? ring_cap - 1 : 0; d.qctl = qctl.p; d.live = live.p; d.tiles_done = tiles_done.p;
+        d.stage = stage.p; d.busy_ns = busy_ns.p;
+        return d;
+    }
 };
+
+// Loads of per-search state that ANOTHER CTA may have written earlier in the same launch (the device-resident loop) must
+// not be served from this SM's L1: CG = true reads through L2 (ld.global.cg).  The host-driven kernels use plain loads.
+template <bool CG, typename T>
+__device__ __forceinline__ T ldv(const T *p)
+{
+    if constexpr (CG) return __ldcg(p);
+    else return *p;
+}
 
 // ---- candidate generation + mask dictionary ----------------------------------------------------------------
 // mode 0: the single "candidate" closure(better) used for the initial score (R/mnems.r:135-141)
@@ -65,50 +119,70 @@ struct SearchBatch {
 // hash order; they only index a table, so no result depends on them.
 // For insertions the "changed" set written to cand_J is the whole row of v (the columns the one-step closure may
 // touch): candidates that share v then share the set, and the scoring kernel reuses their unchanged-column maximum.
-template <int NT>
-__device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int mode, const uint32_t *Prow,
-                                                  const int32_t *active, uint32_t *__restrict__ Pcol,
-                                                  uint32_t *__restrict__ cand_cols, uint32_t *__restrict__ cand_J,
-                                                  int32_t *__restrict__ ncand, int8_t *__restrict__ cand_kind,
-                                                  uint32_t *__restrict__ dict_masks, int32_t *__restrict__ nd,
-                                                  uint16_t *__restrict__ cand_id, uint16_t *__restrict__ base_id,
-                                                  uint16_t *__restrict__ pair_id, int32_t *__restrict__ nins,
-                                                  int32_t *__restrict__ overflow)
+//
+// Chains (mode 1, dictionary only).  Inserting u -> v needs, for every u, the maximum over the columns j in D_v (row v
+// of the graph) of the table entry of col_j | col_u.  Whenever D_c is a subset of D_v (always for a descendant c of v in
+// a closed graph) that maximum is max(the maximum over D_c, the look-ups over D_v \ D_c), so the scorer walks chains
+// c_1, c_2, ... of targets with nested rows bottom-up and pays |D_top| look-up rounds per chain instead of sum |D_c|.
+// The greedy cover built here (largest uncovered row first, then repeatedly its largest uncovered subset) tests the
+// nesting directly, so it needs no closure assumption (intermediate graphs need not be closed, R/mnems.r:128-134).
+struct GenSmem {
+    uint32_t *keys;     // [kDictHash]
+    uint16_t *ids;      // [kDictHash]
+    uint16_t *pair;     // [32 * 32]
+    int *warp;          // [NT / 32]
+};
+constexpr size_t kGenSmemBytes = kDictHash * 4 + kDictHash * 2 + 1024 * 2 + 64 * 4;
+
+__device__ __forceinline__ GenSmem gen_smem_at(unsigned char *base)
 {
-    __shared__ uint32_t keys[kDictHash];
-    __shared__ uint16_t ids[kDictHash];
-    __shared__ uint16_t s_pair[32 * 32];
-    __shared__ int s_warp[NT / 32];
+    GenSmem g;
+    g.keys = reinterpret_cast<uint32_t *>(base);
+    g.ids = reinterpret_cast<uint16_t *>(base + kDictHash * 4);
+    g.pair = reinterpret_cast<uint16_t *>(base + kDictHash * 6);
+    g.warp = reinterpret_cast<int *>(base + kDictHash * 6 + 2048);
+    return g;
+}
+
+template <int NT, bool CG>
+__device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, int q, int mode)
+{
+    uint32_t *keys = sm.keys;
+    uint16_t *ids = sm.ids, *s_pair = sm.pair;
+    int *s_warp = sm.warp;
     constexpr int kPer = kDictHash / NT;          // hash slots per thread in the dense-id scan
     static_assert(kPer * NT == kDictHash, "thread count must divide the hash size");
+    const int S = d.S, maxc = d.maxc, dcap = d.dcap;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
-    if (!active[q]) {
-        if (tid == 0) { ncand[q] = 0; if (nd) { nd[q] = 0; nins[q] = 0; } }
+    const bool dict = d.dict_masks != nullptr;
+    if (!ldv<CG>(d.active + q)) {
+        if (tid == 0) { d.ncand[q] = 0; if (dict) { d.nd[q] = 0; d.nins[q] = 0; d.nchain[q] = 0; } }
         return;
     }
-    const bool dict = dict_masks != nullptr;
     if (dict)
         for (int i = tid; i < kDictHash; i += NT) keys[i] = 0u;
     __syncthreads();
-    auto insert = [&](uint32_t m) -> int {          // returns the hash slot of m
+    auto insert = [&](uint32_t m) -> int {          // returns the hash slot of m (a table that is full reports overflow)
         int h = (int)((m * 2654435761u) >> 21);
-        while (true) {
+        for (int probe = 0; probe < kDictHash; ++probe) {
             const uint32_t prev = atomicCAS(&keys[h], 0u, m);
             if (prev == 0u || prev == m) return h;
             h = (h + 1) & (kDictHash - 1);
         }
+        atomicOr(d.overflow, 1);
+        return 0;
     };
     const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
-    const uint32_t row = lane < S ? (Prow[q * 32 + lane] | (1u << lane)) & smask : 0u;
+    const uint32_t row = lane < S ? (ldv<CG>(d.Prow + q * 32 + lane) | (1u << lane)) & smask : 0u;
     const uint32_t col = warp_transpose(row, lane, S);
-    uint32_t *cc = cand_cols + (size_t)q * maxc * 32;
-    uint32_t *cj = cand_J + (size_t)q * maxc;
-    uint16_t *ci = dict ? cand_id + (size_t)q * maxc * 32 : nullptr;
+    uint32_t *cc = d.cand_cols + (size_t)q * maxc * 32;
+    uint32_t *cj = d.cand_J + (size_t)q * maxc;
+    uint16_t *ci = dict ? d.cand_id + (size_t)q * maxc * 32 : nullptr;
     int total = 0;
     if (warp == 0) {
-        Pcol[q * 32 + lane] = col;
-        if (dict && lane < S) base_id[q * 32 + lane] = (uint16_t)insert(col);
+        d.Pcol[q * 32 + lane] = col;
+        if (dict && lane < S) d.base_id[q * 32 + lane] = (uint16_t)insert(col);
     }
     if (mode == 0) {
         if (warp == 0) {
@@ -116,7 +190,7 @@ __device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int m
             const uint32_t ccol = warp_transpose(clo, lane, S);
             cc[lane] = ccol;
             if (dict && lane < S) ci[lane] = (uint16_t)insert(ccol);
-            if (lane == 0) { cj[0] = smask; ncand[q] = 1; if (dict) nins[q] = 0; }
+            if (lane == 0) { cj[0] = smask; d.ncand[q] = 1; if (dict) { d.nins[q] = 0; d.nchain[q] = 0; } }
         }
         total = 1;
     } else {
@@ -146,7 +220,38 @@ __device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int m
             base += __shfl_sync(kFull, incl, 31);
         }
         total = base;
-        if (tid == 0) { ncand[q] = base; if (dict) nins[q] = off[1]; }   // lane 0: off[1] = number of insertions
+        if (tid == 0) { d.ncand[q] = base; if (dict) d.nins[q] = off[1]; }   // lane 0: off[1] = number of insertions
+        if (dict && warp == nwarp - 1) {
+            // chains of nested insertion targets for the scorer (see above); lane v: row v = D_v, km[0] = sources into v
+            d.rowm[q * 32 + lane] = row;
+            const int cost = __popc(row);
+            unsigned unclaimed = __ballot_sync(kFull, km[0] != 0u);       // targets that have candidates at all
+            int nch = 0, npos = 0;
+            uint8_t *cv = d.chain_v + q * 32, *cs = d.chain_start + q * 33;
+            if (lane == 0) cs[0] = 0;
+            while (unclaimed) {
+                unsigned long long list = 0ull;                           // the chain top-down, 5 bits per node
+                int len = 0;
+                uint32_t cur = 0xffffffffu;                               // row of the node above (none yet: everything nests)
+                while (len < 12) {
+                    // largest uncovered target whose row nests inside `cur`; ties -> lowest index
+                    const bool ok = ((unclaimed >> lane) & 1u) && (row & ~cur) == 0u;
+                    int key = ok ? (cost << 5) | (31 - lane) : -1;
+                    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
+                    if (key < 0) break;
+                    const int v = 31 - (key & 31);
+                    list |= (unsigned long long)v << (5 * len);
+                    ++len;
+                    unclaimed &= ~(1u << v);
+                    cur = __shfl_sync(kFull, row, v);
+                }
+                if (lane < len) cv[npos + lane] = (uint8_t)((list >> (5 * (len - 1 - lane))) & 31ull);    // bottom-up
+                npos += len;
+                ++nch;
+                if (lane == 0) cs[nch] = (uint8_t)npos;
+            }
+            if (lane == 0) d.nchain[q] = nch;
+        }
         for (int item = warp; item < 3 * S; item += nwarp) {
             const int kd = item / S, v = item - kd * S;
             uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
@@ -189,7 +294,7 @@ __device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int m
                 if (dict && kd != 0 && ((J >> lane) & 1u)) ci[(size_t)idx * 32 + lane] = (uint16_t)insert(nc);
                 if (lane == 0) {
                     cj[idx] = J;
-                    if (cand_kind) cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
+                    if (d.cand_kind) d.cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
                 }
                 ++idx;
             }
@@ -215,37 +320,33 @@ __device__ __forceinline__ void gen_body(int q, int S, int maxc, int dcap, int m
         const uint32_t k = keys[tid * kPer + i];
         if (k != 0u) {
             ids[tid * kPer + i] = (uint16_t)min(base, dcap - 1);   // overflow: stay inside the table (the host reports it)
-            if (base < dcap) dict_masks[(size_t)q * dcap + base] = k;
+            if (base < dcap) d.dict_masks[(size_t)q * dcap + base] = k;
             ++base;
         }
     }
     if (tid == NT - 1) {
-        nd[q] = base;
-        if (base > dcap) atomicOr(overflow, 1);
+        d.nd[q] = base;
+        if (base > dcap) atomicOr(d.overflow, 1);
     }
     __syncthreads();
     // hash slots -> dense ids (cand_id / base_id written by this CTA above; __syncthreads makes them visible)
-    if (tid < S) base_id[q * 32 + tid] = ids[base_id[q * 32 + tid]];
-    const int first = mode == 0 ? 0 : nins[q];            // written by thread 0 before the barriers above
-    for (int i = first * 32 + tid; i < total * 32; i += NT) {
+    if (tid < S) d.base_id[q * 32 + tid] = ids[ldv<CG>(d.base_id + q * 32 + tid)];
+    // insertions carry no per-candidate ids: convert from the first reversal on (mode 0: the single candidate)
+    const int nins_q = mode == 0 ? 0 : ldv<CG>(d.nins + q);   // written by thread 0 before the barriers above
+    for (int i = nins_q * 32 + tid; i < total * 32; i += NT) {
         const int c = i >> 5, j = i & 31;
-        if ((cj[c] >> j) & 1u) ci[i] = ids[ci[i]];
+        if ((ldv<CG>(cj + c) >> j) & 1u) ci[i] = ids[ldv<CG>(ci + i)];
     }
     if (mode != 0)
         for (int i = tid; i < 32 * 32; i += NT)
-            pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
+            d.pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
 }
 
-__global__ void __launch_bounds__(256) gen_kernel(int S, int maxc, int dcap, int mode, const uint32_t *Prow,
-                                                  const int32_t *active, uint32_t *Pcol, uint32_t *cand_cols,
-                                                  uint32_t *cand_J, int32_t *ncand, int8_t *cand_kind,
-                                                  uint32_t *dict_masks, int32_t *nd, uint16_t *cand_id,
-                                                  uint16_t *base_id, uint16_t *pair_id, int32_t *nins, int32_t *overflow)
+__global__ void __launch_bounds__(256) gen_kernel(SearchDev d, int mode)
 {
-    gen_body<256>(blockIdx.x, S, maxc, dcap, mode, Prow, active, Pcol, cand_cols, cand_J, ncand, cand_kind, dict_masks, nd, cand_id,
-                  base_id, pair_id, nins, overflow);
+    __shared__ __align__(16) unsigned char s_gen[kGenSmemBytes];
+    gen_body<256, false>(d, gen_smem_at(s_gen), blockIdx.x, mode);
 }
-
 // ---- candidate scoring -----------------------------------------------------------------------------------
 template <int SP>
 __device__ __forceinline__ double col_sum(const double (&r)[SP], uint32_t m)
@@ -341,46 +442,83 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
     }
 }
 
+
 // ---- dictionary scoring ----------------------------------------------------------------------------------
-// scoreAdj for every candidate of every active search.  grid = (G row groups, searches), block = 16 warps, lane = E-gene
-// row of a 32-row tile.  Per tile:
+// scoreAdj for every candidate of one search over a set of 32-row tiles.  block = 16 warps, lane = E-gene row of the tile.
+// Per tile:
 // (1) table T[entry][row] = sum of the R columns in the entry's mask, ascending S-gene order (the order of the Eigen
 //     product in src/mm.cpp:10); each warp takes every 16th entry, two at a time.
-// (2) insertions, one v per warp at a time: inserting u -> v replaces column j by col_j | col_u for every j in row v
-//     (D_v).  A_v = max over the columns outside D_v is computed once; then for every j in D_v the S look-ups
-//     T[pair(u, j)] update B[u] (registers, u unrolled), and max(0, A_v, B[u]) is summed over the 32 rows for all u at
-//     once by a transposed butterfly (31 exchanges for 32 candidates instead of 5 per candidate).
-// (3) reversals / deletions: per candidate, changed columns by id, unchanged-column maximum cached while the changed
-//     set repeats.
-// Per-candidate sums accumulate in shared memory in ascending tile order.  Both reductions pair the rows as
-// (l, l^16), (l, l^8), ...: the same function of the 32 row values, so equal rows give bit-equal sums whatever the
-// candidate kind (exact score ties decide graphs, R/mnems.r:236, 279-283).
-// Dynamic shared memory: T, the per-candidate sums, the masks, the pair-id matrix.
-template <int SP>
-__global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
-    int E, int S, int maxc, int dcap, int G, const double *const *__restrict__ Rptr, const int32_t *__restrict__ ncand,
-    const int32_t *__restrict__ nins, const int32_t *__restrict__ nd, const uint32_t *__restrict__ dict_masks,
-    const uint16_t *__restrict__ base_id, const uint16_t *__restrict__ pair_id, const uint32_t *__restrict__ Pcol,
-    const uint32_t *__restrict__ cand_J, const uint16_t *__restrict__ cand_id, double *__restrict__ partial,
-    const int32_t *__restrict__ qlist)
+// (2) floors: for every insertion target v the maximum A_v over the columns OUTSIDE D_v (row v of the graph) of the
+//     current subweights, floored at 0, one target per warp; one more warp keeps the four largest current subweights of
+//     each row for the reversal / deletion candidates (whose changed sets are arbitrary).
+// (3) work items, handed out by a shared counter so that the 16 warps finish together:
+//     insertions: one item = one chain of nested targets (see gen_body) x 8 sources u.  The item walks the chain
+//     bottom-up; for every NEW column j of D_v the 8 look-ups T[col_j | col_u] update the running maxima B[u] held in
+//     registers; at every target the values max(A_v, B[u]) of the 32 rows are added by a butterfly that halves the
+//     number of candidates per lane in its first three stages.
+//     reversals / deletions: per candidate, changed columns by id, unchanged-column maximum from the four largest.
+// Per-candidate sums of every tile go to partial[q][tile][c]; tiles are added in ascending order later.  Every row
+// reduction pairs the rows as (l, l^16), (l, l^8), ...: the same function of the 32 row values, so equal rows give
+// bit-equal sums whatever the candidate kind (exact score ties decide graphs, R/mnems.r:236, 279-283).
+struct ScoreSmem {
+    double *T;          // [dcap][32]
+    uint32_t *dmask;    // [dcap]
+    uint32_t *pid;      // [32][32]: pid[j*32 + u] = byte offset in T of the row of col_j | col_u
+    double *A0;         // [32][32]: A0[v*32 + row] = max(0, max over the columns outside D_v)
+    double *tv;         // [4][32] the four largest current subweights of each row ...
+    int *ti;            // [4][32] ... and their columns (32 = none)
+};
+__host__ __device__ inline size_t score_smem_bytes(int dcap)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    const int q = qlist ? qlist[blockIdx.y] : blockIdx.y, g = blockIdx.x;
-    const int nc = ncand[q];
+    return (size_t)dcap * kDictRows * 8 + (((size_t)dcap * 4 + 15) & ~(size_t)15) + 4096 + 32 * 32 * 8 + 4 * 32 * 8 + 4 * 32 * 4;
+}
+__device__ __forceinline__ ScoreSmem score_smem_at(unsigned char *base, int dcap)
+{
+    ScoreSmem s;
+    s.T = reinterpret_cast<double *>(base);
+    s.dmask = reinterpret_cast<uint32_t *>(s.T + (size_t)dcap * kDictRows);
+    s.pid = s.dmask + ((dcap + 3) & ~3);
+    s.A0 = reinterpret_cast<double *>(s.pid + 1024);
+    s.tv = s.A0 + 32 * 32;
+    s.ti = reinterpret_cast<int *>(s.tv + 4 * 32);
+    return s;
+}
+
+template <int SP, bool CG>
+__device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s_raw, int q, int tile_begin, int tile_end,
+                                            int tile_step)
+{
+    __shared__ int s_vlist[32];          // chain nodes, chain after chain, each chain bottom-up
+    __shared__ int s_cstart[33];         // chain h = s_vlist[s_cstart[h] .. s_cstart[h + 1])
+    __shared__ uint32_t s_rowm[32];      // D_v
+    __shared__ int s_ctr[2];
+    __shared__ int s_aflag[33];          // [h] floors of chain h, [32] top four: == gen once written for the current tile
+    const int E = d.E, S = d.S, maxc = d.maxc, dcap = d.dcap;
+    const int nc = ldv<CG>(d.ncand + q);
     if (nc == 0) return;
-    const int ni = nins[q];
-    const int ndq = min(nd[q], dcap);
-    double *T = reinterpret_cast<double *>(s_raw);                      // [dcap][32]
-    uint32_t *dmask = reinterpret_cast<uint32_t *>(T + (size_t)dcap * kDictRows);   // [dcap]
-    uint32_t *pid = dmask + ((dcap + 3) & ~3);      // [32][32]: pid[j*32 + u] = byte offset in T of the row of col_j | col_u
+    const int ni = ldv<CG>(d.nins + q);
+    const int ndq = min(ldv<CG>(d.nd + q), dcap);
+    const ScoreSmem sm = score_smem_at(s_raw, dcap);
+    double *T = sm.T;
+    uint32_t *dmask = sm.dmask, *pid = sm.pid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kDictThreads / 32;
-    for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = dict_masks[(size_t)q * dcap + i];
-    if (ni > 0)
-        for (int i = tid; i < 1024; i += kDictThreads) pid[i] = (uint32_t)pair_id[(size_t)q * 1024 + i] * (kDictRows * 8u);
-    const uint32_t bid = lane < S ? base_id[q * 32 + lane] : 0u;
+    constexpr int kRestChunk = 4;
+    constexpr int kParts = (SP + kUP - 1) / kUP;    // work items per chain
+    static_assert(kUP == 8, "the row reduction below halves 8 -> 4 -> 2 -> 1 over the lane bits 16, 8, 4");
+    for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = ldv<CG>(d.dict_masks + (size_t)q * dcap + i);
+    const int nv = ni > 0 ? ldv<CG>(d.nchain + q) : 0;
+    if (ni > 0) {
+        for (int i = tid; i < 1024; i += kDictThreads) pid[i] = (uint32_t)ldv<CG>(d.pair_id + (size_t)q * 1024 + i) * (kDictRows * 8u);
+        if (tid < 32) { s_vlist[tid] = ldv<CG>(d.chain_v + q * 32 + tid); s_rowm[tid] = ldv<CG>(d.rowm + q * 32 + tid); }
+        if (tid < 33) s_cstart[tid] = ldv<CG>(d.chain_start + q * 33 + tid);
+    }
+    if (tid == 0) { s_ctr[0] = 0; s_ctr[1] = 0; }
+    if (tid < 33) s_aflag[tid] = 0;
+    int gen = 0;
+    const uint32_t bid = lane < S ? ldv<CG>(d.base_id + q * 32 + lane) : 0u;
     const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
-    const uint32_t pcol = lane < S ? Pcol[q * 32 + lane] : 0u;          // lane = column
+    const uint32_t pcol = lane < S ? ldv<CG>(d.Pcol + q * 32 + lane) : 0u;     // lane = column
     const uint32_t zmask = lane < S ? (~pcol & smask) : 0u;            // rows u with P[u, lane] == 0: insertions into lane
     int offv;                                                           // first candidate index of column `lane`
     {
@@ -392,148 +530,191 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
         }
         offv = incl - cnt;
     }
-    const double *R = Rptr[q];
-    const uint32_t *cJ = cand_J + (size_t)q * maxc;
-    const uint16_t *cI = cand_id + (size_t)q * maxc * 32;
-    // Work items of a tile, handed out by a shared counter so that the 16 warps finish together (an insertion target v
-    // costs |D_v| rounds of 32 look-ups, anything from 1 to S): first the insertion targets, most expensive first, then
-    // the reversal / deletion candidates in chunks of kRestChunk.
-    __shared__ int s_vlist[32];
-    __shared__ int s_nv;
-    __shared__ int s_ctr[2];
-    constexpr int kRestChunk = 4;
-    if (warp == 0) {
-        const bool valid = zmask != 0u;
-        int cost = 0;
-        for (int j = 0; j < S; ++j) cost += (__shfl_sync(kFull, pcol, j) >> lane) & 1u;     // |D_lane| = ones in row `lane`
-        int rank = 0;
-        for (int o = 0; o < 32; ++o) {
-            const int oc = __shfl_sync(kFull, cost, o);
-            const bool ov = __shfl_sync(kFull, (int)valid, o) != 0;
-            if (ov && (oc > cost || (oc == cost && o < lane))) ++rank;
-        }
-        if (valid) s_vlist[rank] = lane;
-        const unsigned vm = __ballot_sync(kFull, valid);
-        if (lane == 0) { s_nv = ni > 0 ? __popc(vm) : 0; s_ctr[0] = 0; s_ctr[1] = 0; }
-    }
+    const double *R = d.Rptr[q];
+    const uint32_t *cJ = d.cand_J + (size_t)q * maxc;
+    const uint16_t *cI = d.cand_id + (size_t)q * maxc * 32;
     const int nrest = nc - ni;
     const int nchunks = (nrest + kRestChunk - 1) / kRestChunk;
     __syncthreads();
-    const int nv = s_nv;
     int parity = 0;
-    const int ntiles = (E + kDictRows - 1) / kDictRows;
-    for (int tile = g; tile < ntiles; tile += (int)gridDim.x) {       // G row groups = gridDim.x
+    const int ntiles = d.ntiles;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
         const int row = tile * kDictRows + lane;
-        double *ptile = partial + ((size_t)q * ntiles + tile) * maxc;   // this tile's per-candidate sums
+        double *ptile = d.partial + ((size_t)q * ntiles + tile) * maxc;   // this tile's per-candidate sums
         {
             double r[SP];
 #pragma unroll
             for (int s = 0; s < SP; ++s) r[s] = (s < S && row < E) ? R[(size_t)s * E + row] : 0.0;
-            // (1) the table
-            for (int ent = warp; ent < ndq; ent += 2 * NW) {
+            // (1) the table: four independent sums per warp in flight (the adds of one entry form a dependent chain)
+            for (int ent = warp; ent < ndq; ent += 4 * NW) {
                 const uint32_t m0 = dmask[ent];
-                const bool two = ent + NW < ndq;
-                const uint32_t m1 = two ? dmask[ent + NW] : 0u;
-                double w0 = 0.0, w1 = 0.0;
+                const bool h1 = ent + NW < ndq, h2 = ent + 2 * NW < ndq, h3 = ent + 3 * NW < ndq;
+                const uint32_t m1 = h1 ? dmask[ent + NW] : 0u, m2 = h2 ? dmask[ent + 2 * NW] : 0u,
+                               m3 = h3 ? dmask[ent + 3 * NW] : 0u;
+                double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
 #pragma unroll
                 for (int s = 0; s < SP; ++s) {
                     if ((m0 >> s) & 1u) { MN_KEEP_BRANCH(); w0 += r[s]; }
                     if ((m1 >> s) & 1u) { MN_KEEP_BRANCH(); w1 += r[s]; }
+                    if ((m2 >> s) & 1u) { MN_KEEP_BRANCH(); w2 += r[s]; }
+                    if ((m3 >> s) & 1u) { MN_KEEP_BRANCH(); w3 += r[s]; }
                 }
                 T[ent * kDictRows + lane] = w0;
-                if (two) T[(ent + NW) * kDictRows + lane] = w1;
+                if (h1) T[(ent + NW) * kDictRows + lane] = w1;
+                if (h2) T[(ent + 2 * NW) * kDictRows + lane] = w2;
+                if (h3) T[(ent + 3 * NW) * kDictRows + lane] = w3;
             }
         }
-        __syncthreads();
-        // the four largest subweights of the current graph in this row: the maximum over the columns a candidate
-        // leaves unchanged is the first of them whose column is outside the changed set (full scan only if all
-        // four are inside)
-        double t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
-        int i0 = 32, i1 = 32, i2 = 32, i3 = 32;              // 32 = no column
-        for (int j = 0; j < S; ++j) {
-            const int id = __shfl_sync(kFull, bid, j);
-            const double w = T[id * kDictRows + lane];
-            if (w > t0) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = t0; i1 = i0; t0 = w; i0 = j; }
-            else if (w > t1) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = w; i1 = j; }
-            else if (w > t2) { t3 = t2; i3 = i2; t2 = w; i2 = j; }
-            else if (w > t3) { t3 = w; i3 = j; }
-        }
-        auto unchanged_max = [&](uint32_t Jset) -> double {
-            const unsigned long long Jx = Jset;
-            const bool in0 = (Jx >> i0) & 1ull, in1 = (Jx >> i1) & 1ull, in2 = (Jx >> i2) & 1ull, in3 = (Jx >> i3) & 1ull;
-            double A = !in0 ? t0 : (!in1 ? t1 : (!in2 ? t2 : t3));
-            const bool need_scan = in0 && in1 && in2 && in3;
-            if (__any_sync(kFull, need_scan)) {
-                double sc = -INFINITY;
-                for (int j = 0; j < S; ++j) {
-                    const int id = __shfl_sync(kFull, bid, j);
-                    if (!((Jset >> j) & 1u)) { const double t = T[id * kDictRows + lane]; sc = t > sc ? t : sc; }
-                }
-                if (need_scan) A = sc;
-            }
-            return A;
-        };
         if (tid == 0) s_ctr[parity ^ 1] = 0;                  // next tile's counter (idle until after the barrier below)
+        ++gen;
+        __syncthreads();
+        // (2) + (3) work items: [0, nv) floors of chain h; [nv] top four of the current row (if there are reversal /
+        // deletion candidates); then the insertion items (chain x 8 sources), then the other candidates in fours.  The
+        // floor items come first in the queue, so whoever needs a floor finds its producer already at work and waits on
+        // a shared-memory flag instead of a block-wide barrier.
+        const int nA = nv + (nrest > 0 ? 1 : 0);
         while (true) {
             int item = 0;
             if (lane == 0) item = atomicAdd(&s_ctr[parity], 1);
             item = __shfl_sync(kFull, item, 0);
-            if (item >= nv + nchunks) break;
+            if (item >= nA + nv * kParts + nchunks) break;
             if (item < nv) {
-                // (2) insertions into v
-                const int v = s_vlist[item];
-                const uint32_t zm = __shfl_sync(kFull, zmask, v);
-                const uint32_t Dv = __ballot_sync(kFull, (pcol >> v) & 1u);      // columns j with P[v, j] = 1 (diag included)
-                const double A = unchanged_max(Dv);
-                const double A0 = A > 0.0 ? A : 0.0;                 // max(0, unchanged columns): the floor of every candidate
-                double B[32];
-#pragma unroll
-                for (int u = 0; u < 32; ++u) B[u] = A0;
-                uint32_t m = Dv;
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    // ids of col_j | col_u for all u: one 64-byte row, fetched as uniform 16-byte loads; the look-ups
-                    // are unconditional (also for u that are no candidates) so that they pipeline instead of
-                    // serialising behind 30 uniform branches
-                    uint32_t ofs[(SP + 3) / 4 * 4];
-#pragma unroll
-                    for (int w4 = 0; w4 < (SP + 3) / 4; ++w4) {
-                        const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + w4 * 4);
-                        ofs[w4 * 4 + 0] = x.x; ofs[w4 * 4 + 1] = x.y; ofs[w4 * 4 + 2] = x.z; ofs[w4 * 4 + 3] = x.w;
+                // floors A_v = max(0, max over the columns outside D_v of the current subweights) for the targets of chain
+                // `item`, top-down: the complements grow, so the running maximum carries over
+                const int h = item;
+                const int cbeg = s_cstart[h];
+                uint32_t outside = 0u;                                 // columns already covered by the running maximum
+                double sc = -INFINITY;
+                for (int ci = s_cstart[h + 1] - 1; ci >= cbeg; --ci) {
+                    const int v = s_vlist[ci];
+                    uint32_t m = ~s_rowm[v] & smask & ~outside;
+                    outside |= m;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int id = __shfl_sync(kFull, bid, j);
+                        const double w = T[id * kDictRows + lane];
+                        sc = w > sc ? w : sc;
                     }
-                    const unsigned char *Tl = reinterpret_cast<const unsigned char *>(T + lane);
-#pragma unroll
-                    for (int u = 0; u < SP; ++u) {
-                        const double t = *reinterpret_cast<const double *>(Tl + ofs[u]);
-                        B[u] = t > B[u] ? t : B[u];
-                    }
+                    sm.A0[v * 32 + lane] = sc > 0.0 ? sc : 0.0;
                 }
-#pragma unroll
-                for (int u = 0; u < 32; ++u) B[u] = (u < SP && ((zm >> u) & 1u)) ? B[u] : 0.0;
-                // transposed butterfly: afterwards lane l holds the sum over the 32 rows of B[l]
-#pragma unroll
-                for (int d = 16; d >= 1; d >>= 1) {
-                    const bool hi = (lane & d) != 0;
-#pragma unroll
-                    for (int i = 0; i < d; ++i) {
-                        const double send = hi ? B[i] : B[i + d];
-                        const double recv = __shfl_xor_sync(kFull, send, d);
-                        B[i] = (hi ? B[i + d] : B[i]) + recv;
-                    }
-                }
-                const int off = __shfl_sync(kFull, offv, v);
-                if ((zm >> lane) & 1u) ptile[off + __popc(zm & ((1u << lane) - 1u))] = B[0];
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *reinterpret_cast<volatile int *>(&s_aflag[h]) = gen;
                 continue;
             }
-            // (3) reversals and deletions (and the single closure "candidate" of the initial score)
-            const int cbeg = ni + (item - nv) * kRestChunk, cend = min(nc, cbeg + kRestChunk);
+            if (item < nA) {
+                double t0 = -INFINITY, t1 = -INFINITY, t2 = -INFINITY, t3 = -INFINITY;
+                int i0 = 32, i1 = 32, i2 = 32, i3 = 32;              // 32 = no column
+                for (int j = 0; j < S; ++j) {
+                    const int id = __shfl_sync(kFull, bid, j);
+                    const double w = T[id * kDictRows + lane];
+                    if (w > t0) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = t0; i1 = i0; t0 = w; i0 = j; }
+                    else if (w > t1) { t3 = t2; i3 = i2; t2 = t1; i2 = i1; t1 = w; i1 = j; }
+                    else if (w > t2) { t3 = t2; i3 = i2; t2 = w; i2 = j; }
+                    else if (w > t3) { t3 = w; i3 = j; }
+                }
+                sm.tv[lane] = t0; sm.tv[32 + lane] = t1; sm.tv[64 + lane] = t2; sm.tv[96 + lane] = t3;
+                sm.ti[lane] = i0; sm.ti[32 + lane] = i1; sm.ti[64 + lane] = i2; sm.ti[96 + lane] = i3;
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *reinterpret_cast<volatile int *>(&s_aflag[32]) = gen;
+                continue;
+            }
+            item -= nA;
+            if (item < nv * kParts) {
+                // insertions into the targets of chain `item / kParts`, bottom-up, for the sources u in [u0, u0 + kUP)
+                const int h = item / kParts, u0 = (item - h * kParts) * kUP;
+                while (*reinterpret_cast<volatile int *>(&s_aflag[h]) != gen) { }     // the chain's floors are in shared memory
+                __threadfence_block();
+                double B[kUP];                                        // B[i] = max over the columns seen so far of T[col_j | col_(u0+i)]
+#pragma unroll
+                for (int i = 0; i < kUP; ++i) B[i] = -INFINITY;
+                uint32_t seen = 0u;
+                const int cend = s_cstart[h + 1];
+                const unsigned char *Tl = reinterpret_cast<const unsigned char *>(T + lane);
+                for (int ci = s_cstart[h]; ci < cend; ++ci) {
+                    const int v = s_vlist[ci];
+                    const uint32_t zfull = __shfl_sync(kFull, zmask, v);
+                    const uint32_t zm = zfull >> u0;
+                    const uint32_t Dv = s_rowm[v];                                   // columns j with P[v, j] = 1 (diag included)
+                    uint32_t m = Dv & ~seen;
+                    seen = Dv;
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+                        // ids of col_j | col_u: uniform 16-byte loads; the look-ups are unconditional (also for u that are
+                        // no candidates) so that they pipeline instead of serialising behind uniform branches
+                        uint32_t ofs[kUP];
+#pragma unroll
+                        for (int w4 = 0; w4 < kUP / 4; ++w4) {
+                            const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + u0 + w4 * 4);
+                            ofs[w4 * 4 + 0] = x.x; ofs[w4 * 4 + 1] = x.y; ofs[w4 * 4 + 2] = x.z; ofs[w4 * 4 + 3] = x.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < kUP; ++i) {
+                            const double t = *reinterpret_cast<const double *>(Tl + ofs[i]);
+                            B[i] = t > B[i] ? t : B[i];
+                        }
+                    }
+                    if (zm & ((1u << kUP) - 1u)) {                    // warp-uniform: any candidate among these sources?
+                        const double A0 = sm.A0[v * 32 + lane];
+                        // value of candidate u in this row: max(0, A_v, B[u]).  Rows are added pairwise over the lane bits
+                        // 16, 8, 4, 2, 1 (the shape of every row reduction here); the first three stages halve the number
+                        // of candidates a lane carries, after which lane l holds candidate 4 b16 + 2 b8 + b4.  B itself stays
+                        // intact for the next target of the chain.
+                        double V[kUP];
+#pragma unroll
+                        for (int i = 0; i < kUP; ++i) V[i] = ((zm >> i) & 1u) ? (B[i] > A0 ? B[i] : A0) : 0.0;
+#pragma unroll
+                        for (int dd = 16, n = kUP / 2; n >= 1; dd >>= 1, n >>= 1) {
+                            const bool hi = (lane & dd) != 0;
+#pragma unroll
+                            for (int i = 0; i < n; ++i) {
+                                const double send = hi ? V[i] : V[i + n];
+                                const double recv = __shfl_xor_sync(kFull, send, dd);
+                                V[i] = (hi ? V[i + n] : V[i]) + recv;
+                            }
+                        }
+                        V[0] += __shfl_xor_sync(kFull, V[0], 2);
+                        V[0] += __shfl_xor_sync(kFull, V[0], 1);
+                        const int ui = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        const int off = __shfl_sync(kFull, offv, v);
+                        if ((lane & 3) == 0 && ((zm >> ui) & 1u))
+                            ptile[off + __popc(zfull & ((1u << (u0 + ui)) - 1u))] = V[0];
+                    }
+                }
+                continue;
+            }
+            // reversals and deletions (and the single closure "candidate" of the initial score)
+            while (*reinterpret_cast<volatile int *>(&s_aflag[32]) != gen) { }
+            __threadfence_block();
+            const double t0 = sm.tv[lane], t1 = sm.tv[32 + lane], t2 = sm.tv[64 + lane], t3 = sm.tv[96 + lane];
+            const int i0 = sm.ti[lane], i1 = sm.ti[32 + lane], i2 = sm.ti[64 + lane], i3 = sm.ti[96 + lane];
+            // the maximum over the columns a candidate leaves unchanged is the first of the four largest whose column is
+            // outside the changed set (full scan only if all four are inside)
+            auto unchanged_max = [&](uint32_t Jset) -> double {
+                const unsigned long long Jx = Jset;
+                const bool in0 = (Jx >> i0) & 1ull, in1 = (Jx >> i1) & 1ull, in2 = (Jx >> i2) & 1ull, in3 = (Jx >> i3) & 1ull;
+                double A = !in0 ? t0 : (!in1 ? t1 : (!in2 ? t2 : t3));
+                const bool need_scan = in0 && in1 && in2 && in3;
+                if (__any_sync(kFull, need_scan)) {
+                    double sc = -INFINITY;
+                    for (int j = 0; j < S; ++j) {
+                        const int id = __shfl_sync(kFull, bid, j);
+                        if (!((Jset >> j) & 1u)) { const double t = T[id * kDictRows + lane]; sc = t > sc ? t : sc; }
+                    }
+                    if (need_scan) A = sc;
+                }
+                return A;
+            };
+            const int cbeg = ni + (item - nv * kParts) * kRestChunk, cend = min(nc, cbeg + kRestChunk);
             uint32_t lastJ = 0u;
             double A = -INFINITY;
             bool haveA = false;
             for (int c = cbeg; c < cend; ++c) {
-                uint32_t J = cJ[c];
-                const uint32_t myid = ((J >> lane) & 1u) ? cI[(size_t)c * 32 + lane] : 0u;
+                uint32_t J = ldv<CG>(cJ + c);
+                const uint32_t myid = ((J >> lane) & 1u) ? ldv<CG>(cI + (size_t)c * 32 + lane) : 0u;
                 if (!haveA || J != lastJ) {
                     A = unchanged_max(J);
                     lastJ = J;
@@ -557,25 +738,50 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(
     }
 }
 
-// ---- argmax, accept rule, graph update -------------------------------------------------------------------
-template <int NT>
-__device__ __forceinline__ void finish_body(int q, int S, int maxc, int etiles, int mode, const int32_t *ncand,
-                                            const double *__restrict__ partial, const uint32_t *cand_cols,
-                                            const uint32_t *Pcol, uint32_t *Prow, int32_t *active, double *oldscore,
-                                            double *maxtrace, int32_t *niter, unsigned long long *nscored,
-                                            int32_t *n_active)
+// host-driven loop: grid = (G row groups, searches of the chain)
+template <int SP>
+__global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(SearchDev d, const int32_t *__restrict__ qlist)
 {
-    __shared__ double s_best[NT];
-    __shared__ int s_idx[NT];
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int q = qlist ? qlist[blockIdx.y] : blockIdx.y;
+    score_tiles<SP, false>(d, s_raw, q, blockIdx.x, d.ntiles, gridDim.x);
+}
+
+// ---- argmax, accept rule, graph update -------------------------------------------------------------------
+struct FinSmem {
+    double *best;     // [NT]
+    int *idx;         // [NT]
+    int *flag;        // [1] 1: the search goes on (a move was accepted, or the initial score was taken)
+};
+template <int NT>
+__device__ __forceinline__ FinSmem fin_smem_at(unsigned char *base)
+{
+    FinSmem f;
+    f.best = reinterpret_cast<double *>(base);
+    f.idx = reinterpret_cast<int *>(base + NT * 8);
+    f.flag = f.idx + NT;
+    return f;
+}
+__host__ __device__ constexpr size_t fin_smem_bytes(int nt) { return (size_t)nt * 12 + 16; }
+
+// scores of candidate c: sum over `etiles` tile rows of src[(q*etiles + et)*maxc + c], ascending (etiles = 1: src = scores)
+template <int NT, bool CG>
+__device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs, int q, int mode, int etiles,
+                                            const double *__restrict__ src, int32_t *n_active)
+{
+    double *s_best = fs.best;
+    int *s_idx = fs.idx;
+    const int S = d.S, maxc = d.maxc;
     const int tid = threadIdx.x;
-    if (!active[q]) return;
-    const int nc = ncand[q];
+    if (tid == 0) fs.flag[0] = 0;
+    if (!ldv<CG>(d.active + q)) { __syncthreads(); return; }
+    const int nc = ldv<CG>(d.ncand + q);
     double best = -INFINITY;
     int bidx = INT_MAX;
     for (int c = tid; c < nc; c += NT) {
         double sc = 0.0;                                           // tiles in ascending order, whatever CTA produced them
 #pragma unroll 8
-        for (int et = 0; et < etiles; ++et) sc += partial[((size_t)q * etiles + et) * maxc + c];
+        for (int et = 0; et < etiles; ++et) sc += ldv<CG>(src + ((size_t)q * etiles + et) * maxc + c);
         if (isnan(sc)) sc = 0.0;                                   // scores[is.na(scores)] <- 0   R/mnems.r:235
         if (sc > best) { best = sc; bidx = c; }                    // ascending c: first maximum kept
     }
@@ -590,63 +796,171 @@ __device__ __forceinline__ void finish_body(int q, int S, int maxc, int etiles, 
         }
         __syncthreads();
     }
-    if (tid >= 32) return;
-    best = s_best[0];
-    bidx = s_idx[0];
-    if (nc == 0 || bidx == INT_MAX) {
-        if (tid == 0) active[q] = 0;
-        return;
-    }
-    if (mode == 0) {
-        if (tid == 0) { oldscore[q] = best; maxtrace[q] = best; }
-        return;
-    }
-    const uint32_t ccol = cand_cols[((size_t)q * maxc + bidx) * 32 + tid];
-    int np = __popc(Pcol[q * 32 + tid]), ncn = __popc(ccol);
-    for (int o = 16; o > 0; o >>= 1) {
-        np += __shfl_down_sync(kFull, np, o);
-        ncn += __shfl_down_sync(kFull, ncn, o);
-    }
-    np = __shfl_sync(kFull, np, 0);
-    ncn = __shfl_sync(kFull, ncn, 0);
-    const double old = oldscore[q];
-    // R/mnems.r:279-283: better score, or equal score and fewer edges
-    const bool accept = best > old || (best == old && np > ncn);
-    const uint32_t newrow = warp_transpose(ccol, tid, S);
-    if (tid == 0) nscored[q] += (unsigned long long)nc;
-    if (accept) {
-        Prow[q * 32 + tid] = newrow;
-        if (tid == 0) {
-            oldscore[q] = best;
-            if (best > maxtrace[q]) maxtrace[q] = best;
-            niter[q] += 1;
-            atomicAdd(n_active, 1);
+    if (tid < 32) {
+        best = s_best[0];
+        bidx = s_idx[0];
+        if (nc == 0 || bidx == INT_MAX) {
+            if (tid == 0) d.active[q] = 0;
+        } else if (mode == 0) {
+            if (tid == 0) { d.oldscore[q] = best; d.maxtrace[q] = best; fs.flag[0] = 1; }
+        } else {
+            const uint32_t ccol = ldv<CG>(d.cand_cols + ((size_t)q * maxc + bidx) * 32 + tid);
+            int np = __popc(ldv<CG>(d.Pcol + q * 32 + tid)), ncn = __popc(ccol);
+            for (int o = 16; o > 0; o >>= 1) {
+                np += __shfl_down_sync(kFull, np, o);
+                ncn += __shfl_down_sync(kFull, ncn, o);
+            }
+            np = __shfl_sync(kFull, np, 0);
+            ncn = __shfl_sync(kFull, ncn, 0);
+            const double old = ldv<CG>(d.oldscore + q);
+            // R/mnems.r:279-283: better score, or equal score and fewer edges
+            const bool accept = best > old || (best == old && np > ncn);
+            const uint32_t newrow = warp_transpose(ccol, tid, S);
+            if (tid == 0) d.nscored[q] = ldv<CG>(d.nscored + q) + (unsigned long long)nc;
+            if (accept) {
+                d.Prow[q * 32 + tid] = newrow;
+                if (tid == 0) {
+                    d.oldscore[q] = best;
+                    if (best > ldv<CG>(d.maxtrace + q)) d.maxtrace[q] = best;
+                    const int it = ldv<CG>(d.niter + q) + 1;
+                    d.niter[q] = it;
+                    if (n_active) atomicAdd(n_active, 1);
+                    if (it >= d.hard_cap) { d.active[q] = 0; atomicOr(d.overflow, 2); }    // not converged: reported by the host
+                    else fs.flag[0] = 1;
+                }
+            } else if (tid == 0) {
+                d.active[q] = 0;
+            }
         }
-    } else if (tid == 0) {
-        active[q] = 0;
     }
+    __syncthreads();       // the accepted graph (Prow), the active flag and fs.flag are visible to the whole CTA
 }
 
 // finish of greedy iteration i fused with the candidate generation of iteration i + 1 (same CTA per search): one
 // launch less per iteration and no host round trip between the accept decision and the next neighbourhood.
 constexpr int kFgThreads = 1024;   // 32 warps: the 3*S candidate groups of a search spread over all of them
-__global__ void __launch_bounds__(kFgThreads) finish_gen_kernel(int S, int maxc, int etiles, int fmode, int dcap, int32_t *ncand,
-                                                         const double *partial, uint32_t *cand_cols, uint32_t *Pcol,
-                                                         uint32_t *Prow, int32_t *active, double *oldscore,
-                                                         double *maxtrace, int32_t *niter, unsigned long long *nscored,
-                                                         int32_t *n_active, uint32_t *cand_J, uint32_t *dict_masks,
-                                                         int32_t *nd, uint16_t *cand_id, uint16_t *base_id,
-                                                         uint16_t *pair_id, int32_t *nins, int32_t *overflow,
-                                                         const int32_t *__restrict__ qlist)
+__global__ void __launch_bounds__(kFgThreads) finish_gen_kernel(SearchDev d, int fmode, int32_t *n_active,
+                                                                const int32_t *__restrict__ qlist)
 {
-    const int q = qlist[blockIdx.x];                 // the searches of one chain (see search_run)
-    finish_body<kFgThreads>(q, S, maxc, etiles, fmode, ncand, partial, cand_cols, Pcol, Prow, active, oldscore, maxtrace, niter,
-                     nscored, n_active);
-    __syncthreads();       // the accepted graph (Prow) and the active flag are visible to the whole CTA
-    gen_body<kFgThreads>(q, S, maxc, dcap, 1, Prow, active, Pcol, cand_cols, cand_J, ncand, (int8_t *)nullptr, dict_masks, nd,
-                         cand_id, base_id, pair_id, nins, overflow);
+    __shared__ __align__(16) unsigned char s_gen[kGenSmemBytes];
+    __shared__ __align__(16) unsigned char s_fin[fin_smem_bytes(kFgThreads)];
+    const int q = qlist[blockIdx.x];                 // the searches of one chain (see search_run_host)
+    finish_body<kFgThreads, false>(d, fin_smem_at<kFgThreads>(s_fin), q, fmode, 1, d.scores, n_active);
+    gen_body<kFgThreads, false>(d, gen_smem_at(s_gen), q, 1);
 }
 
+// ---- the device-resident greedy loop -----------------------------------------------------------------------
+// One persistent CTA per SM.  A task is (search, first tile, number of tiles) of the current iteration of that search;
+// CTAs draw tickets from a ring.  The CTA that scores the LAST tile of a search's iteration finishes it on the spot:
+// adds the tiles (ascending), takes which.max, applies the accept rule, generates the next neighbourhood with its
+// dictionary and chains, and publishes the tasks of the next iteration.  Searches therefore advance independently of
+// each other (no launch, no grid-wide barrier, no host round trip per iteration), a long search never holds back the
+// short ones, and the SMs stay busy as long as any search has tiles left.  Results do not depend on the schedule: every
+// number is produced by the same arithmetic in the same order as in the host-driven loop (tested bit for bit).
+__device__ __forceinline__ unsigned long long task_encode(int q, int tile0, int nt)
+{
+    return ((unsigned long long)q << 40) | ((unsigned long long)tile0 << 8) | (unsigned long long)nt;
+}
+
+// (re)publishes the tiles of search q as tasks; called by one thread
+__device__ __forceinline__ void publish_search(const SearchDev &d, int q)
+{
+    const int live = max(1, *reinterpret_cast<volatile int32_t *>(d.live));
+    int chunk = (int)(((long)d.ntiles * live + 2L * d.nsm - 1) / (2L * d.nsm));
+    chunk = max(1, min(kMaxChunk, chunk));
+    const int nch = (d.ntiles + chunk - 1) / chunk;
+    d.tiles_done[q] = 0;
+    const unsigned r = atomicAdd(&d.qctl[1], (unsigned)nch);
+    for (int i = 0; i < nch; ++i)
+        d.ring[(r + i) & d.ring_mask] = task_encode(q, i * chunk, min(chunk, d.ntiles - i * chunk));
+    __threadfence();
+    while (atomicCAS(&d.qctl[2], r, r + (unsigned)nch) != r) __nanosleep(40);       // commit in reservation order
+}
+
+__global__ void search_seed_kernel(SearchDev d, int n)
+{
+    // one thread: every search starts with the score of closure(start) pending (stage 0)
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    d.qctl[0] = 0u; d.qctl[1] = 0u; d.qctl[2] = 0u; d.qctl[3] = 0u;
+    *d.live = n;
+    for (int q = 0; q < n; ++q) d.stage[q] = 0;
+    __threadfence();
+    for (int q = 0; q < n; ++q) publish_search(d, q);
+}
+
+template <int SP>
+__global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(SearchDev d)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ unsigned long long s_task;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    unsigned long long t_begin = 0ull, t_task = 0ull, busy = 0ull;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    while (true) {
+        if (tid == 0) {
+            if (t_task) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); busy += now - t_task; }
+            const unsigned idx = atomicAdd(&d.qctl[0], 1u);
+            unsigned long long task = ~0ull;
+            while (true) {
+                if (*reinterpret_cast<volatile unsigned *>(&d.qctl[3])) break;      // every search has ended (or the run was aborted)
+                const unsigned committed = *reinterpret_cast<volatile unsigned *>(&d.qctl[2]);
+                if ((int)(committed - idx) > 0) {
+                    __threadfence();
+                    task = __ldcg(d.ring + (idx & d.ring_mask));
+                    break;
+                }
+                __nanosleep(100);
+            }
+            s_task = task;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_task));
+        }
+        __syncthreads();
+        const unsigned long long task = s_task;
+        if (task == ~0ull) break;
+        const int q = (int)(task >> 40), tile0 = (int)((task >> 8) & 0xffffffffu), nt = (int)(task & 0xffu);
+        score_tiles<SP, true>(d, s_raw, q, tile0, tile0 + nt, 1);
+        __threadfence();                                   // this CTA's partial sums are out before the count moves
+        __syncthreads();
+        if (tid == 0) {
+            const int prev = atomicAdd(&d.tiles_done[q], nt);
+            s_last = prev + nt == d.ntiles;
+            if (s_last) __threadfence();
+        }
+        __syncthreads();
+        if (!s_last) continue;
+        // ---- this CTA closes the iteration of search q ----
+        const int mode = __ldcg(d.stage + q);
+        finish_body<kDictThreads, true>(d, fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes), q, mode, d.ntiles, d.partial,
+                                        nullptr);
+        const int go = fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes).flag[0];
+        __syncthreads();
+        if (go) {
+            gen_body<kDictThreads, true>(d, gen_smem_at(s_raw), q, 1);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                d.stage[q] = 1;
+                if (*reinterpret_cast<volatile int32_t *>(d.overflow) & 1) {      // dictionary overflow: stop everything
+                    *reinterpret_cast<volatile unsigned *>(&d.qctl[3]) = 1u;
+                } else {
+                    __threadfence();
+                    publish_search(d, q);
+                }
+            }
+        } else if (tid == 0) {
+            __threadfence();
+            if (atomicSub(d.live, 1) == 1) { __threadfence(); *reinterpret_cast<volatile unsigned *>(&d.qctl[3]) = 1u; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicAdd(&d.busy_ns[0], busy);
+        atomicAdd(&d.busy_ns[1], now - t_begin);
+    }
+}
 __global__ void search_init_kernel(int n, int S, const uint32_t *__restrict__ start_rows, uint32_t *__restrict__ Prow,
                                    int32_t *active, int32_t *niter, unsigned long long *nscored)
 {
@@ -751,6 +1065,7 @@ int launch_theta(const double *const *Rptr_dev, int n, int E, int S, const uint3
     return 0;
 }
 
+
 static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
 {
     dim3 grid((sb->maxc + kCT - 1) / kCT, sb->etiles, n);
@@ -773,7 +1088,7 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
 }
 
 // scores[q][c] = sum over the row tiles, ascending -- fully parallel over candidates, so the single-CTA finish step
-// reads one value per candidate instead of one per (candidate, tile)
+// of the host-driven loop reads one value per candidate instead of one per (candidate, tile)
 __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles, const int32_t *__restrict__ ncand,
                                                            const double *__restrict__ partial, double *__restrict__ scores,
                                                            const int32_t *__restrict__ qlist)
@@ -789,11 +1104,20 @@ __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles,
 
 static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
 {
-    MN_LAUNCH(gen_kernel, n, 256, 0, st, sb->S, sb->maxc, sb->dcap, mode, sb->Prow.p, sb->active.p, sb->Pcol.p,
-              sb->cand_cols.p, sb->cand_J.p, sb->ncand.p, (int8_t *)nullptr, sb->dict_masks.p, sb->nd.p, sb->cand_id.p,
-              sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p);
+    MN_LAUNCH(gen_kernel, n, 256, 0, st, sb->dev(), mode);
     return 0;
 }
+
+// the templates are instantiated for these numbers of S-gene registers
+#define MN_FOR_SP(S, M)                                                                                            \
+    do {                                                                                                           \
+        if ((S) <= 8) M(8);                                                                                        \
+        else if ((S) <= 16) M(16);                                                                                 \
+        else if ((S) <= 24) M(24);                                                                                 \
+        else if ((S) <= 28) M(28);                                                                                 \
+        else if ((S) <= 30) M(30);                                                                                 \
+        else M(32);                                                                                                \
+    } while (0)
 
 // scores of the `n` searches listed in qlist (device; nullptr = searches 0..n-1) with G row groups each
 static int launch_score_dict(SearchBatch *sb, int n, int G, const int32_t *qlist, cudaStream_t st)
@@ -807,20 +1131,12 @@ static int launch_score_dict(SearchBatch *sb, int n, int G, const int32_t *qlist
         return 0;
     }
     dim3 grid(G, n);
-#define MN_SCORE(SPV)                                                                                              \
-    MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, sb->E, S, sb->maxc, sb->dcap, G,       \
-              sb->Rptr.p, sb->ncand.p, sb->nins.p, sb->nd.p, sb->dict_masks.p, sb->base_id.p, sb->pair_id.p,       \
-              sb->Pcol.p, sb->cand_J.p, sb->cand_id.p, sb->partial.p, qlist)
-    if (S <= 8) MN_SCORE(8);
-    else if (S <= 16) MN_SCORE(16);
-    else if (S <= 24) MN_SCORE(24);
-    else if (S <= 28) MN_SCORE(28);
-    else if (S <= 30) MN_SCORE(30);
-    else MN_SCORE(32);
+    const SearchDev d = sb->dev();
+#define MN_SCORE(SPV) MN_LAUNCH(score_dict_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, d, qlist)
+    MN_FOR_SP(S, MN_SCORE);
 #undef MN_SCORE
-    const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
     dim3 rgrid((sb->maxc + 255) / 256, n);
-    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, ntiles, sb->ncand.p, sb->partial.p, sb->scores.p, qlist);
+    MN_LAUNCH(reduce_tiles_kernel, rgrid, 256, 0, st, sb->maxc, d.ntiles, sb->ncand.p, sb->partial.p, sb->scores.p, qlist);
     return 0;
 }
 
@@ -846,18 +1162,29 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     sb->nmax = nmax; sb->E = E; sb->S = S;
     sb->etiles = (E + kRows - 1) / kRows;
     sb->maxc = std::max(1, 3 * S * (S - 1));
+    const int ntiles = (E + kDictRows - 1) / kDictRows;
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            sb->sm_count = sms;
+        cudaGetLastError();
+    }
     {   // dictionary capacity: pairwise unions + deletion masks + slack, limited by the 227 KB of shared memory
         const int need = S * (S + 1) / 2 + S * S / 4 + 2 * S + 8;
-        const int fit = (int)((232448 - 4096 - 512) / (kDictRows * 8 + 4));
+        int fit = 1;
+        while (score_smem_bytes(fit + 1) + 1536 <= 232448) ++fit;   // 1.5 KB of static shared memory in the kernels
         sb->dcap = std::max(1, std::min(need + need / 2, fit));     // 50 % slack where shared memory allows (S <= 26)
-        sb->dict_smem = (size_t)sb->dcap * kDictRows * 8 + (((size_t)sb->dcap * 4 + 15) & ~(size_t)15) + 4096;
-        cudaFuncSetAttribute(score_dict_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
-        cudaFuncSetAttribute(score_dict_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
-        cudaFuncSetAttribute(score_dict_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
-        cudaFuncSetAttribute(score_dict_kernel<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
-        cudaFuncSetAttribute(score_dict_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
-        cudaFuncSetAttribute(score_dict_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem);
+        sb->dict_smem = std::max(score_smem_bytes(sb->dcap), kGenSmemBytes + fin_smem_bytes(kDictThreads));
+        // per device: set on every workspace creation (cheap), the attribute belongs to the current context
+#define MN_ATTR(SPV)                                                                                               \
+        cudaFuncSetAttribute(score_dict_kernel<SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem); \
+        cudaFuncSetAttribute(search_persistent_kernel<SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem)
+        MN_ATTR(8); MN_ATTR(16); MN_ATTR(24); MN_ATTR(28); MN_ATTR(30); MN_ATTR(32);
+#undef MN_ATTR
     }
+    sb->ring_cap = 1;
+    while (sb->ring_cap < (unsigned)nmax * (unsigned)ntiles + 1u) sb->ring_cap <<= 1;
     auto body = [&]() -> int {
         MN_TRY(sb->Rptr.alloc(nmax));
         MN_TRY(sb->Prow.alloc((size_t)nmax * 32, true)); MN_TRY(sb->Pcol.alloc((size_t)nmax * 32, true));
@@ -867,12 +1194,17 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->ncand.alloc(nmax, true)); MN_TRY(sb->active.alloc(nmax, true)); MN_TRY(sb->niter.alloc(nmax, true));
         MN_TRY(sb->n_active.alloc(2 * kChains, true)); MN_TRY(sb->theta.alloc((size_t)nmax * E));
         MN_TRY(sb->qlist.alloc(nmax, true));
-        MN_TRY(sb->partial.alloc((size_t)nmax * ((E + kDictRows - 1) / kDictRows) * sb->maxc));
+        MN_TRY(sb->partial.alloc((size_t)nmax * ntiles * sb->maxc));
         MN_TRY(sb->scores.alloc((size_t)nmax * sb->maxc));
         MN_TRY(sb->dict_masks.alloc((size_t)nmax * sb->dcap)); MN_TRY(sb->nd.alloc(nmax, true));
         MN_TRY(sb->cand_id.alloc((size_t)nmax * sb->maxc * 32, true)); MN_TRY(sb->base_id.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->overflow.alloc(1, true)); MN_TRY(sb->pair_id.alloc((size_t)nmax * 1024, true));
         MN_TRY(sb->nins.alloc(nmax, true));
+        MN_TRY(sb->rowm.alloc((size_t)nmax * 32, true)); MN_TRY(sb->chain_v.alloc((size_t)nmax * 32, true));
+        MN_TRY(sb->chain_start.alloc((size_t)nmax * 33, true)); MN_TRY(sb->nchain.alloc(nmax, true));
+        MN_TRY(sb->ring.alloc(sb->ring_cap)); MN_TRY(sb->qctl.alloc(4, true)); MN_TRY(sb->live.alloc(1, true));
+        MN_TRY(sb->tiles_done.alloc(nmax, true)); MN_TRY(sb->stage.alloc(nmax, true)); MN_TRY(sb->busy_ns.alloc(2, true));
+        MN_CU(cudaMallocHost((void **)&sb->h_busy, 2 * sizeof(unsigned long long)));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
         MN_CU(cudaMallocHost((void **)&sb->h_n_active, (2 * kChains + 1) * sizeof(int32_t)));
         for (int i = 0; i <= 2 * kChains; ++i) sb->h_n_active[i] = 0;
@@ -883,6 +1215,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
             if (h > 0) MN_CU(cudaStreamCreateWithFlags(&sb->cst[h], cudaStreamNonBlocking));
         }
         MN_CU(cudaEventCreateWithFlags(&sb->ev_fork, cudaEventDisableTiming));
+        // the zero fills above ran on the legacy default stream; the searches run on non-blocking streams
+        MN_CU(cudaDeviceSynchronize());
         return 0;
     };
     int rc = body();
@@ -895,6 +1229,7 @@ void search_destroy(SearchBatch *sb)
 {
     if (!sb) return;
     if (sb->h_n_active) cudaFreeHost(sb->h_n_active);
+    if (sb->h_busy) cudaFreeHost(sb->h_busy);
     for (int h = 0; h < kChains; ++h) {
         for (int i = 0; i < 2; ++i) if (sb->ev[h][i]) cudaEventDestroy(sb->ev[h][i]);
         if (sb->ev_join[h]) cudaEventDestroy(sb->ev_join[h]);
@@ -904,16 +1239,42 @@ void search_destroy(SearchBatch *sb)
     delete sb;
 }
 
-int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const uint32_t *start_rows_dev, cudaStream_t st)
+static int search_check_flags(SearchBatch *sb, int32_t flags)
 {
-    MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
-    const int S = sb->S;
+    if (flags & 1) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+    if (flags & 2)
+        return set_err(MNEMCU_ERR_ARG, "a greedy search did not converge within %d moves", 4 * sb->S * sb->S + 16);
+    return 0;
+}
+
+// The greedy loops of all n searches inside ONE launch (search_persistent_kernel); the host only seeds the queue.
+static int search_loop_device(SearchBatch *sb, int n, cudaStream_t st)
+{
+    const SearchDev d = sb->dev();
+    MN_CU(cudaMemsetAsync(sb->busy_ns.p, 0, 2 * sizeof(unsigned long long), st));
+    MN_LAUNCH(search_seed_kernel, 1, 32, 0, st, d, n);
+    const int grid = std::max(1, std::min(sb->sm_count, n * d.ntiles));
+#define MN_PERS(SPV) MN_LAUNCH(search_persistent_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, d)
+    MN_FOR_SP(sb->S, MN_PERS);
+#undef MN_PERS
+    int32_t *h_over = sb->h_n_active + 2 * kChains;
+    MN_CU(cudaMemcpyAsync(h_over, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MN_CU(cudaMemcpyAsync(sb->h_busy, sb->busy_ns.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    MN_CU(cudaStreamSynchronize(st));
+    sb->busy_acc += (double)sb->h_busy[0];
+    sb->resident_acc += (double)sb->h_busy[1];
+    return search_check_flags(sb, *h_over);
+}
+
+// The same loops driven from the host, one greedy iteration of a chain = three launches.  Kept for
+// scoreAdj(marginal = TRUE) (whose scorer is not dictionary-based) and as the reference schedule the device-resident
+// loop is tested against bit for bit (MNEMCU_SEARCH=host).
+static int search_loop_host(SearchBatch *sb, int n, cudaStream_t st)
+{
     const int ntiles = (sb->E + kDictRows - 1) / kDictRows;
-    MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
-    MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
-    // initial score of closure(better), R/mnems.r:135-141
-    MN_TRY(launch_gen(sb, n, 0, st));
-    MN_TRY(launch_score_dict(sb, n, pick_groups(n, ntiles, 148), nullptr, st));
+    const int sms = sb->sm_count;
+    const SearchDev d = sb->dev();
+    MN_TRY(launch_score_dict(sb, n, pick_groups(n, ntiles, sms), nullptr, st));
     // Chains.  Searches come in pairs (2p: empty start, 2p+1: previous graph, R/mnems.r:2036-2073) with very different
     // lengths, so pairs -- not single searches -- are dealt round-robin.
     int want = 2;                                      // default number of chains
@@ -929,7 +1290,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
                 if ((q >> 1) % nch == h) ql.push_back(q);
             ch[h].n = (int)ql.size() - ch[h].off;
             ch[h].st = h == 0 ? st : sb->cst[h];
-            ch[h].G = pick_groups(ch[h].n, ntiles, 148);
+            ch[h].G = pick_groups(ch[h].n, ntiles, sms);
             ch[h].done = ch[h].n == 0;
         }
         // pageable source: the call returns once the bytes are staged, so the stack vector may go out of scope
@@ -943,10 +1304,9 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     // accepted a move one iteration late (the copy of iteration it is awaited while iteration it+1 is already queued), so
     // the GPU never idles on a host round trip; the one surplus iteration at the end finds every search of the chain
     // inactive and does nothing.
-    const int hard_cap = 4 * S * S + 16;   // a strict hill-climb cannot take more moves than this in practice
     int32_t *h_over = sb->h_n_active + 2 * kChains;
     auto all_done = [&]() { for (int h = 0; h < nch; ++h) if (!ch[h].done) return false; return true; };
-    for (int it = 0; it < hard_cap && !all_done(); ++it) {
+    for (int it = 0; it < d.hard_cap + 2 && !all_done(); ++it) {
         const int slot = it & 1;
         for (int h = 0; h < nch; ++h) {
             Chain &c = ch[h];
@@ -955,10 +1315,7 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
             const int32_t *ql = sb->qlist.p + c.off;
             MN_CU(cudaMemsetAsync(na, 0, sizeof(int32_t), c.st));
             // *na counts the searches of the chain that accept a move in this fused finish
-            MN_LAUNCH(finish_gen_kernel, c.n, kFgThreads, 0, c.st, S, sb->maxc, 1, it == 0 ? 0 : 1, sb->dcap, sb->ncand.p,
-                      sb->scores.p, sb->cand_cols.p, sb->Pcol.p, sb->Prow.p, sb->active.p, sb->oldscore.p, sb->maxtrace.p,
-                      sb->niter.p, sb->nscored.p, na, sb->cand_J.p, sb->dict_masks.p, sb->nd.p, sb->cand_id.p,
-                      sb->base_id.p, sb->pair_id.p, sb->nins.p, sb->overflow.p, ql);
+            MN_LAUNCH(finish_gen_kernel, c.n, kFgThreads, 0, c.st, d, it == 0 ? 0 : 1, na, ql);
             MN_TRY(launch_score_dict(sb, c.n, c.G, ql, c.st));
             MN_CU(cudaMemcpyAsync(sb->h_n_active + 2 * h + slot, na, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
             MN_CU(cudaMemcpyAsync(h_over, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, c.st));
@@ -966,11 +1323,11 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
             if (c.pending >= 0) {
                 const int ps = c.pending & 1;
                 MN_CU(cudaEventSynchronize(sb->ev[h][ps]));
-                if (*h_over) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+                if (*h_over & 1) return search_check_flags(sb, *h_over);
                 // iteration 0's finish is the initial score (mode 0): it accepts nothing by design
                 const int acc = sb->h_n_active[2 * h + ps];
                 if (c.pending > 0 && acc == 0) c.done = true;
-                else if (c.pending > 0) c.G = pick_groups(acc, ntiles, 148);
+                else if (c.pending > 0) c.G = pick_groups(acc, ntiles, sms);
             }
             c.pending = it;
         }
@@ -980,7 +1337,21 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
         MN_CU(cudaStreamWaitEvent(st, sb->ev_join[h], 0));
     }
     MN_CU(cudaStreamSynchronize(st));
-    if (*h_over) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
+    return search_check_flags(sb, *h_over);
+}
+
+int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const uint32_t *start_rows_dev, cudaStream_t st)
+{
+    MN_ARG(n >= 1 && n <= sb->nmax, "too many searches for the workspace");
+    const int S = sb->S;
+    MN_CU(cudaMemcpyAsync(sb->Rptr.p, R_ptrs_host, sizeof(double *) * n, cudaMemcpyHostToDevice, st));
+    MN_CU(cudaMemsetAsync(sb->overflow.p, 0, sizeof(int32_t), st));
+    MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
+    // initial score of closure(better), R/mnems.r:135-141
+    MN_TRY(launch_gen(sb, n, 0, st));
+    bool host_loop = sb->marginal != 0;
+    if (const char *e = getenv("MNEMCU_SEARCH")) host_loop = host_loop || strcmp(e, "host") == 0;
+    MN_TRY(host_loop ? search_loop_host(sb, n, st) : search_loop_device(sb, n, st));
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
     return 0;
@@ -993,6 +1364,7 @@ const double *search_score(const SearchBatch *sb) { return sb->oldscore.p; }
 const double *search_maxtrace(const SearchBatch *sb) { return sb->maxtrace.p; }
 const int32_t *search_niter(const SearchBatch *sb) { return sb->niter.p; }
 const unsigned long long *search_nscored(const SearchBatch *sb) { return sb->nscored.p; }
+double search_sm_busy(const SearchBatch *sb) { return sb->resident_acc > 0 ? sb->busy_acc / sb->resident_acc : 0.0; }
 
 }  // namespace mn
 
@@ -1167,9 +1539,10 @@ extern "C" int mnemcu_neighbours(const uint8_t *P, int S, uint8_t *models, int8_
     MN_CU(cudaMemcpy(dg.p, P, (size_t)S * S, cudaMemcpyHostToDevice));
     MN_CU(cudaMemcpy(dact.p, &one, sizeof(one), cudaMemcpyHostToDevice));
     MN_TRY(launch_rows_from_u8(dg.p, 1, S, drow.p, 0));
-    MN_LAUNCH(gen_kernel, 1, 256, 0, 0, S, maxc, 0, 1, drow.p, dact.p, dPcol.p, dcc.p, dJ.p, dn.p, dkind.p,
-              (uint32_t *)nullptr, (int32_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr, (uint16_t *)nullptr,
-              (int32_t *)nullptr, (int32_t *)nullptr);
+    SearchDev d;                              // candidates only: no dictionary, no chains
+    d.S = S; d.maxc = maxc; d.Prow = drow.p; d.active = dact.p; d.Pcol = dPcol.p; d.cand_cols = dcc.p; d.cand_J = dJ.p;
+    d.ncand = dn.p; d.cand_kind = dkind.p;
+    MN_LAUNCH(gen_kernel, 1, 256, 0, 0, d, 1);
     int32_t n = 0;
     MN_CU(cudaMemcpy(&n, dn.p, sizeof(n), cudaMemcpyDeviceToHost));
     if (n > 0) {

@@ -187,3 +187,39 @@ def test_config4_shape_model_selection():
     fpar = sum(int((orc.mytc(c["phi"]) - np.eye(24, dtype=int) != 0).sum()) for c in fit["comp"]) + k * sim["E"] + (k - 1)
     ic = np.log(sim["C"]) * fpar - 2 * np.max(fit["ll"]) * np.log(2)
     assert abs(ic - out["ics"][k]) <= 1e-9 * abs(ic)
+
+
+@pytest.mark.parametrize("S,E,n", [(1, 5, 2), (2, 40, 3), (7, 130, 9), (13, 33, 5), (20, 1000, 12), (30, 2000, 10), (32, 700, 6)])
+def test_device_resident_greedy_loop_equals_the_host_driven_one(S, E, n, monkeypatch):
+    """The greedy loop runs inside one persistent kernel (search_persistent_kernel: a queue of (search, tiles) tasks, the
+    CTA that scores the last tile of an iteration finishes it and publishes the next).  Every number must be produced by
+    the same arithmetic as in the host-driven schedule (one launch per step, MNEMCU_SEARCH=host): graphs, theta, scores,
+    traces and counts are compared bit for bit, from empty and from random non-closed starts (exact score ties included:
+    duplicated and zero columns)."""
+    rng = np.random.default_rng(100 * S + n)
+    R = rng.normal(size=(n, E, S)) * 3
+    if S > 2:
+        R[:, :, 1] = R[:, :, 0]                                   # duplicated S-gene: structural ties
+        R[0, :, 2] = 0.0
+    starts = np.stack([np.triu((rng.random((S, S)) < 0.15).astype(np.uint8), 1) for _ in range(n)])
+    for st in (None, starts):
+        monkeypatch.setenv("MNEMCU_SEARCH", "host")
+        a = mb.nem_greedy(R, st)
+        monkeypatch.setenv("MNEMCU_SEARCH", "device")
+        b = mb.nem_greedy(R, st)
+        for key in ("adj", "subtopo", "score", "max_trace", "n_iter", "n_scored"):
+            assert np.array_equal(a[key], b[key]), key
+        assert b["n_iter"].max() > 0 or S == 1
+
+
+def test_em_fit_is_the_same_on_both_greedy_schedules(monkeypatch):
+    sim = simdata.make_config(dict(S=9, Egenes=12, C=4000, mw=[0.3, 0.3, 0.4], k=3, starts=5, uninform=3), seed=77)
+    init = simdata.init_phi(9, 3, 5, seed=78)
+    with mb.Context.synthetic(sim) as cx:
+        monkeypatch.setenv("MNEMCU_SEARCH", "host")
+        a = mb.em_run(cx, init, complete=True)
+        monkeypatch.setenv("MNEMCU_SEARCH", "device")
+        b = mb.em_run(cx, init, complete=True)
+    for key in ("adj", "theta", "ll", "mw", "n_iter", "probs", "best"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["stats"]["cand_scored"] == b["stats"]["cand_scored"] and a["stats"]["greedy_iters"] == b["stats"]["greedy_iters"]
