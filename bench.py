@@ -24,9 +24,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# EM loop iterations per start of the seeded benchmark fits (measured on the GPU path, which the oracle matches iteration
-# for iteration at the sizes it can run): the CPU arm cannot afford to run a fit to convergence, so it evaluates its
-# fitted cost model at this many iterations per start
+# EM loop iterations per start of the seeded benchmark fits.  The CPU arm cannot afford to run 100 starts at 1M cells to
+# convergence (about an hour of one core per start), so it evaluates its measured per-iteration cost at this many
+# iterations per start.  The numbers are the means over all starts of the device fits of the same seeded inputs
+# (profiles/r2_bench_cfg*.json, "em_iters_per_step" / starts); the device's iteration counts are those of the oracle
+# on every start the oracle has replayed (tests/test_gpu_scale_parity.py: n_iter bit-exact).  bench.py's own
+# `cpu_baseline` leg (N = 1) does not use the table: it takes the mean of the fit it has just timed.
 MEAN_EM_ITERS = {1: 4.0, 2: 6.0, 3: 10.0, 4: 10.0, 5: 12.96}
 
 
@@ -112,9 +115,8 @@ def cpu_sample(sim, init, n_threads, cells, guard=1):
     phase + exactly `guard` EM loop iterations each (max_iter_guard), with the reference's redundant recomputation
     switched on (faithful_cost).  Returns wall seconds and counts."""
     import oracle as orc
-    from mnem_b200 import simdata
     cells = min(cells, sim["C"])
-    D = simdata.host_data_native(sim, 0, cells, nthreads=max(1, n_threads))
+    D = orc.simgen(sim, 0, cells, nthreads=max(1, n_threads))
     pert = sim["pert"][:cells]
     ph = init[:n_threads]
     t0 = time.time()
@@ -125,7 +127,7 @@ def cpu_sample(sim, init, n_threads, cells, guard=1):
                 starts=len(ph))
 
 
-def cpu_extrapolated(sim, init, n_threads, cells, mean_iters):
+def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0):
     """EM iterations/s of the CPU restatement for the FULL workload, from bounded component timings.
 
     Per start the reference spends (R/mnems.r:1905-1915, 1976-2108; the oracle's orc_em_start with faithful_cost):
@@ -137,11 +139,11 @@ def cpu_extrapolated(sim, init, n_threads, cells, mean_iters):
     import concurrent.futures
 
     import oracle as orc
-    from mnem_b200 import simdata
     c = min(cells, sim["C"])
+    c0 = max(0, min(c0, sim["C"] - c))
     k, S, E = sim["k"], sim["S"], sim["E"]
-    D = simdata.host_data_native(sim, 0, c, nthreads=max(1, n_threads))
-    pert = sim["pert"][:c]
+    D = orc.simgen(sim, c0, c, nthreads=max(1, n_threads))       # the oracle's own generator twin: no product library here
+    pert = sim["pert"][c0:c0 + c]
     n_threads = max(1, min(n_threads, len(init)))
 
     def one(s):
@@ -179,15 +181,29 @@ def cpu_extrapolated(sim, init, n_threads, cells, mean_iters):
     return dict(value=float(value), seconds=wall, t_init_full=t_init, t_em_full=t_em, cells=c, starts=n_threads,
                 mean_iters=mean_iters,
                 cand_scores_per_s=float(sum(t["scored"] for t in ts) / max(1e-9, sum(2 * k * t["greedy"] for t in ts)) * n_threads),
-                sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) concurrently, first %d of %d cells "
+                sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) concurrently, cells %d..%d of %d "
                         "(%.1f s): per start getProbs(theta=NULL) %.2f s, doMean %.3f s, getProbs(theta) %.2f s (each scaled by "
                         "%d/%d cells), nem_greedy %.2f s per search (independent of the cell count); redundant passes kept; "
                         "T = init + n*(2k*doMean + 2k*greedy + getProbs) at n = %.2f EM iterations per start: init %.3g s, "
-                        "EM iteration %.3g s per start" % (n_threads, c, sim["C"], wall, m["init"], m["domean"], m["estep"],
+                        "EM iteration %.3g s per start" % (n_threads, c0, c0 + c, sim["C"], wall, m["init"], m["domean"], m["estep"],
                                                           sim["C"], c, m["greedy"], mean_iters, t_init, t_em)))
 
 
+def bench_config(args, sim, name):
+    """The `config` object of the JSON line: the same for both arms."""
+    return {"workload": name, "batch": args.batch or max(1, 20 // sim["k"]),
+            "l2": "inputs larger than L2 (D = %.1f GB per layout)" % (8e-9 * sim["E"] * sim["C"]),
+            "candidate_count": "graphs generated and scored, before unique()"}
+
+
 def run_reference(args):
+    """The reference's CPU implementation of the path (the oracle port: R is not installable here) on all host threads.
+
+    One step = one bounded sample of the workload: one EM start per host thread, all concurrently, on a slice of C/32
+    cells -- a DIFFERENT slice and different starts in every step, so the W + K steps of a default run together time
+    6/32 of the cells of the matrix once each instead of one small sample over and over.  Each step times the four
+    component passes of an EM iteration (cpu_extrapolated) and reports EM iterations/s for the full workload; what is
+    extrapolated (linear in the cell count for the three data passes) is spelled out in `sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -199,19 +215,21 @@ def run_reference(args):
     except AttributeError:
         ncpu = os.cpu_count() or 1
     nthr = max(1, min(ncpu, sim["starts"]))
-    cells = args.cpu_cells or max(2000, sim["C"] // 128)
+    cells = args.cpu_cells or max(2000, sim["C"] // 32)
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_extrapolated(sim, init, nthr, cells, MEAN_EM_ITERS.get(args.config, 10.0))
+        first = (i * nthr) % max(1, len(init) - nthr + 1)
+        r = cpu_extrapolated(sim, init[first:first + nthr], nthr, cells, MEAN_EM_ITERS.get(args.config, 10.0), c0=i * cells)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
-    sample = vals[-1]["sample"]
+    sample = "%d timed steps on disjoint slices, the last: %s" % (len(vals), vals[-1]["sample"])
     line = {"impl": "reference", "metric": "em_iterations_per_s", "value": v, "unit": "EM iterations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * float(np.mean([x["seconds"] for x in vals])), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "sample": sample},
+            "config": bench_config(args, sim, name),
+            "values_per_step": [x["value"] for x in vals],
             "cpu_baseline": {"value": v, "unit": "EM iterations/s", "cores": nthr, "kind": "port", "sample": sample},
             "cand_scores_per_s": float(np.mean([x["cand_scores_per_s"] for x in vals])),
             "e2e": {"value": v, "unit": "EM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -301,6 +319,16 @@ def run_ours(args):
                 "launches_per_step": st["passes_estep"],
                 "pairs_per_launch": (bytes_launch - 8.0 * E * Cn) / (8.0 * Cn),
                 "share_of_step": st["ms_estep"] / max(st["ms_total"], 1e-9)}
+    # the kernel that decides `value`: the device-resident greedy search (one persistent launch per EM tick).  Live numbers
+    # from this run; pipe utilisation from the committed ncu capture of the same kernel (profiles/search_ncu.json).
+    cand_rank0 = st["cand_scored"] / max(1e-9, st["ms_search"] * 1e-3)
+    roofline_search = {"bound": "fp64 issue (shared-memory look-ups + FP64 compares)", "kernel": "search_persistent_kernel",
+                       "share_of_step": st["ms_search"] / max(st["ms_total"], 1e-9),
+                       "candidates_per_s_in_search_rank0": cand_rank0, "sm_busy_in_kernel": st.get("search_sm_busy", 0.0),
+                       "ms_search_per_step": st["ms_search"]}
+    sp = os.path.join(ROOT, "profiles", "search_ncu.json")
+    if os.path.exists(sp):
+        roofline_search["ncu"] = json.load(open(sp))
     breakdown = {"ms_estep": st["ms_estep"], "ms_mstats": st["ms_mstats"], "ms_search": st["ms_search"],
                  "ms_mixture": st["ms_mixture"], "ms_total": st["ms_total"], "passes_estep": st["passes_estep"],
                  "passes_mstats": st["passes_mstats"], "search_sm_busy": st.get("search_sm_busy", 0.0)}
@@ -336,8 +364,8 @@ def run_ours(args):
                 mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
             times, iters = [], []
             # N > 1: every rank uploads 1/N of the columns from ITS host copy and the slices are exchanged over NVLink
-            # (NCCL broadcast per slice) instead of pushing N full copies of D through PCIe and the host memory bus
-            bounds = [Cn * r // world for r in range(world + 1)]
+            # (one NCCL all-gather) instead of pushing N full copies of D through PCIe and the host memory bus
+            per = -(-Cn // world)
             for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
                 queue = mdist.StartQueue(sim["starts"])
                 barrier()
@@ -345,15 +373,18 @@ def run_ours(args):
                 if world == 1:
                     cxe = mb.Context(Dh, sim["pert"], device=local)
                 else:
-                    Dd = torch.empty((Cn, E), dtype=torch.float64, device=dev)
-                    Dd[bounds[rank]:bounds[rank + 1]].copy_(host[bounds[rank]:bounds[rank + 1]], non_blocking=True)
-                    for r in range(world):
-                        dist.broadcast(Dd[bounds[r]:bounds[r + 1]], src=r)
+                    # one in-place all-gather over NVLink: rank r owns rows [r*per, (r+1)*per) of the (padded) device matrix
+                    Dd = torch.empty((world * per, E), dtype=torch.float64, device=dev)
+                    mine = Dd[rank * per:(rank + 1) * per]
+                    n_mine = max(0, min(Cn, (rank + 1) * per) - rank * per)
+                    mine[:n_mine].copy_(host[rank * per:rank * per + n_mine], non_blocking=True)
+                    dist.all_gather_into_tensor(Dd, mine)
                     torch.cuda.synchronize()
                     cxe = mb.Context.from_device(Dd.data_ptr(), E, Cn, sim["pert"], device=local)
                     del Dd
                 with cxe:
-                    r = mb.em_run(cxe, init, complete=sim["complete"], batch=args.batch, want_probs=False, next_start=queue)
+                    # probs="winner": the k x C log ratios of the best start come back to the host, as in mnem()'s result
+                    r = mb.em_run(cxe, init, complete=sim["complete"], batch=args.batch, probs="winner", next_start=queue)
                 my = sorted(queue.taken)
                 mdist.gather_winner(my, r["ll"][my], sim["starts"], device=dev)     # the winner is part of the result
                 torch.cuda.synchronize()
@@ -366,7 +397,7 @@ def run_ours(args):
             e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
                    "h2d_bytes_per_step": int(8 * E * Cn + world * (4 * Cn + sim["starts"] * k * S * S)),
                    "nvlink_bytes_per_step": int(8 * E * Cn * (world - 1)),
-                   "d2h_bytes_per_step": int(sim["starts"] * per_start),
+                   "d2h_bytes_per_step": int(sim["starts"] * per_start + world * 8 * k * Cn),   # + every rank's best probs
                    "seconds_per_step": float(np.mean(times)), "steps": len(times)}
             del hnp, Dh
         del host
@@ -382,13 +413,11 @@ def run_ours(args):
         line = {"metric": "em_iterations_per_s", "value": value, "unit": "EM iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": name, "starts_on_rank0": len(my),
-                           "sharding": "one queue of starts drained by all ranks" if world > 1 else "single GPU", "batch": args.batch or max(1, 20 // k),
-                           "l2": "inputs larger than L2 (D = %.1f GB per layout)" % (8e-9 * E * Cn),
-                           "candidate_count": "graphs generated and scored, before unique()"},
+                "config": bench_config(args, sim, name), "starts_on_rank0": len(my),
+                "sharding": "one queue of starts drained by all ranks" if world > 1 else "single GPU",
                 "em_iters_per_step": em_iters, "cand_scores_per_s": cand_rate,
                 "cand_scores_per_s_in_search": cand_rate_search, "estep_gbs": achieved,
-                "roofline": roofline, "breakdown_last_step_rank0": breakdown, "cpu_baseline": cpu, "e2e": e2e,
+                "roofline": roofline, "roofline_search": roofline_search, "breakdown_last_step_rank0": breakdown, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches_timed), "clocks": clocks, "winner_start": int(winner),
                 "wall_ms_per_step": 1e3 * float(np.mean([x["wall"] for x in recs]))}
         print(json.dumps(line))

@@ -152,6 +152,26 @@ typedef struct {
     void *next_start_user;
     int affinity;        /* mnem(affinity =): 0 soft responsibilities (default), 1 hard assignments in every
                           * getAffinity call of the loop (R/mnems.r:1393-1417); not with complete = TRUE */
+    /* Optional decision tape for audits (NULL = off; costs a few device-to-host copies per EM iteration): every
+     * decision of the fit that compares floating-point sums, as int32 records [code, start, index, ...]:
+     *   1 start inner  theta[k*E]             theta inside the theta-free getProbs (R/mnems_low.r:618-619), inner iteration
+     *   6 start inner  flag                    `ll0 - llold > 0` there (:646-648)
+     *   2 start iter comp restart n rows[n*S]  a greedy search (R/mnems.r:203-291): the graph (S row masks, bit j of row s =
+     *                                          edge s -> j, diagonal set) after each of its n accepted moves
+     *   3 start iter comp pick                 which restart was kept (:2069-2073)
+     *   4 start iter   theta[k*E]              theta after the M-step of EM iteration iter
+     *   5 start iter   accept improved         `probs$ll > probs0$ll` (:2104) and whether getProbs improved on its input
+     *   7 start count                          best result replaced after `count` EM iterations (:1960-1963, :2144-2147)
+     *   8 start n_iter                         end of the start
+     * tests/ replay it through the CPU oracle (oracle/mnem_oracle.c, orc_advice). */
+    int32_t *tape;
+    int64_t tape_cap;    /* capacity of `tape` in int32 words; a fit that needs more fails and reports the need in
+                          * mnemcu_em_stats::tape_words */
+    int probs_mode;      /* layout of probs_out: 0 = one k x C block per start (starts * k * C doubles);
+                          * 1 = ONE k x C block, that of the winning start among those this call fitted -- what mnem()
+                          * returns (R/mnems.r:2222-2240) without keeping k x C doubles per start on the host */
+    const double *mw;    /* mnem(mw =): k initial mixture weights of every start (R/mnems.r:1771-1773, handed to the first
+                          * getProbs :1906-1913); NULL = rep(1, k)/k */
 } mnemcu_em_opts;
 
 typedef struct {
@@ -163,6 +183,7 @@ typedef struct {
     double ms_total, ms_estep, ms_mstats, ms_search, ms_mixture;   /* CUDA-event times */
     double estep_bytes;      /* algorithmic bytes moved by all E-step launches */
     double search_sm_busy;   /* device-resident greedy loop: time its CTAs spent on tasks / time they were resident */
+    int64_t tape_words;      /* int32 words of the decision tape (0 when off) */
 } mnemcu_em_stats;
 
 /* mnem(D, phi = init) EM phase: do_inits for every start, R/mnems.r:1884-2165 (explicit-phi entry :1792-1793).

@@ -29,14 +29,16 @@ NEXT_START_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p)
 class EmOpts(C.Structure):
     _fields_ = [("complete", C.c_int), ("logtype", C.c_double), ("batch", C.c_int), ("max_trace", C.c_int),
                 ("max_iter_guard", C.c_int), ("next_start", NEXT_START_FN), ("next_start_user", C.c_void_p),
-                ("affinity", C.c_int)]
+                ("affinity", C.c_int), ("tape", C.POINTER(C.c_int32)), ("tape_cap", C.c_int64),
+                ("probs_mode", C.c_int), ("mw", C.POINTER(C.c_double))]
 
 
 class EmStats(C.Structure):
     _fields_ = [("em_iters", C.c_int64), ("cand_scored", C.c_int64), ("greedy_iters", C.c_int64),
                 ("passes_estep", C.c_int64), ("passes_mstats", C.c_int64), ("ms_total", C.c_double),
                 ("ms_estep", C.c_double), ("ms_mstats", C.c_double), ("ms_search", C.c_double),
-                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double), ("search_sm_busy", C.c_double)]
+                ("ms_mixture", C.c_double), ("estep_bytes", C.c_double), ("search_sm_busy", C.c_double),
+                ("tape_words", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol of include/mnemcu.h

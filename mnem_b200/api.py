@@ -403,8 +403,55 @@ def sample_init(S, k, starts, seed=0):
     return init_phi(S, k, starts, seed)
 
 
+def parse_tape(words, k, E, S):
+    """Decision tape of mnemcu_em_run (record layout: include/mnemcu.h, mnemcu_em_opts::tape) -> {start: dict}.
+
+    Per start: init_theta [T][k][E], init_best [T], searches {(iter, comp, restart): [n][S] uint32 row masks},
+    pick [n_iter][k], theta [n_iter][k][E], accept / improved [n_iter], best_at (sorted counts), n_iter."""
+    w = np.asarray(words, dtype=np.int32)
+    out = {}
+    kE = k * E
+
+    def st(s):
+        return out.setdefault(int(s), dict(init_theta={}, init_best={}, searches={}, pick={}, theta={}, accept={},
+                                           improved={}, best_at=[], n_iter=None))
+    i = 0
+    while i < len(w):
+        code, s = int(w[i]), int(w[i + 1])
+        d = st(s)
+        if code == 1:
+            d["init_theta"][int(w[i + 2])] = w[i + 3:i + 3 + kE].reshape(k, E).copy()
+            i += 3 + kE
+        elif code == 6:
+            d["init_best"][int(w[i + 2])] = int(w[i + 3])
+            i += 4
+        elif code == 2:
+            it, comp, rst, n = (int(x) for x in w[i + 2:i + 6])
+            d["searches"][(it, comp, rst)] = w[i + 6:i + 6 + n * S].view(np.uint32).reshape(n, S).copy()
+            i += 6 + n * S
+        elif code == 3:
+            d["pick"][(int(w[i + 2]), int(w[i + 3]))] = int(w[i + 4])
+            i += 5
+        elif code == 4:
+            d["theta"][int(w[i + 2])] = w[i + 3:i + 3 + kE].reshape(k, E).copy()
+            i += 3 + kE
+        elif code == 5:
+            d["accept"][int(w[i + 2])] = int(w[i + 3])
+            d["improved"][int(w[i + 2])] = int(w[i + 4])
+            i += 5
+        elif code == 7:
+            d["best_at"].append(int(w[i + 2]))
+            i += 3
+        elif code == 8:
+            d["n_iter"] = int(w[i + 2])
+            i += 3
+        else:
+            raise ValueError("decision tape: unknown record code %d at word %d" % (code, i))
+    return out
+
+
 def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, max_iter_guard=0, want_probs=True,
-           next_start=None, affinity=0):
+           next_start=None, affinity=0, tape=False, probs="all", mw=None):
     """mnemcu_em_run on a Context: all starts, returns per-start arrays + winner + stats.
 
     next_start: optional callable returning the next start index to fit (or -1 when none is left) -- the ticket
@@ -413,10 +460,18 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
     init_phi = np.asarray(init_phi)
     starts, k = init_phi.shape[:2]
     S, E, Cn = cx.S, cx.E, cx.C
+    mw0 = None
+    if mw is not None:                     # mnem(mw =): initial mixture weights of every start (R/mnems.r:1771-1773)
+        mw0 = np.ascontiguousarray(mw, dtype=np.float64)
+        if mw0.shape != (k,):
+            raise ValueError("mw must hold k weights")
     pb, _, _ = _graphs(init_phi.reshape(starts * k, S, S), S)
     adj = np.zeros(starts * k * S * S, dtype=np.uint8)
     theta = np.zeros((starts, k, E), dtype=np.int32)
-    probs = np.zeros((starts, Cn, k)) if want_probs else None
+    if probs not in ("all", "winner"):
+        raise ValueError("probs must be 'all' or 'winner'")
+    winner_only = probs == "winner"       # ONE k x C block: that of the best start this call fitted (what mnem() returns)
+    probs = np.zeros((1 if winner_only else starts, Cn, k)) if want_probs else None
     mw = np.zeros((starts, k))
     ll = np.zeros(starts)
     nit = np.zeros(starts, dtype=np.int32)
@@ -433,14 +488,20 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
             return -1
 
     cb = _lib.NEXT_START_FN(_ticket) if next_start is not None else _lib.NEXT_START_FN()
-    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None, int(affinity))
+    tape_buf = None
+    if tape:        # audit runs: capacity for 64 EM iterations of 2k searches with S*S/2 moves each, per start (checked by the library)
+        tape_buf = np.zeros(starts * (2 * k * 64 * (S * S // 2 + 8) * S + (64 + 100) * (k * E + 16)) + 1024, dtype=np.int32)
+    o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None, int(affinity),
+               tape_buf.ctypes.data_as(C.POINTER(C.c_int32)) if tape else None, tape_buf.size if tape else 0,
+               1 if winner_only else 0, dp(mw0) if mw0 is not None else None)
     check(load_library().mnemcu_em_run(cx._h, starts, k, u8p(pb), C.byref(o), u8p(adj), i32p(theta), dp(probs), dp(mw),
                                        dp(ll), i32p(nit), dp(tr[0]), dp(tr[1]), dp(tr[2]), dp(tr[3]), C.byref(best),
                                        C.byref(st)))
     if cb_err:
         raise cb_err[0]
     stats = {f: getattr(st, f) for f, _ in EmStats._fields_}
-    return dict(best=best.value, adj=_ungraphs(adj, starts * k, S).reshape(starts, k, S, S), theta=theta,
+    extra = dict(tape=parse_tape(tape_buf[:st.tape_words], k, E, S), tape_words=tape_buf[:st.tape_words].copy()) if tape else {}
+    return dict(**extra, best=best.value, adj=_ungraphs(adj, starts * k, S).reshape(starts, k, S, S), theta=theta,
                 probs=np.transpose(probs, (0, 2, 1)) if want_probs else None, mw=mw, ll=ll, n_iter=nit,
                 lls=[tr[0][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)],
                 phievo=[tr[1][s, :max(0, min(nit[s], max_trace))].copy() for s in range(starts)],
@@ -449,8 +510,8 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
 
 
 def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0,
-         Rho=None, affinity=0):
-    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho).
+         Rho=None, affinity=0, mw=None):
+    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho, affinity, mw).
 
     Returns the fields of the reference's `mnem` object that the hot path produces: limits (per start), comp
     (phi reduced, theta), mw (lambda0, R/mnems.r:2298-2303), probs (k x C log ratios of the winner), lls, phievo,
@@ -466,7 +527,8 @@ def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, se
             phi = sample_init(cx.S, k, starts, seed)
         if k == 1:
             return _mnem_k1(cx, phi[0, 0], complete, logtype)
-        r = em_run(cx, phi, complete=complete, logtype=logtype, batch=batch, max_iter_guard=max_iter_guard, affinity=affinity)
+        r = em_run(cx, phi, complete=complete, logtype=logtype, batch=batch, max_iter_guard=max_iter_guard, affinity=affinity,
+                   mw=mw)
         b = r["best"]
         limits = [dict(adj=r["adj"][s], theta=r["theta"][s], probs=r["probs"][s], mw=r["mw"][s], ll=r["ll"][s],
                        lls=r["lls"][s], phievo=r["phievo"][s], thetaevo=r["thetaevo"][s], mwevo=r["mwevo"][s])

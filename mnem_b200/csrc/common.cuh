@@ -245,6 +245,10 @@ const int32_t *search_niter(const SearchBatch *sb);         // [n]
 const unsigned long long *search_nscored(const SearchBatch *sb);   // [n]
 // fraction of their resident time the CTAs of the device-resident greedy loop spent on tasks, over all runs of sb
 double search_sm_busy(const SearchBatch *sb);
+// decision tape (audit runs): rows of the graph after every accepted move, [q][search_hard_cap][32]
+int search_enable_tape(SearchBatch *sb);
+const uint32_t *search_tape(const SearchBatch *sb);
+int search_hard_cap(const SearchBatch *sb);
 // theta[q][e] = first argmax_j (R_q %*% cols_q)[e, j] with the null column FIRST (null_last = 0, R/mnems.r:447-450)
 // or LAST (null_last = 1, R/mnems_low.r:617-619); W_out (n*E*S) optional.  cols: [n][32] column masks.
 int launch_theta(const double *const *R_dev_ptrs_dev, int n, int E, int S, const uint32_t *cols, int null_last,

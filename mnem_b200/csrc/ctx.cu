@@ -7,9 +7,13 @@
 
 namespace mn {
 
-// ---- synthetic data: counter-based, integer-exact, identical on host and device ----------------------------
-// noise(seed, idx) = (sum of twelve 16-bit uniforms - 6*65535) / 65536: Irwin-Hall(12), mean 0, variance ~1,
-// a multiple of 2^-16, so host and device agree bit for bit (no libm involved).
+// ---- synthetic data: counter-based, identical on host and device ------------------------------------------
+// noise(seed, idx) = (sum of twelve 16-bit uniforms - 6*65535) / 65536  [Irwin-Hall(12): mean 0, variance ~1]
+//                  + (a 53-bit uniform - 0.5) / 65536                   [fills the mantissa below 2^-16]
+// Every operation is a single correctly rounded IEEE operation on exactly representable operands (no libm), so host
+// and device agree bit for bit; the second term makes the values full-precision doubles, so that sums over them round
+// differently in different orders (with multiples of 2^-16 alone every E-step sum would be exact in ANY order and the
+// parity of summation orders could not be observed).
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z)
 {   // splitmix64 finaliser
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
@@ -25,7 +29,10 @@ __host__ __device__ __forceinline__ double syn_noise(uint64_t seed, uint64_t idx
         sum += (uint32_t)(w & 0xffff) + (uint32_t)((w >> 16) & 0xffff) + (uint32_t)((w >> 32) & 0xffff) +
                (uint32_t)(w >> 48);
     }
-    return ((double)sum - 393210.0) * (1.0 / 65536.0);
+    const uint64_t w4 = mix64((seed ^ 0xA0761D6478BD642FULL) + 0xE7037ED1A0B428DBULL * (idx + 1));
+    const double coarse = ((double)sum - 393210.0) * (1.0 / 65536.0);                       // exact
+    const double fine = ((double)(w4 >> 11) * (1.0 / 9007199254740992.0) - 0.5) * (1.0 / 65536.0);   // exact
+    return coarse + fine;                                                                   // one rounding
 }
 // D[e,c] = (bin - 0.5)/0.5 + noise (README.md:38-39); bin = phi_true[comp(c)][pert(c), theta_true[comp(c)][e]]
 // (simData R/mnems.r:3084-3138), uninformative rows (theta 0) are fair coin flips (:3147-3151).
@@ -214,6 +221,7 @@ static int ctx_layout(mnemcu_ctx *cx, int E, int C, const std::vector<uint32_t> 
     if (e1 != cudaSuccess) return set_err(MNEMCU_ERR_NOMEM, "cudaMalloc Dcol (%zu bytes): %s", ncol * 8, cudaGetErrorString(e1));
     e1 = cudaMalloc((void **)&cx->Dblk, sizeof(double) * std::max<size_t>(1, nblkE));
     if (e1 == cudaSuccess) e1 = cudaMemset(cx->Dblk + (size_t)cx->nblk * E * kBlkCells, 0, sizeof(double) * 256 * kBlkCells);
+    if (e1 == cudaSuccess) e1 = cudaDeviceSynchronize();      // legacy-stream memset vs the non-blocking work stream
     if (e1 != cudaSuccess) return set_err(MNEMCU_ERR_NOMEM, "cudaMalloc Dblk (%zu bytes): %s", nblkE * 8, cudaGetErrorString(e1));
     return 0;
 }

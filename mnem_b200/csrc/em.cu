@@ -90,6 +90,7 @@ struct Slot {
     double llold_inner = -INFINITY;
     // do_inits state
     double ll = -INFINITY, llold = -INFINITY, bestll = -INFINITY, probs_ll = -INFINITY;
+    double maxll = -INFINITY;     // max(lls) over ALL iterations (limits$ll, R/mnems.r:2157), whatever the trace capacity
     bool time0 = true, stop = false, have_theta = false, pending_outer = false, pending_outer_guard = false;
     int count = 0;
     double mw[32], bestmw[32], mwold[32];
@@ -122,6 +123,15 @@ struct Engine {
     double *tacc[kTimers] = {};
     int ntimer = 0;
     mnemcu_em_stats stats{};
+    // Decision tape (audit runs, mnemcu_em_opts::tape): every decision of the fit that compares floating-point sums --
+    // accepted greedy moves, restart picks, theta attachments, EM-level accept / best updates -- as int32 records
+    // [code, start, index, ...] (codes in include/mnemcu.h), so that the CPU oracle can replay the fit decision by decision.
+    bool tape_on = false;
+    std::vector<int32_t> tape;
+    std::vector<int32_t> h_i32;
+    std::vector<uint32_t> h_u32;
+    std::vector<double> h_f64;
+    void rec(std::initializer_list<int32_t> w) { tape.insert(tape.end(), w.begin(), w.end()); }
 
     ~Engine()
     {
@@ -185,6 +195,8 @@ struct Engine {
         MN_CU(cudaMallocHost((void **)&h_counters, sizeof(unsigned long long) * 2));
         for (int i = 0; i < kTimers; ++i) { MN_CU(cudaEventCreate(&tev[i][0])); MN_CU(cudaEventCreate(&tev[i][1])); }
         for (int b = 0; b < B; ++b) slots[b].best_rows.assign((size_t)k * 32, 0u);
+        // the zero fills of DevBuf::alloc ran on the legacy default stream; the work stream does not synchronise with it
+        MN_CU(cudaDeviceSynchronize());
         return 0;
     }
 
@@ -290,6 +302,47 @@ struct Engine {
         for (int b : list)
             MN_CU(cudaMemcpyAsync(d_theta.p + (size_t)b * k * cx->E, d_theta_tmp.p + (size_t)b * k * cx->E,
                                   sizeof(int32_t) * (size_t)k * cx->E, cudaMemcpyDeviceToDevice, st));
+        if (tape_on) MN_TRY(tape_theta(list, 1));
+        return 0;
+    }
+
+    // tape: theta of the listed slots (code 1: inside the theta-free getProbs, index = inner iteration; code 4: after an
+    // M-step, index = EM iteration)
+    int tape_theta(const std::vector<int> &list, int code)
+    {
+        const size_t kE = (size_t)k * cx->E;
+        h_i32.resize(kE);
+        for (int b : list) {
+            MN_CU(cudaMemcpyAsync(h_i32.data(), d_theta.p + (size_t)b * kE, sizeof(int32_t) * kE, cudaMemcpyDeviceToHost, st));
+            MN_CU(cudaStreamSynchronize(st));
+            rec({code, slots[b].start, code == 1 ? slots[b].inner : slots[b].count});
+            tape.insert(tape.end(), h_i32.begin(), h_i32.end());
+        }
+        return 0;
+    }
+
+    // tape: the accepted moves of every search of the tick (code 2) and the restart pick of every pair (code 3)
+    int tape_searches(const std::vector<int32_t> &pairs)
+    {
+        const int np = (int)pairs.size(), S = cx->S, cap = search_hard_cap(sb);
+        std::vector<int32_t> nit(2 * np);
+        std::vector<double> mtr(2 * np);
+        MN_CU(cudaMemcpyAsync(nit.data(), search_niter(sb), sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, st));
+        MN_CU(cudaMemcpyAsync(mtr.data(), search_maxtrace(sb), sizeof(double) * 2 * np, cudaMemcpyDeviceToHost, st));
+        MN_CU(cudaStreamSynchronize(st));
+        for (int q = 0; q < 2 * np; ++q) {
+            const int m = pairs[q >> 1], b = m / k, comp = m - b * k;
+            h_u32.resize((size_t)std::max(1, nit[q]) * 32);
+            if (nit[q] > 0) {
+                MN_CU(cudaMemcpyAsync(h_u32.data(), search_tape(sb) + (size_t)q * cap * 32, sizeof(uint32_t) * 32 * nit[q],
+                                      cudaMemcpyDeviceToHost, st));
+                MN_CU(cudaStreamSynchronize(st));
+            }
+            rec({2, slots[b].start, slots[b].count, comp, q & 1, nit[q]});
+            for (int i = 0; i < nit[q]; ++i)
+                for (int r = 0; r < S; ++r) tape.push_back((int32_t)h_u32[(size_t)i * 32 + r]);
+            if (q & 1) rec({3, slots[b].start, slots[b].count, comp, mtr[q] > mtr[q - 1] ? 1 : 0});   // = pick_kernel
+        }
         return 0;
     }
 
@@ -335,6 +388,7 @@ struct Engine {
                   search_adj_rows(sb), search_closed_rows(sb), search_theta(sb), search_niter(sb), search_nscored(sb),
                   d_res1.p, d_clo.p, d_theta.p, d_edge.p, d_thch.p, d_counters.p);
         MN_TRY(toc(&stats.ms_search));
+        if (tape_on) { MN_TRY(tape_searches(pairs)); MN_TRY(tape_theta(list, 4)); }
         return 0;
     }
 };
@@ -492,6 +546,8 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     Engine en;
     MN_TRY(en.init(cx, k, B, opts->complete, opts->logtype, true));
     en.affinity = opts->affinity;
+    MN_ARG(opts->tape_cap >= 0 && (opts->tape || opts->tape_cap == 0), "tape_cap without a tape buffer");
+    if (opts->tape) { en.tape_on = true; MN_TRY(search_enable_tape(en.sb)); }
     cudaStream_t st = en.st;
     const int T = en.T;
     const size_t kC = (size_t)k * C, kE = (size_t)k * E, kSS = (size_t)k * S * S;
@@ -507,6 +563,12 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         }
         return next_seq < starts ? next_seq++ : -1;
     };
+    MN_ARG(opts->probs_mode == 0 || opts->probs_mode == 1, "probs_mode must be 0 or 1");
+    if (opts->mw)
+        for (int i = 0; i < k; ++i) MN_ARG(opts->mw[i] >= 0.0 && std::isfinite(opts->mw[i]), "mw must be finite and non-negative");
+    const bool winner_probs = probs_out && opts->probs_mode == 1;
+    DevBuf<double> winner_L;                  // probs of the best start so far, internal layout
+    if (winner_probs) MN_TRY(winner_L.alloc(en.kCp));
     cudaEvent_t evA, evB;
     MN_CU(cudaEventCreate(&evA)); MN_CU(cudaEventCreate(&evB));
     MN_CU(cudaEventRecord(evA, st));
@@ -518,6 +580,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         const int sidx = s.start;
         // final best update, R/mnems.r:2144-2147
         if (s.ll - s.bestll > 0) {
+            if (en.tape_on) en.rec({7, sidx, s.count});
             s.bestll = s.ll;
             MN_CU(cudaMemcpyAsync(en.d_best_rows.p + (size_t)b * k * 32, en.d_res1.p + (size_t)b * k * 32,
                                   sizeof(uint32_t) * k * 32, cudaMemcpyDeviceToDevice, st));
@@ -530,20 +593,26 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         MN_CU(cudaMemcpyAsync(adj_out + (size_t)sidx * kSS, en.d_u8.p + (size_t)b * kSS, kSS, cudaMemcpyDeviceToHost, st));
         MN_CU(cudaMemcpyAsync(theta_out + (size_t)sidx * kE, en.d_theta_best.p + (size_t)b * kE, sizeof(int32_t) * kE,
                               cudaMemcpyDeviceToHost, st));
-        if (probs_out) {
+        if (probs_out && !winner_probs) {
             MN_TRY(launch_L_from_internal(cx, en.buf(b, s.best), k, en.Lstage.p, st));
             MN_CU(cudaMemcpyAsync(probs_out + (size_t)sidx * kC, en.Lstage.p, sizeof(double) * kC, cudaMemcpyDeviceToHost, st));
         }
         MN_CU(cudaStreamSynchronize(st));
         for (int i = 0; i < k; ++i) mw_out[(size_t)sidx * k + i] = s.bestmw[i];
-        double mx = -INFINITY;                                              // limits$ll <- max(lls)  :2157
-        if (lls) {
-            for (int i = 0; i < std::min(s.count, mt); ++i) mx = std::max(mx, lls[(size_t)sidx * mt + i]);
-        } else mx = s.bestll;
+        const double mx = s.maxll;                                          // limits$ll <- max(lls)  :2157
         ll_out[sidx] = mx;
         n_iter_out[sidx] = s.count;
+        if (en.tape_on) en.rec({8, sidx, s.count});
         en.stats.em_iters += s.count;
-        if (winner < 0 || winner_ll <= mx) { winner_ll = mx; winner = sidx; }   // `<=`: last maximal start, :2226
+        // `<=` in an upward scan over the starts (:2222-2230): the maximal start with the LARGEST index wins, whatever
+        // the order in which the slots finish
+        if (winner < 0 || mx > winner_ll || (mx == winner_ll && sidx > winner)) {
+            winner_ll = mx; winner = sidx;
+            if (winner_probs) {
+                MN_CU(cudaMemcpyAsync(winner_L.p, en.buf(b, s.best), sizeof(double) * en.kCp, cudaMemcpyDeviceToDevice, st));
+                MN_CU(cudaStreamSynchronize(st));          // the slot's buffers are reused by the next start
+            }
+        }
         s.start = -1;
         --running;
         return 0;
@@ -560,7 +629,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         MN_TRY(en.load_graphs(b, init_phi + (size_t)sidx * kSS));
         MN_CU(cudaMemsetAsync(en.buf(b, 0), 0, sizeof(double) * en.kCp, st));      // probs <- matrix(0, k, C)  :1905
         MN_CU(cudaMemsetAsync(en.flag(b, 0), 0, sizeof(int32_t), st));
-        MN_TRY(en.set_mw(b, nullptr));                                            // mw <- rep(1, k)/k  :1771-1773
+        MN_TRY(en.set_mw(b, opts->mw));                                           // mw <- rep(1, k)/k unless given  :1771-1773
         // getProbs preamble, R/mnems_low.r:591-595
         MN_TRY(en.op_stats({b}, {0}, false, false, 127, true));
         // best graphs default to the initial ones (bestres is only assigned inside the loop)
@@ -591,6 +660,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                 Slot &s = en.slots[b];
                 if (!s.time0) {
                     if (s.ll - s.bestll > 0) {
+                        if (en.tape_on) en.rec({7, s.start, s.count});
                         s.bestll = s.ll;
                         MN_CU(cudaMemcpyAsync(en.d_best_rows.p + (size_t)b * k * 32, en.d_res1.p + (size_t)b * k * 32,
                                               sizeof(uint32_t) * k * 32, cudaMemcpyDeviceToDevice, st));
@@ -633,6 +703,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             for (int b : ini) {
                 Slot &s = en.slots[b];
                 const double ll0 = en.h_ll[b * 128];
+                if (en.tape_on) en.rec({6, s.start, s.inner, ll0 - s.llold_inner > 0 ? 1 : 0});
                 if (ll0 - s.llold_inner > 0) s.best = s.nw;
                 s.cur = s.nw;
                 s.llold_inner = ll0;
@@ -653,6 +724,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                 double lo = -INFINITY;
                 for (int t = 0; t < T; ++t) { if (en.h_ll[b * 128 + t] - lo > 0) improved = true; lo = en.h_ll[b * 128 + t]; }
                 const double newll = en.h_ll[b * 128 + T - 1];
+                if (en.tape_on) en.rec({5, s.start, s.count, newll > s.probs_ll ? 1 : 0, improved ? 1 : 0});
                 if (newll > s.probs_ll) {                                          // :2104-2106
                     if (improved) s.cur = s.nw;                                   // else getProbs returned its input
                     s.probs_ll = newll;
@@ -684,6 +756,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                 long double dm = 0;
                 for (int i = 0; i < k; ++i) dm += fabs(s.mw[i] - s.mwold[i]);
                 const int sidx = s.start;
+                if (s.ll > s.maxll) s.maxll = s.ll;
                 if (s.count < mt) {
                     if (lls) lls[(size_t)sidx * mt + s.count] = s.ll;
                     if (phievo) phievo[(size_t)sidx * mt + s.count] = ec;
@@ -708,6 +781,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         return 0;
     };
     int rc = body();
+    if (!rc && winner_probs && winner >= 0) {
+        rc = launch_L_from_internal(cx, winner_L.p, k, en.Lstage.p, st);
+        if (!rc && cudaMemcpyAsync(probs_out, en.Lstage.p, sizeof(double) * kC, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = set_err(MNEMCU_ERR_CUDA, "copy of the winner's probs failed");
+    }
     if (!rc) rc = en.flush_timers();
     if (!rc) {
         cudaEventRecord(evB, st);
@@ -720,6 +798,14 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         en.stats.greedy_iters = (int64_t)en.h_counters[1];
         *best_out = winner;
         en.stats.search_sm_busy = en.sb ? search_sm_busy(en.sb) : 0.0;
+        en.stats.tape_words = (int64_t)en.tape.size();
+        if (en.tape_on) {
+            if ((int64_t)en.tape.size() > opts->tape_cap) {
+                if (stats_out) *stats_out = en.stats;        // tape_words = the capacity this fit needs
+                rc = set_err(MNEMCU_ERR_ARG, "decision tape: %lld words needed, capacity %lld", (long long)en.tape.size(),
+                             (long long)opts->tape_cap);
+            } else std::copy(en.tape.begin(), en.tape.end(), opts->tape);
+        }
         if (stats_out) *stats_out = en.stats;
     }
     cudaEventDestroy(evA); cudaEventDestroy(evB);

@@ -53,6 +53,7 @@ struct SearchDev {
     int32_t *tiles_done = nullptr;    // [q] tiles of the current iteration already scored
     int32_t *stage = nullptr;         // [q] 0: the pending scores are the initial score of closure(start); 1: neighbours
     unsigned long long *busy_ns = nullptr;   // [0] ns the CTAs spent on tasks, [1] ns they were resident (utilisation of the loop)
+    uint32_t *tape = nullptr;         // decision tape (audit runs only): [q][hard_cap][32] rows of the graph after every accepted move
 };
 
 struct SearchBatch {
@@ -69,6 +70,7 @@ struct SearchBatch {
     DevBuf<int32_t> ncand, active, niter, n_active, theta, nd, nins, overflow, nchain, live, tiles_done, stage;
     DevBuf<double> partial, scores, oldscore, maxtrace;
     DevBuf<unsigned long long> nscored, ring, busy_ns;
+    DevBuf<uint32_t> tape;            // see SearchDev::tape; allocated by search_enable_tape
     unsigned long long *h_busy = nullptr;     // pinned copy of busy_ns
     double busy_acc = 0.0, resident_acc = 0.0;   // accumulated over the search_run calls of this workspace
     DevBuf<unsigned> qctl;
@@ -93,7 +95,7 @@ struct SearchBatch {
         d.nd = nd.p; d.nins = nins.p; d.overflow = overflow.p; d.nchain = nchain.p; d.partial = partial.p;
         d.scores = scores.p; d.oldscore = oldscore.p; d.maxtrace = maxtrace.p; d.nscored = nscored.p; d.ring = ring.p;
         d.ring_mask = ring_cap ? ring_cap - 1 : 0; d.qctl = qctl.p; d.live = live.p; d.tiles_done = tiles_done.p;
-        d.stage = stage.p; d.busy_ns = busy_ns.p;
+        d.stage = stage.p; d.busy_ns = busy_ns.p; d.tape = tape.p;
         return d;
     }
 };
@@ -819,6 +821,8 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
             if (tid == 0) d.nscored[q] = ldv<CG>(d.nscored + q) + (unsigned long long)nc;
             if (accept) {
                 d.Prow[q * 32 + tid] = newrow;
+                if (d.tape) d.tape[((size_t)q * d.hard_cap + ldv<CG>(d.niter + q)) * 32 + tid] = newrow;
+                __syncwarp();                      // lane 0 advances niter below
                 if (tid == 0) {
                     d.oldscore[q] = best;
                     if (best > ldv<CG>(d.maxtrace + q)) d.maxtrace[q] = best;
@@ -1357,6 +1361,14 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     return 0;
 }
 
+int search_enable_tape(SearchBatch *sb)
+{
+    if (sb->tape.p) return 0;
+    MN_TRY(sb->tape.alloc((size_t)sb->nmax * (4 * sb->S * sb->S + 16) * 32));
+    return 0;
+}
+const uint32_t *search_tape(const SearchBatch *sb) { return sb->tape.p; }
+int search_hard_cap(const SearchBatch *sb) { return 4 * sb->S * sb->S + 16; }
 const uint32_t *search_adj_rows(const SearchBatch *sb) { return sb->adj_rows.p; }
 const uint32_t *search_closed_rows(const SearchBatch *sb) { return sb->closed_rows.p; }
 const int32_t *search_theta(const SearchBatch *sb) { return sb->theta.p; }

@@ -108,11 +108,10 @@ static int launch_estep_t(const mnemcu_ctx *cx, const uint32_t *maskT, int M, co
     const int groups = (M + MT - 1) / MT;
     const int eper = ((cx->E + esplit - 1) / esplit + 31) / 32 * 32;
     size_t smem = esplit > 1 ? (size_t)groups * (esplit - 1) * MT * 32 * sizeof(double2) : 0;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {     // small C: up to 7 partial-sum slabs of MT x 32 double2 (70 KB at MT = 20)
+    // the attribute belongs to the current device's context (a process may hold contexts on several devices): set it
+    // whenever it is needed -- the call is cheap next to a pass over D
+    if (smem > 48 * 1024)                    // small C: up to 7 partial-sum slabs of MT x 32 double2 (70 KB at MT = 20)
         MN_CU(cudaFuncSetAttribute(estep_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 7 * 20 * 32 * 16));
-        attr_set = true;
-    }
     MN_LAUNCH(estep_kernel<MT>, cx->nblk, 32 * groups * esplit, smem, st, cx->Dblk, cx->E, maskT, cx->blk_seg, M, eper,
               groups, out);
     return 0;
@@ -419,11 +418,8 @@ static int launch_mstats_t(const mnemcu_ctx *cx, const double *gam, int M, int M
     dim3 grid((M + MT - 1) / MT, (pairs + tpb - 1) / tpb, cx->nchunk);
     const int gw = gamma_stride(M);
     const size_t smem = (size_t)kStages * kStCells * ((size_t)(2 * tpb + 8) + gw) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        MN_CU(cudaFuncSetAttribute(mstats_kernel<MT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        attr_set = true;
-    }
+    // per device / context, see launch_estep_t
+    MN_CU(cudaFuncSetAttribute(mstats_kernel<MT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     MN_LAUNCH(mstats_kernel<MT8>, grid, tpb, smem, st, cx->Dcol, cx->Epad, gam, gw, M, MT, cx->chunk_cp0, cx->chunk_n,
               partial);
     return 0;

@@ -9,6 +9,7 @@ produce bit-identical matrices for any sub-range of cells.
   D[e, c] = (bin[e, c] - 0.5) / 0.5 + noise(seed, e + E*c)                                   README.md:38-39
   bin[e, c] = closure(Nem_i)[pert(c), theta_i(e)]  for the component i of cell c             R/mnems.r:3084-3138
   noise = (sum of twelve 16-bit uniforms - 6*65535) / 65536   (Irwin-Hall(12): mean 0, variance 1.0000)
+        + (53-bit uniform - 0.5) / 65536                      (full-precision mantissas: sums are order-dependent)
 """
 import numpy as np
 
@@ -84,7 +85,10 @@ def noise(seed, idx):
             w = _mix64(np.uint64(seed) + _G * (np.uint64(3) * idx + np.uint64(j + 1)))
             tot += (w & np.uint64(0xFFFF)) + ((w >> np.uint64(16)) & np.uint64(0xFFFF)) + \
                    ((w >> np.uint64(32)) & np.uint64(0xFFFF)) + (w >> np.uint64(48))
-    return (tot.astype(np.float64) - 393210.0) * (1.0 / 65536.0)
+        w4 = _mix64((np.uint64(seed) ^ np.uint64(0xA0761D6478BD642F)) + np.uint64(0xE7037ED1A0B428DB) * (idx + np.uint64(1)))
+    coarse = (tot.astype(np.float64) - 393210.0) * (1.0 / 65536.0)
+    fine = ((w4 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0) - 0.5) * (1.0 / 65536.0)
+    return coarse + fine
 
 
 def host_data(sim, c0=0, nc=None):

@@ -24,7 +24,7 @@ class NemInfo(C.Structure):
 
 class EmOpts(C.Structure):
     _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
-                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int)]
+                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int), ("mw0", c_dp)]
 
 
 class EmInfo(C.Structure):
@@ -243,7 +243,7 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 
 # ---- EM --------------------------------------------------------------------------------------------------
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
-            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld"):
+            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None):
     """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
     D = _f(D)
     E, Cn = D.shape
@@ -257,7 +257,9 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     mw = np.zeros((starts, k))
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     infos = (EmInfo * starts)()
-    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode), int(affinity))
+    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
+    o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode), int(affinity),
+               _d(mw0) if mw0 is not None else None)
     best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
                                 _i32(theta), _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
     adj = _ungraphs(adj, starts * k, S).reshape(starts, k, S, S)
@@ -273,6 +275,124 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
                thetaevo=[tr[2][s, :n_iter[s]].copy() for s in range(starts)],
                mwevo=[tr[3][s, :n_iter[s]].copy() for s in range(starts)])
     return res
+
+
+def simgen(sim, c0=0, nc=None, nthreads=8):
+    """Cells [c0, c0+nc) of the synthetic matrix of a mnem_b200.simdata config dict (E x nc, Fortran order) from the
+    oracle's own C twin of the generator (oracle/simgen.c) -- the CPU arm never loads the product library."""
+    nc = sim["C"] - c0 if nc is None else nc
+    out = np.zeros((sim["E"], nc), order="F")
+    pert = np.ascontiguousarray(sim["pert"], dtype=np.int32)
+    comp = np.ascontiguousarray(sim["comp"], dtype=np.uint8)
+    phi = _graphs(sim["phi_true"])
+    th = np.ascontiguousarray(sim["theta_true"], dtype=np.int32)
+    lib().orc_simgen_fill(_d(out), int(sim["E"]), C.c_int64(c0), C.c_int64(nc), _i32(pert), int(sim["S"]), _u8(comp), _u8(phi),
+                          _i32(th), C.c_uint64(sim["seed"]), int(nthreads))
+    return out
+
+
+ADV_KINDS = ("greedy_move", "greedy_stop", "restart_pick", "theta", "init_theta", "init_best", "accept", "best_or_length")
+
+
+class Advice(C.Structure):
+    _fields_ = [("tol", C.c_double), ("tol_ll", C.c_double), ("T", C.c_int), ("init_theta", c_i32p), ("init_best", c_i32p),
+                ("n_em", C.c_int), ("move_off", C.POINTER(C.c_int64)), ("move_rows", C.POINTER(C.c_uint32)),
+                ("pick", c_i32p), ("theta", c_i32p), ("accept", c_i32p), ("best_at", c_i32p),
+                ("n_checked", C.c_long * 8), ("n_forced", C.c_long * 8), ("n_hard", C.c_long * 8),
+                ("max_forced", C.c_double * 8), ("min_hard", C.c_double * 8), ("diverged", C.c_int),
+                ("first_hard", C.c_char * 256)]
+
+
+def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", start=0, cap=1 << 24):
+    """One EM start fitted by the oracle while it writes a decision tape of its own (device record format).  Returns the
+    int32 words (parse with mnem_b200.api.parse_tape) and the fit's n_iter / ll."""
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    init_phi = np.asarray(init_phi)
+    k = init_phi.shape[0]
+    buf = np.zeros(cap, dtype=np.int32)
+    L_ = lib(acc)
+    L_.orc_recorder_words.restype = C.c_int64
+    L_.orc_set_recorder(_i32(buf), C.c_int64(cap), int(start))
+    try:
+        pb = _graphs(init_phi.reshape(k, S, S))
+        adj = np.zeros(k * S * S, dtype=np.uint8)
+        th = np.zeros((k, E), dtype=np.int32)
+        L = np.zeros((Cn, k))
+        mw = np.zeros(k)
+        tr = [np.zeros(256) for _ in range(4)]
+        info = EmInfo()
+        o = EmOpts(256, int(bool(complete)), logtype, 0, 0, 0, 0)
+        L_.orc_em_start(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), _u8(adj), _i32(th), _d(L), _d(mw), _d(tr[0]),
+                        _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
+        n = int(L_.orc_recorder_words())
+    finally:
+        L_.orc_set_recorder(None, C.c_int64(0), 0)
+    if n > cap:
+        raise RuntimeError("tape capacity %d < %d words" % (cap, n))
+    return dict(words=buf[:n].copy(), n_iter=info.n_iter, ll=info.ll, adj=_ungraphs(adj, k, S), theta=th, mw=mw,
+                lls=tr[0][:info.n_iter].copy())
+
+
+def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e-13, tol_ll=1e-12, max_trace=256,
+                 affinity=0, acc="ld"):
+    """One EM start replayed against the decision tape of a device fit (mnem_b200.api.parse_tape(...)[start]).
+
+    The oracle runs the start in its own arithmetic and takes the tape's choice wherever its own decision differs by
+    less than `tol` (scores, weights; relative) / `tol_ll` (log-likelihoods) -- see orc_advice in mnem_oracle.c.
+    Returns the fit (like mnem_em, one start) plus report = {kind: dict(checked, forced, hard, max_forced, min_hard)},
+    diverged and first_hard."""
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    init_phi = np.asarray(init_phi)
+    k = init_phi.shape[0]
+    assert C.sizeof(Advice) == lib(acc).orc_advice_size()
+    T = len(tape["init_theta"])
+    n_em = int(tape["n_iter"])
+    init_theta = np.ascontiguousarray(np.stack([tape["init_theta"][t] for t in range(T)]), dtype=np.int32)
+    init_best = np.array([tape["init_best"][t] for t in range(T)], dtype=np.int32)
+    off = np.zeros(n_em * k * 2 + 1, dtype=np.int64)
+    rows = []
+    for it in range(n_em):
+        for i in range(k):
+            for j in range(2):
+                m = tape["searches"][(it, i, j)]
+                rows.append(m.reshape(-1, S))
+                q = (it * k + i) * 2 + j
+                off[q + 1] = off[q] + len(m)
+    rows = np.ascontiguousarray(np.concatenate(rows + [np.zeros((1, S), dtype=np.uint32)]), dtype=np.uint32)
+    pick = np.array([tape["pick"][(it, i)] for it in range(n_em) for i in range(k)] + [0], dtype=np.int32)
+    theta = np.ascontiguousarray(np.stack([tape["theta"][it] for it in range(n_em)] + [np.zeros((k, E), dtype=np.int32)]),
+                                 dtype=np.int32)
+    accept = np.array([tape["accept"][it] for it in range(n_em)] + [0], dtype=np.int32)
+    best_at = np.zeros(n_em + 2, dtype=np.int32)
+    for c in tape["best_at"]:
+        best_at[c] = 1
+    adv = Advice()
+    adv.tol, adv.tol_ll, adv.T, adv.n_em = tol, tol_ll, T, n_em
+    adv.init_theta, adv.init_best = _i32(init_theta), _i32(init_best)
+    adv.move_off, adv.move_rows = off.ctypes.data_as(C.POINTER(C.c_int64)), rows.ctypes.data_as(C.POINTER(C.c_uint32))
+    adv.pick, adv.theta, adv.accept, adv.best_at = _i32(pick), _i32(theta), _i32(accept), _i32(best_at)
+    pb = _graphs(init_phi.reshape(k, S, S))
+    adj = np.zeros(k * S * S, dtype=np.uint8)
+    th = np.zeros((k, E), dtype=np.int32)
+    L = np.zeros((Cn, k))
+    mw = np.zeros(k)
+    tr = [np.zeros(max_trace) for _ in range(4)]
+    info = EmInfo()
+    o = EmOpts(max_trace, int(bool(complete)), logtype, 0, 0, 0, int(affinity))
+    lib(acc).orc_em_start_advised(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), C.byref(adv), _u8(adj), _i32(th),
+                                  _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
+    n = info.n_iter
+    report = {name: dict(checked=int(adv.n_checked[q]), forced=int(adv.n_forced[q]), hard=int(adv.n_hard[q]),
+                         max_forced=float(adv.max_forced[q]), min_hard=float(adv.min_hard[q]))
+              for q, name in enumerate(ADV_KINDS)}
+    return dict(adj=_ungraphs(adj, k, S), theta=th, probs=L.T.copy(), mw=mw, ll=info.ll, n_iter=n, lls=tr[0][:n].copy(),
+                phievo=tr[1][:n].copy(), thetaevo=tr[2][:n].copy(), mwevo=tr[3][:n].copy(), n_raw=info.n_raw,
+                n_dec=info.n_dec, n_dec_tight=info.n_dec_tight, min_margin=info.min_margin, report=report,
+                diverged=bool(adv.diverged), first_hard=adv.first_hard.decode("utf-8", "replace"))
 
 
 def final_mw(L, mw_best, complete=False, logtype=2.0, affinity=0, acc="ld"):

@@ -501,6 +501,98 @@ int orc_neighbours(const uint8_t *P, int S, uint8_t *models, int8_t *kind, int *
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Decision replay ("advice").  TEST HARNESS, not part of the reference's algorithm.                    */
+/*                                                                                                      */
+/* Every graph the EM returns is the outcome of comparisons between floating-point sums, and at scale a  */
+/* few per cent of them are closer than the rounding error of ANY summation order (the greedy search     */
+/* keeps accepting moves that improve a score of 4e6 by 1e-9, see n_dec_tight).  Two correct             */
+/* implementations then legitimately part ways.  To still compare a device fit with this oracle decision */
+/* by decision, the device records every such decision on a tape (include/mnemcu.h, mnemcu_em_opts::tape)*/
+/* and the oracle replays the fit in ITS OWN arithmetic: wherever its decision differs from the tape's   */
+/* it measures the margin in its own numbers; a margin <= tol means "decided by rounding" and the tape's  */
+/* choice is taken (counted in n_forced), a larger one is a genuine disagreement (n_hard; the replay then */
+/* stops listening to the tape).  With n_hard == 0 both fits walk through the same graphs, and the final  */
+/* results are compared exactly (graphs, theta) and to 1e-9 (likelihoods) by the caller.                  */
+/* ------------------------------------------------------------------------------------------------ */
+enum { ADV_MOVE = 0, ADV_STOP, ADV_PICK, ADV_THETA, ADV_INIT_THETA, ADV_INIT_BEST, ADV_ACCEPT, ADV_BEST, ADV_KINDS };
+typedef struct {
+    double tol;                  /* relative margin below which a score / weight comparison counts as rounding noise */
+    double tol_ll;               /* same for log-likelihood comparisons */
+    int T;                       /* inner iterations of the theta-free getProbs on tape */
+    const int32_t *init_theta;   /* [T][k*E] in 0..S */
+    const int32_t *init_best;    /* [T] */
+    int n_em;                    /* EM iterations on tape */
+    const int64_t *move_off;     /* [n_em*k*2 + 1] first move of search (iter, comp, restart) in move_rows */
+    const uint32_t *move_rows;   /* [moves][S] row masks (bit j of row s = edge s -> j, diagonal set) after each accepted move */
+    const int32_t *pick;         /* [n_em*k] */
+    const int32_t *theta;        /* [n_em][k*E] */
+    const int32_t *accept;       /* [n_em] */
+    const int32_t *best_at;      /* [n_em + 1]: best result replaced after `count` iterations */
+    /* report */
+    long n_checked[ADV_KINDS], n_forced[ADV_KINDS], n_hard[ADV_KINDS];
+    double max_forced[ADV_KINDS];     /* largest margin that was overridden */
+    double min_hard[ADV_KINDS];       /* smallest margin that was NOT (first evidence of a real disagreement) */
+    int diverged;
+    char first_hard[256];
+} orc_advice;
+
+static __thread orc_advice *g_adv = NULL;           /* active replay of the calling thread */
+static __thread const uint32_t *g_adv_rows = NULL;  /* moves of the search about to run */
+static __thread int g_adv_nmoves = 0;
+static __thread double *g_adv_W = NULL;             /* if set, nem_greedy leaves the subweights of its final graph here */
+static __thread int g_adv_probs = 0;                /* the next getProbs call is the theta-free one on tape */
+
+/* The oracle can also WRITE a tape of its own fit, in the device's record format (include/mnemcu.h).  Used to test the
+ * replay on the CPU: the tape of the double-accumulator build replayed by the long-double build is the same situation
+ * as a device tape (two correct implementations that round differently). */
+static __thread int32_t *g_rec = NULL;
+static __thread int64_t g_rec_n = 0, g_rec_cap = 0;
+static __thread int g_rec_start = 0, g_rec_iter = 0, g_rec_comp = 0, g_rec_restart = 0, g_rec_probs = 0;
+void orc_set_recorder(int32_t *buf, int64_t cap, int start) { g_rec = buf; g_rec_cap = cap; g_rec_n = 0; g_rec_start = start; }
+int64_t orc_recorder_words(void) { return g_rec_n; }
+static void rec_w(int32_t w) { if (g_rec) { if (g_rec_n < g_rec_cap) g_rec[g_rec_n] = w; g_rec_n++; } }
+static void rec_theta(int code, int idx, const int32_t *th, size_t n, int S, int coded_null_last)
+{
+    if (!g_rec) return;
+    rec_w(code); rec_w(g_rec_start); rec_w(idx);
+    for (size_t i = 0; i < n; i++) rec_w(coded_null_last && th[i] == S + 1 ? 0 : th[i]);
+}
+
+static int adv_on(void) { return g_adv && !g_adv->diverged; }
+static void adv_forced(int kind, double mg)
+{
+    g_adv->n_forced[kind]++;
+    if (mg > g_adv->max_forced[kind]) g_adv->max_forced[kind] = mg;
+}
+static void adv_hard(int kind, double mg, const char *what, int a, int b, int c)
+{
+    g_adv->n_hard[kind]++;
+    if (mg < g_adv->min_hard[kind]) g_adv->min_hard[kind] = mg;
+    if (!g_adv->diverged)
+        snprintf(g_adv->first_hard, sizeof g_adv->first_hard, "%s (at %d, %d, %d): margin %.3e > tolerance", what, a, b, c, mg);
+    g_adv->diverged = 1;
+}
+/* theta of one component against the tape: W is E x ncol column-major (subweights), own[e] / tape[e] in 0..S with
+ * 0 = the null column (value 0).  Entries that differ are overridden when the two weights are closer than
+ * tol * sum_j |W[e, j]|.  Returns the number of overridden entries. */
+static int adv_theta(int kind, const double *W, int E, int S, int32_t *own, const int32_t *tape, int where_a, int where_b)
+{
+    int nf = 0;
+    for (int e = 0; e < E && adv_on(); e++) {
+        g_adv->n_checked[kind]++;
+        if (own[e] == tape[e]) continue;
+        double sc = 0;
+        for (int j = 0; j < S; j++) sc += fabs(W[e + (size_t)j * E]);
+        const double wa = own[e] == 0 ? 0.0 : W[e + (size_t)(own[e] - 1) * E];
+        const double wb = (tape[e] < 1 || tape[e] > S) ? 0.0 : W[e + (size_t)(tape[e] - 1) * E];
+        const double mg = fabs(wa - wb) / (sc > 1e-300 ? sc : 1e-300);
+        if (tape[e] >= 0 && tape[e] <= S && mg <= g_adv->tol) { adv_forced(kind, mg); own[e] = tape[e]; nf++; }
+        else adv_hard(kind, mg, kind == ADV_THETA ? "theta after the M-step" : "theta of the initial E-step", where_a, where_b, e);
+    }
+    return nf;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* nem(search="greedy", runs=1, domean already applied): R/mnems.r:111-142, 203-307, 362-379           */
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -538,6 +630,8 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
     uint8_t *models = (uint8_t *)malloc((size_t)3 * SS * SS + SS);
     int8_t *kind = (int8_t *)malloc((size_t)3 * SS + 1);
     int haveP = 0;
+    int64_t rec_hdr = -1;
+    if (g_rec) { rec_w(2); rec_w(g_rec_start); rec_w(g_rec_iter); rec_w(g_rec_comp); rec_w(g_rec_restart); rec_hdr = g_rec_n; rec_w(0); }
     double oldscore = orc_score_adj_m(R, E, S, better, 1, marginal, logtype, NULL, NULL);   /* :135-141 closes inside */
     double maxtrace = oldscore;
     long nscored = 0, nraw = 0, ndec = 0, ntight = 0;
@@ -568,7 +662,8 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
             (sc_) = marginal ? score_total_marginal((Wbuf_), E, S, logtype, NULL) : score_total((Wbuf_), E, S, NULL); \
             if (isnan(sc_)) (sc_) = 0.0;                                         /* :235 */                  \
         } while (0)
-        if (g_inner > 1 && nm > 1) {
+        double *adv_scs = NULL;
+        if ((g_inner > 1 && nm > 1) || adv_on()) {
             /* candidates are independent: score them on g_inner threads, then take which.max in candidate order */
             double *scs = (double *)malloc(sizeof(double) * (size_t)nm);
 #ifdef _OPENMP
@@ -589,8 +684,8 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
                 if (sc > bests) { second = bests; bests = sc; bestidx = m; }     /* which.max: first */
                 else if (sc > second && sc < bests) second = sc;
             }
-            free(scs);
-            { double sc; ORC_SCORE_CAND(bestidx, Pbest, sc); (void)sc; }          /* subweights of the winner */
+            if (adv_on()) adv_scs = scs; else free(scs);
+            if (!adv_scs) { double sc; ORC_SCORE_CAND(bestidx, Pbest, sc); (void)sc; }   /* subweights of the winner */
         } else {
             for (int m = 0; m < nm; m++) {
                 double sc;
@@ -602,11 +697,50 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
                 } else if (sc > second && sc < bests) second = sc;
             }
         }
-#undef ORC_SCORE_CAND
         const uint8_t *best = models + (size_t)bestidx * SS;
         int nb = 0, nc = 0;
         for (int i = 0; i < SS; i++) { nb += better[i] == 1; nc += best[i] == 1; }
         double scale = fabs(bests) > 1e-300 ? fabs(bests) : 1e-300;   /* margins relative to the score itself */
+        int force_accept = 0, force_stop = 0;
+        if (adv_scs) {
+            /* replay: the tape's decision for this iteration against the oracle's own (see orc_advice) */
+            const int accept_own = bests > oldscore || (bests == oldscore && nb > nc);
+            if (niter < g_adv_nmoves) {
+                const uint32_t *rows = g_adv_rows + (size_t)niter * S;
+                int mstar = -1;
+                for (int m = 0; m < nm && mstar < 0; m++) {
+                    const uint8_t *cand = models + (size_t)m * SS;
+                    int same = 1;
+                    for (int j = 0; j < S && same; j++)
+                        for (int s_ = 0; s_ < S; s_++)
+                            if ((cand[s_ + j * S] != 0) != (int)((rows[s_] >> j) & 1u)) { same = 0; break; }
+                    if (same) mstar = m;
+                }
+                g_adv->n_checked[ADV_MOVE]++;
+                if (mstar < 0) adv_hard(ADV_MOVE, INFINITY, "the taped move is no neighbour of the current graph", niter, nm, 0);
+                else if (!(mstar == bestidx && accept_own)) {
+                    const double m1 = (bests - adv_scs[mstar]) / scale, m2 = (oldscore - adv_scs[mstar]) / scale;
+                    const double mg = m1 > m2 ? (m1 > 0 ? m1 : 0) : (m2 > 0 ? m2 : 0);
+                    if (mg <= g_adv->tol) {
+                        adv_forced(ADV_MOVE, mg);
+                        if (getenv("ORC_TRACE_MARGIN"))
+                            fprintf(stderr, "forced move: iter %d own idx %d (%.17g, accept %d) tape idx %d (%.17g) old %.17g\n", niter,
+                                    bestidx, bests, accept_own, mstar, adv_scs[mstar], oldscore);
+                        bestidx = mstar; bests = adv_scs[mstar]; best = models + (size_t)bestidx * SS; force_accept = 1;
+                    } else adv_hard(ADV_MOVE, mg, "greedy move", niter, bestidx, mstar);
+                }
+            } else {
+                g_adv->n_checked[ADV_STOP]++;
+                if (accept_own) {
+                    const double mg = (bests - oldscore) / scale;
+                    if (mg <= g_adv->tol) { adv_forced(ADV_STOP, mg); force_stop = 1; }
+                    else adv_hard(ADV_STOP, mg, "greedy search stops on the tape but not here", niter, bestidx, 0);
+                }
+            }
+            { double sc; ORC_SCORE_CAND(bestidx, Pbest, sc); (void)sc; }          /* subweights of the move taken */
+            free(adv_scs);
+        }
+#undef ORC_SCORE_CAND
         if (bests != oldscore && fabs(bests - oldscore) / scale < minmargin) minmargin = fabs(bests - oldscore) / scale;
         if (isfinite(second) && (bests - second) / scale < minmargin) minmargin = (bests - second) / scale;
         ndec++;
@@ -616,8 +750,14 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
                                            (isfinite(second) && (bests - second) / scale < 1e-13)))
             fprintf(stderr, "near-tie: greedy iter %d nm %d best %.17g (idx %d kind %d) second %.17g old %.17g\n", niter, nm,
                     bests, bestidx, (int)kind[bestidx], second, oldscore);
-        if (bests > oldscore || (bests == oldscore && nb > nc)) {                /* :279-286 */
+        if (!force_stop && (force_accept || bests > oldscore || (bests == oldscore && nb > nc))) {   /* :279-286 */
             memcpy(tmp, best, SS); memcpy(better, tmp, SS);
+            if (g_rec)
+                for (int s_ = 0; s_ < S; s_++) {
+                    uint32_t rw = 0;
+                    for (int j = 0; j < S; j++) if (better[s_ + j * S]) rw |= 1u << j;
+                    rec_w((int32_t)rw);
+                }
             oldscore = bests;
             if (oldscore > maxtrace) maxtrace = oldscore;
             memcpy(P, Pbest, sizeof(double) * (size_t)E * S);
@@ -626,11 +766,22 @@ void orc_nem_greedy_m(const double *R, int E, int S, const uint8_t *start, int m
         } else break;                                                            /* :287-289 */
     }
     /* :362-369 theta from the closed final graph, :374 reduction */
-    orc_score_adj_m(R, E, S, better, 1, marginal, logtype, theta_out, NULL);
+    if (g_rec && rec_hdr >= 0 && rec_hdr < g_rec_cap) g_rec[rec_hdr] = niter;
+    orc_score_adj_m(R, E, S, better, 1, marginal, logtype, theta_out, g_adv_W);
     orc_trans_reduce(better, S, adj_out);
     if (info) { info->score = oldscore; info->max_trace = maxtrace; info->n_iter = niter; info->n_scored = nscored;
                 info->min_margin = minmargin; info->n_raw = nraw; info->n_dec = ndec; info->n_dec_tight = ntight; }
     free(P); free(Wc); free(Pbest); free(models); free(kind);
+}
+
+/* replay of theta inside the theta-free getProbs: th[e] in 1..S+1 (S+1 = the appended null column), tape in 0..S */
+static void adv_init_theta(const double *W, int E, int S, int32_t *th, const int32_t *tape, int count, int comp)
+{
+    int32_t *own = (int32_t *)malloc(sizeof(int32_t) * E);
+    for (int e = 0; e < E; e++) own[e] = th[e] == S + 1 ? 0 : th[e];
+    if (adv_theta(ADV_INIT_THETA, W, E, S, own, tape, count, comp) > 0)
+        for (int e = 0; e < E; e++) th[e] = own[e] == 0 ? S + 1 : own[e];
+    free(own);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -665,7 +816,12 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
         for (int q = 0; q < SS; q++) clo[(size_t)i * SS + q] = clo[(size_t)i * SS + q] != 0;
         orc_mytc(clo + (size_t)i * SS, S); }                                     /* :610 */
     int have0 = 0;
+    const int adv_probs = g_adv_probs;                     /* replay: this is the theta-free call the tape describes */
+    g_adv_probs = 0;
+    const int rec_probs = g_rec_probs && !theta;
+    g_rec_probs = 0;
     for (int count = 0; count < max_count; count++) {                            /* converged = -Inf: never stops early */
+        const int adv_here = adv_probs && !theta && adv_on() && count < g_adv->T;
         if (!theta) orc_get_affinity(probs, k, C, mw, affinity, complete, logtype, post);   /* :601-603 (probsold = probs) */
         if ((!theta || !have0) && g_inner > 1 && !faithful_cost && S <= 32) {
             /* Same arithmetic with ONE pass over D per step and threads over independent outputs (see g_inner):
@@ -701,8 +857,11 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
                         }
                     }
                 }
-                for (int i = 0; i < k; i++)
+                for (int i = 0; i < k; i++) {
                     orc_max_col_row(Wall + (size_t)i * (S + 1) * E, E, S + 1, th + (size_t)i * E);   /* values 1..S+1 */
+                    if (adv_here) adv_init_theta(Wall + (size_t)i * (S + 1) * E, E, S, th + (size_t)i * E,
+                                                 g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
+                }
                 free(Wall);
             } else {
                 for (size_t q = 0; q < (size_t)k * E; q++) th[q] = theta[q] == 0 ? S + 1 : theta[q];     /* :621-622 */
@@ -744,6 +903,7 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
                             }
                     }
                     orc_max_col_row(Wtmp, E, S + 1, thi);                         /* values 1..S+1 */
+                    if (adv_here) adv_init_theta(Wtmp, E, S, thi, g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
                 } else {
                     for (int e = 0; e < E; e++) { int t = theta[(size_t)i * E + e]; thi[e] = t == 0 ? S + 1 : t; }  /* :621-622 */
                 }
@@ -763,8 +923,20 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
             }
             have0 = 1;
         }
+        if (rec_probs) rec_theta(1, count, th, (size_t)k * E, S, 1);
         double ll0 = orc_get_ll(probs0, k, C, mw, complete, logtype);            /* :643 */
-        if (ll0 - llold > 0) memcpy(best, probs0, sizeof(double) * kc);          /* :646-648 */
+        int better_ll = ll0 - llold > 0;
+        if (adv_here) {
+            g_adv->n_checked[ADV_INIT_BEST]++;
+            const int want = g_adv->init_best[count] != 0;
+            if (want != better_ll) {
+                const double mg = fabs(ll0 - llold) / (fabs(llold) > 1e-300 ? fabs(llold) : 1e-300);
+                if (isfinite(mg) && mg <= g_adv->tol_ll) { adv_forced(ADV_INIT_BEST, mg); better_ll = want; }
+                else adv_hard(ADV_INIT_BEST, mg, "best probs inside the initial getProbs", count, 0, 0);
+            }
+        }
+        if (rec_probs) { rec_w(6); rec_w(g_rec_start); rec_w(count); rec_w(better_ll); }
+        if (better_ll) memcpy(best, probs0, sizeof(double) * kc);                /* :646-648 */
         memcpy(probs, probs0, sizeof(double) * kc);                              /* :649 */
         mw_update_a(probs, k, C, mw, affinity, complete, logtype, 0, scratch);   /* :653-657 */
         llold = ll0;                                                             /* :658 */
@@ -798,6 +970,7 @@ typedef struct {
                              * resolve such noise-level (<= 1e-12 relative) comparisons as FALSE / TRUE so that both
                              * legitimate outcomes can be enumerated */
     int affinity;           /* mnem(affinity =): 0 soft responsibilities, 1 hard assignments in every getAffinity call */
+    const double *mw0;      /* mnem(mw =): initial mixture weights (R/mnems.r:1771-1773); NULL = rep(1, k)/k */
 } orc_em_opts;
 
 typedef struct {
@@ -814,10 +987,32 @@ typedef struct {
 
 /* outputs: adj_out k*S*S (reduced, diag 0), theta_out k*E, L_out k*C (bestprobs), mw_out k (bestmw),
  * lls/phievo/thetaevo/mwevo traces of length n_iter. */
+void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *init_phi,
+                          const orc_em_opts *o, orc_advice *adv, uint8_t *adj_out, int32_t *theta_out, double *L_out,
+                          double *mw_out, double *lls, double *phievo, double *thetaevo, double *mwevo, orc_em_info *info);
 void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *init_phi,
                   const orc_em_opts *o, uint8_t *adj_out, int32_t *theta_out, double *L_out, double *mw_out,
                   double *lls, double *phievo, double *thetaevo, double *mwevo, orc_em_info *info)
 {
+    orc_em_start_advised(D, E, C, pert, S, k, init_phi, o, NULL, adj_out, theta_out, L_out, mw_out, lls, phievo, thetaevo,
+                         mwevo, info);
+}
+
+/* adv != NULL: replay of a device fit, see orc_advice.  adv == NULL: the plain restatement. */
+void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, int S, int k, const uint8_t *init_phi,
+                          const orc_em_opts *o, orc_advice *adv, uint8_t *adj_out, int32_t *theta_out, double *L_out,
+                          double *mw_out, double *lls, double *phievo, double *thetaevo, double *mwevo, orc_em_info *info)
+{
+    g_adv = adv;
+    if (adv) {
+        for (int q = 0; q < ADV_KINDS; q++) { adv->n_checked[q] = adv->n_forced[q] = adv->n_hard[q] = 0; adv->max_forced[q] = 0;
+                                              adv->min_hard[q] = INFINITY; }
+        adv->diverged = 0; adv->first_hard[0] = 0;
+        g_adv_probs = 1;
+    }
+    g_rec_probs = g_rec != NULL;
+    double *Wfin0 = adv ? (double *)malloc(sizeof(double) * (size_t)E * S) : NULL;
+    double *Wfin1 = adv ? (double *)malloc(sizeof(double) * (size_t)E * S) : NULL;
     const int SS = S * S;
     size_t kc = (size_t)k * C;
     double logtype = o->logtype;
@@ -836,7 +1031,7 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     int32_t *bestth = (int32_t *)malloc(sizeof(int32_t) * (size_t)k * E);
     int have_res1_theta = 0;
     double mw[256], bestmw[256], mwnew[256];
-    for (int i = 0; i < k; i++) mw[i] = 1.0 / k;                                   /* R/mnems.r:1771-1773 */
+    for (int i = 0; i < k; i++) mw[i] = o->mw0 ? o->mw0[i] : 1.0 / k;             /* R/mnems.r:1771-1773 */
     memcpy(res1_adj, init_phi, (size_t)k * SS);                                   /* :1885-1893 */
     memset(res1_th, 0, sizeof(int32_t) * (size_t)k * E);
     memset(probs, 0, sizeof(double) * kc);                                        /* :1905 */
@@ -859,9 +1054,32 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     double minmargin = INFINITY, acceptmargin = INFINITY;
     /* :1955-1958 with converged=-Inf, increase=TRUE: (ll - llold > -Inf & |ll - llold| > 0) | time0, & !stop.
      * `count < max_iter` binds only to the !increase arm (operator precedence). */
-    while ((((ll - llold > -INFINITY) && fabs(ll - llold) > 0) || time0) && !stop) {
+    for (;;) {
+        int go = (((ll - llold > -INFINITY) && fabs(ll - llold) > 0) || time0) && !stop;
+        if (adv_on()) {
+            g_adv->n_checked[ADV_BEST]++;
+            const int want = count < adv->n_em;
+            if (want != go) {
+                /* `stop` is integer arithmetic on graphs both sides share; what can differ is |ll - llold| > 0 */
+                const double mg = fabs(ll - llold) / (fabs(ll) > 1e-300 ? fabs(ll) : 1e-300);
+                if (!time0 && isfinite(mg) && mg <= adv->tol_ll && !(want && stop)) { adv_forced(ADV_BEST, mg); go = want; }
+                else adv_hard(ADV_BEST, mg, "EM loop length", count, adv->n_em, 0);
+            }
+        }
+        if (!go) break;
         if (!time0) {
-            if (ll - bestll > 0) {                                                /* :1960-1963 */
+            int upd = ll - bestll > 0;
+            if (adv_on()) {
+                g_adv->n_checked[ADV_BEST]++;
+                const int want = adv->best_at[count] != 0;
+                if (want != upd) {
+                    const double mg = fabs(ll - bestll) / (fabs(ll) > 1e-300 ? fabs(ll) : 1e-300);
+                    if (isfinite(mg) && mg <= adv->tol_ll) { adv_forced(ADV_BEST, mg); upd = want; }
+                    else adv_hard(ADV_BEST, mg, "best result update", count, 0, 0);
+                }
+            }
+            if (upd && g_rec) { rec_w(7); rec_w(g_rec_start); rec_w(count); }
+            if (upd) {                                                            /* :1960-1963 */
                 bestll = ll; memcpy(bestadj, res1_adj, (size_t)k * SS);
                 memcpy(bestth, res1_th, sizeof(int32_t) * (size_t)k * E);
                 memcpy(bestprobs, probs, sizeof(double) * kc);
@@ -886,9 +1104,20 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
                 for (int c = 0; c < C; c++) gam[c] = post[i + (size_t)c * k];
                 orc_do_mean(D, E, C, pert, S, gam, Rk);                           /* nem :101-107 */
             }
+            const int adv_it = adv_on() && count < adv->n_em;                     /* this EM iteration is on the tape */
+            if (adv_it) { const size_t q = ((size_t)count * k + i) * 2;
+                          g_adv_rows = adv->move_rows + (size_t)adv->move_off[q] * S;
+                          g_adv_nmoves = (int)(adv->move_off[q + 1] - adv->move_off[q]); g_adv_W = Wfin0; }
+            else if (adv) adv->diverged = adv->diverged || count >= adv->n_em;
+            g_rec_iter = count; g_rec_comp = i; g_rec_restart = 0;
             orc_nem_greedy(Rk, E, S, NULL, a0, t0, &i0);                          /* j == 1: start0*0 :2042 */
+            g_rec_restart = 1;
             if (o->faithful_cost) orc_do_mean(D, E, C, pert, S, gam, Rk);
+            if (adv_it) { const size_t q = ((size_t)count * k + i) * 2 + 1;
+                          g_adv_rows = adv->move_rows + (size_t)adv->move_off[q] * S;
+                          g_adv_nmoves = (int)(adv->move_off[q + 1] - adv->move_off[q]); g_adv_W = Wfin1; }
             orc_nem_greedy(Rk, E, S, res1_adj + (size_t)i * SS, a1, t1, &i1);     /* j == 2: start0 :2040 */
+            g_adv_rows = NULL; g_adv_nmoves = 0; g_adv_W = NULL;
             nscored += i0.n_scored + i1.n_scored; ngreedy += i0.n_iter + i1.n_iter; nraw += i0.n_raw + i1.n_raw;
             ndec += i0.n_dec + i1.n_dec; ntight += i0.n_dec_tight + i1.n_dec_tight;
             if (i0.min_margin < minmargin) minmargin = i0.min_margin;
@@ -898,14 +1127,28 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
                 double mg = fabs(i1.max_trace - i0.max_trace) / (fabs(i0.max_trace) > 1e-300 ? fabs(i0.max_trace) : 1e-300);
                 if (mg < acceptmargin) acceptmargin = mg;
             }
+            if (adv_it && adv_on()) {
+                g_adv->n_checked[ADV_PICK]++;
+                const int want = adv->pick[(size_t)count * k + i] != 0;
+                if (want != pick1) {
+                    const double mg = fabs(i1.max_trace - i0.max_trace) / (fabs(i0.max_trace) > 1e-300 ? fabs(i0.max_trace) : 1e-300);
+                    if (mg <= adv->tol) { adv_forced(ADV_PICK, mg); pick1 = want; }
+                    else adv_hard(ADV_PICK, mg, "restart pick", count, i, 0);
+                }
+            }
+            if (g_rec) { rec_w(3); rec_w(g_rec_start); rec_w(count); rec_w(i); rec_w(pick1); }
             memcpy(res_adj + (size_t)i * SS, pick1 ? a1 : a0, SS);
             memcpy(res_th + (size_t)i * E, pick1 ? t1 : t0, sizeof(int32_t) * E);
+            if (adv_it && adv_on())
+                adv_theta(ADV_THETA, pick1 ? Wfin1 : Wfin0, E, S, res_th + (size_t)i * E,
+                          adv->theta + ((size_t)count * k + i) * E, count, i);
             for (int q = 0; q < SS; q++)                                          /* :2080-2081 */
                 edgechange += abs((int)res_adj[(size_t)i * SS + q] - (int)res1_adj[(size_t)i * SS + q]);
             if (have_res1_theta)                                                  /* :2082-2083 (NULL != x sums to 0) */
                 for (int e = 0; e < E; e++) thetachange += res_th[(size_t)i * E + e] != res1_th[(size_t)i * E + e];
             free(t0); free(t1);
         }
+        rec_theta(4, count, res_th, (size_t)k * E, S, 0);
         memcpy(res1_adj, res_adj, (size_t)k * SS);                                /* :2092 */
         memcpy(res1_th, res_th, sizeof(int32_t) * (size_t)k * E);
         have_res1_theta = 1;
@@ -921,7 +1164,18 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
             if (o->noise_mode == 1) newll = probsold_ll;                       /* "not greater" */
             else if (newll <= probsold_ll) newll = nextafter(probsold_ll, INFINITY);   /* "greater by one ulp" */
         }
-        if (newll > probsold_ll) { memcpy(probs, newp, sizeof(double) * kc); probs_ll = newll; }
+        int take_new = newll > probsold_ll;
+        if (adv_on() && count < adv->n_em) {
+            g_adv->n_checked[ADV_ACCEPT]++;
+            const int want = adv->accept[count] != 0;
+            if (want != take_new) {
+                const double mg = fabs(newll - probsold_ll) / (fabs(probsold_ll) > 1e-300 ? fabs(probsold_ll) : 1e-300);
+                if (isfinite(mg) && mg <= adv->tol_ll) { adv_forced(ADV_ACCEPT, mg); take_new = want; }
+                else adv_hard(ADV_ACCEPT, mg, "accept of the new E-step", count, 0, 0);
+            }
+        }
+        if (g_rec) { rec_w(5); rec_w(g_rec_start); rec_w(count); rec_w(take_new); rec_w(1); }
+        if (take_new) { memcpy(probs, newp, sizeof(double) * kc); probs_ll = newll; }
         else { memcpy(probs, probsold, sizeof(double) * kc); probs_ll = probsold_ll; }
         ll = probs_ll;                                                            /* :2111, evopen = 0 */
         double mwold[256];
@@ -936,7 +1190,18 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
         time0 = 0;
         if (o->max_iter_guard > 0 && count >= o->max_iter_guard) break;
     }
-    if (ll - bestll > 0) {                                                        /* :2144-2147 */
+    int upd_final = ll - bestll > 0;
+    if (adv_on()) {
+        g_adv->n_checked[ADV_BEST]++;
+        const int want = count <= adv->n_em && adv->best_at[count] != 0;
+        if (want != upd_final) {
+            const double mg = fabs(ll - bestll) / (fabs(ll) > 1e-300 ? fabs(ll) : 1e-300);
+            if (isfinite(mg) && mg <= adv->tol_ll) { adv_forced(ADV_BEST, mg); upd_final = want; }
+            else adv_hard(ADV_BEST, mg, "final best result update", count, 0, 0);
+        }
+    }
+    if (g_rec) { if (upd_final) { rec_w(7); rec_w(g_rec_start); rec_w(count); } rec_w(8); rec_w(g_rec_start); rec_w(count); }
+    if (upd_final) {                                                              /* :2144-2147 */
         bestll = ll; memcpy(bestadj, res1_adj, (size_t)k * SS);
         memcpy(bestth, res1_th, sizeof(int32_t) * (size_t)k * E);
         memcpy(bestprobs, probs, sizeof(double) * kc);
@@ -955,7 +1220,10 @@ void orc_em_start(const double *D, int E, int C, const int32_t *pert, int S, int
     info->n_dec = ndec; info->n_dec_tight = ntight;
     free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk); free(Rall);
     free(res1_adj); free(res_adj); free(res1_th); free(res_th); free(bestadj); free(bestth); free(bestprobs);
+    free(Wfin0); free(Wfin1);
+    g_adv = NULL; g_adv_probs = 0;
 }
+int orc_advice_size(void) { return (int)sizeof(orc_advice); }
 
 /* All starts (lapply / sfLapply over do_inits, R/mnems.r:2166-2170) and the winner (:2222-2230: `<=` so the
  * LAST maximal start wins).  Per-start outputs are laid out start-major.  nthreads > 1 runs starts in

@@ -1,6 +1,7 @@
-// Rcpp pass-through onto libmnemcu.so -- SOURCE ONLY in this repository: R, Rcpp and their headers are not
-// installable in the build image, so this file has never been compiled here.  It is deliberately a thin
-// marshalling layer: every line of numerical logic lives behind the C ABI (include/mnemcu.h) and is exercised
+// Rcpp pass-through onto libmnemcu.so.  R, Rcpp and their headers are not installable in the build image, so here the
+// file is compiled and EXECUTED against a small functional stand-in for <Rcpp.h> (tests/cabi/rcpp_stub/Rcpp.h,
+// driver tests/cabi/shim_check.cpp, run by tests/test_gpu_parity.py) -- that checks syntax, types and the marshalling,
+// not Rcpp itself.  It is deliberately a thin marshalling layer: every line of numerical logic lives behind the C ABI (include/mnemcu.h) and is exercised
 // through the same symbols by the Python host mirror (mnem_b200/) and its tests.
 //
 // Drop-in: add this file and include/mnemcu.h to the reference's src/, link with -lmnemcu (src/Makevars:
@@ -217,7 +218,9 @@ List mnemcu_getProbs(SEXP ctx, NumericMatrix probs, List res, NumericVector mw, 
 // ---- the EM phase of mnem(D, phi = init) (R/mnems.r:1884-2165, 2222-2230) ---------------------------------------
 // init: list over starts of lists over components of S x S matrices, exactly mnem()'s `phi` argument
 // [[Rcpp::export]]
-List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0, int max_trace = 256)
+// affinity: mnem(affinity =) 0 / 1 (R/mnems.r:1393-1417); mw: mnem(mw =) or NULL for rep(1, k)/k (:1771-1773)
+List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0, int max_trace = 256, int affinity = 0,
+               Nullable<NumericVector> mw = R_NilValue)
 {
     mnemcu_ctx *cx = ctx_of(ctx);
     int E, C, S;
@@ -230,12 +233,19 @@ List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0
             std::copy(g.begin(), g.end(), phi.begin() + ((size_t)s * k + i) * S * S);
         }
     std::vector<int32_t> theta((size_t)starts * k * E), nit(starts);
-    std::vector<double> probs((size_t)starts * k * C), mw((size_t)starts * k), ll(starts);
+    std::vector<double> probs((size_t)starts * k * C), mwout((size_t)starts * k), ll(starts);
     std::vector<double> lls((size_t)starts * max_trace), pe(lls.size()), te(lls.size()), me(lls.size());
     int32_t best = -1;
-    mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr, 0};
+    std::vector<double> mw0;
+    if (mw.isNotNull()) {
+        NumericVector m(mw);
+        if ((int)m.size() != k) stop("mw must hold one weight per component");
+        mw0.assign(m.begin(), m.end());
+    }
+    mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr, affinity, nullptr, 0, 0,
+                        mw0.empty() ? nullptr : mw0.data()};
     mnemcu_em_stats st;
-    chk(mnemcu_em_run(cx, starts, k, phi.data(), &o, adj.data(), theta.data(), probs.data(), mw.data(), ll.data(),
+    chk(mnemcu_em_run(cx, starts, k, phi.data(), &o, adj.data(), theta.data(), probs.data(), mwout.data(), ll.data(),
                       nit.data(), lls.data(), pe.data(), te.data(), me.data(), &best, &st));
     List limits(starts);
     for (int s = 0; s < starts; ++s) {
@@ -252,7 +262,7 @@ List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0
         limits[s] = List::create(
             _["probs"] = List::create(_["probs"] = P), _["res"] = res, _["ll"] = ll[s],
             _["lls"] = NumericVector(lls.begin() + (size_t)s * max_trace, lls.begin() + (size_t)s * max_trace + n),
-            _["mw"] = NumericVector(mw.begin() + (size_t)s * k, mw.begin() + (size_t)(s + 1) * k),
+            _["mw"] = NumericVector(mwout.begin() + (size_t)s * k, mwout.begin() + (size_t)(s + 1) * k),
             _["phievo"] = NumericVector(pe.begin() + (size_t)s * max_trace, pe.begin() + (size_t)s * max_trace + n),
             _["thetaevo"] = NumericVector(te.begin() + (size_t)s * max_trace, te.begin() + (size_t)s * max_trace + n),
             _["mwevo"] = NumericVector(me.begin() + (size_t)s * max_trace, me.begin() + (size_t)s * max_trace + n));

@@ -102,10 +102,10 @@ def test_struct_layouts_agree_between_c_and_ctypes():
     o = [int(x) for x in out["em_opts"].split()]
     f = _lib.EmOpts
     assert o == [C.sizeof(f), f.complete.offset, f.logtype.offset, f.batch.offset, f.max_trace.offset, f.max_iter_guard.offset,
-                 f.next_start.offset, f.next_start_user.offset, f.affinity.offset]
+                 f.next_start.offset, f.next_start_user.offset, f.affinity.offset, f.tape.offset, f.tape_cap.offset, f.probs_mode.offset, f.mw.offset]
     s = [int(x) for x in out["em_stats"].split()]
     g = _lib.EmStats
-    assert s == [C.sizeof(g), g.em_iters.offset, g.ms_total.offset, g.estep_bytes.offset]
+    assert s == [C.sizeof(g), g.em_iters.offset, g.ms_total.offset, g.estep_bytes.offset, g.tape_words.offset]
     assert int(out["version"]) == mb.load_library().mnemcu_version()
 
 
@@ -115,3 +115,14 @@ def test_cpp_consumer_sees_clean_errors_without_a_device():
     r = _cabi("nogpu")
     assert r.returncode == 0, r.stdout + r.stderr
     assert "has_gpu" in r.stdout or ("ctx_create rc=2" in r.stdout and "get_ll rc=2" in r.stdout and "null_pert rc=1" in r.stdout)
+
+
+def test_rcpp_shim_compiles_against_the_stub():
+    """rshim/mnemcu_shim.cpp builds (g++ -Wall -Wextra) against tests/cabi/rcpp_stub/Rcpp.h and links libmnemcu.so."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cabi", "shim_check")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build()
+    r = subprocess.run([exe, "syntax"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr

@@ -552,3 +552,59 @@ def test_cpp_consumer_fit_matches_the_python_binding(tmp_path):
     for v in list(adj) + list(th):
         dig = ((dig ^ int(v)) * 1099511628211) % (1 << 64)
     assert dig == digest
+
+
+def test_rcpp_shim_fit_matches_the_python_binding(tmp_path):
+    """rshim/mnemcu_shim.cpp -- the Rcpp glue of INTEGRATION.md -- compiled against the functional Rcpp stand-in
+    (tests/cabi/rcpp_stub/Rcpp.h) and driven like rshim/mnem_cuda.R drives it: mnemcu_context + mnemcu_em on mnem()'s
+    `phi` list.  Winner, likelihood, iteration count and graphs equal the ctypes path; the legacy transClose_W symbol and
+    the external-pointer finalizer work."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "cabi", "shim_check")
+    if not os.path.exists(exe):
+        import __graft_entry__ as ge
+        ge.build()
+    sim = simdata.make_config(dict(S=5, Egenes=6, C=1500, mw=[0.4, 0.6], k=2, starts=3, uninform=1), seed=51)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(5, 2, 3, seed=6)
+    path = str(tmp_path / "problem.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([sim["E"], sim["C"], 5, 2, 3, 0], dtype=np.int32).tobytes())
+        f.write(np.asfortranarray(D).tobytes(order="F"))
+        f.write(np.ascontiguousarray(sim["pert"], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(np.transpose(init.reshape(6, 5, 5), (0, 2, 1))).astype(np.uint8).tobytes())
+    r = subprocess.run([exe, "fit", path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    tok = lines[0].split()
+    best, ll, iters, digest = int(tok[1]), float(tok[3]), int(tok[5]), int(tok[7])
+    fit = mb.mnem(D, sim["pert"], phi=init)
+    assert best == fit["best_start"] and ll == fit["ll"] and iters == int(fit["n_iter"].sum())
+    dig = 1469598103934665603
+    adj = np.ascontiguousarray(np.transpose(fit["limits"][best]["adj"], (0, 2, 1))).astype(np.uint8).ravel()
+    th = fit["limits"][best]["theta"].astype(np.uint32).ravel()
+    for v in list(adj) + list(th):
+        dig = ((dig ^ int(v)) * 1099511628211) % (1 << 64)
+    assert dig == digest
+    assert lines[1] == "closure_1_3 1" and lines[2] == "ctx_released 1"
+
+
+def test_user_mixture_weights_and_winner_probs():
+    """mnem(mw =) (R/mnems.r:1771-1773: the initial mixture weights of every start) against the oracle, and
+    probs = 'winner' (one k x C block, the best start's) against the per-start layout."""
+    sim = simdata.make_config(dict(S=6, Egenes=8, C=3000, mw=[0.3, 0.7], k=2, starts=4, uninform=2), seed=77)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(6, 2, 4, seed=9)
+    mw0 = np.array([0.85, 0.15])
+    ref = orc.mnem_em(D, sim["pert"], 6, init, mw=mw0)
+    with mb.Context(D, sim["pert"]) as cx:
+        r = mb.em_run(cx, init, mw=mw0)
+        rw = mb.em_run(cx, init, mw=mw0, probs="winner")
+        r0 = mb.em_run(cx, init)
+    assert ref["min_margin"].min() > 1e-13
+    assert np.array_equal(r["adj"], ref["adj"]) and np.array_equal(r["theta"], ref["theta"])
+    assert np.array_equal(r["n_iter"], ref["n_iter"])
+    assert np.max(np.abs(r["ll"] - ref["ll"]) / np.abs(ref["ll"])) <= 1e-9
+    assert not np.array_equal(r0["ll"], r["ll"])                       # the weights do change the fits
+    assert rw["best"] == r["best"] and rw["probs"].shape[0] == 1
+    assert np.array_equal(rw["probs"][0], r["probs"][r["best"]])

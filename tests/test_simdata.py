@@ -17,7 +17,8 @@ def test_generator_statistics():
     sim = simdata.make_config(dict(S=8, Egenes=6, C=4000, mw=[0.5, 0.5], k=2, starts=1, uninform=0), seed=2)
     D = simdata.host_data(sim)
     noise = D - np.sign(np.round(D * 65536) / 65536 - 0) * 0  # noqa: F841  (values are multiples of 2^-16)
-    assert np.array_equal(D * 65536, np.round(D * 65536))
+    # full-precision values: hardly any is a multiple of 2^-16 (sums over them are order-dependent, as with real data)
+    assert np.mean(D * 65536 == np.round(D * 65536)) < 1e-3
     comp, pert, th, phi = sim["comp"].astype(int), sim["pert"] - 1, sim["theta_true"], sim["phi_true"]
     b = phi[comp[None, :], pert[None, :], th[comp].T - 1]
     res = D - np.where(b != 0, 1.0, -1.0)
