@@ -72,3 +72,77 @@ def gather_winner(local_ids, local_lls, n_starts, device=None):
     if not (got[1] == 1.0).all():
         raise RuntimeError("starts were not covered exactly once across ranks")
     return pick_winner(got[0]), got[0]
+
+
+def mnemk_sharded(cx, ks, starts, seed=0, phi=None, complete=False, logtype=2, batch=0, device=None, fit_fn=None, k1_fn=None,
+                  ic_fn=None):
+    """mnemk() (R/mnems.r:1560-1574: fit every k, keep the smallest information criterion) with the (k, start) fits spread
+    over all ranks.  Every k has its own shared queue of starts (StartQueue); rank r walks the k's in an order rotated by
+    r and drains whatever is left of each queue, so with few starts per k (the perturb-seq config has 3) different ranks
+    work on different k's at the same time and no GPU waits for a whole k to finish.  Exchanges: one 16-byte-per-start
+    reduction per k (gather_winner) and one all_gather_object of the per-k winners' graphs -- no data-path collective.
+
+    cx: this rank's Context.  phi: optional {k: [starts, k, S, S]} initial graphs (default: sample_init(seed), the same on
+    every rank).  fit_fn(k, init, next_start) / k1_fn() / ic_fn(fit, n_cells) replace the device calls in CPU tests.
+    Returns dict(k, ics, lls, fits = {k: winner summary}, best = fits[k], taken = {k: starts this rank fitted}); `probs`
+    of a winner is present only on the rank that fitted it (its `owner`)."""
+    import torch.distributed as dist
+
+    from . import api
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    rank = dist.get_rank() if on else 0
+    world = dist.get_world_size() if on else 1
+    ks = [int(k) for k in ks]
+    queues = {k: StartQueue(starts if k > 1 else 1) for k in ks}            # constructed in the same order on every rank
+    if fit_fn is None:
+        def fit_fn(k, init, q):
+            return api.em_run(cx, init, complete=complete, logtype=logtype, batch=batch, next_start=q, probs="winner")
+    if k1_fn is None:
+        def k1_fn():
+            return api._mnem_k1(cx, np.zeros((cx.S, cx.S), dtype=np.uint8), complete, logtype)
+    local = {}
+    for i in range(len(ks)):
+        k = ks[(i + rank) % len(ks)]
+        q = queues[k]
+        if k == 1:
+            if q() == 0:
+                f = k1_fn()
+                local[k] = dict(my=[0], ll=np.array([f["ll"]]), adj=np.asarray(f["comp"][0]["phi"])[None, None],
+                                theta=np.asarray(f["comp"][0]["theta"])[None, None], mw=np.ones((1, 1)), probs=f["probs"][None],
+                                best=0)
+            else:
+                local[k] = dict(my=[], ll=np.zeros(0))
+            continue
+        init = np.asarray(phi[k]) if phi is not None else api.sample_init(cx.S, k, starts, seed)
+        r = fit_fn(k, init, q)
+        my = sorted(q.taken)
+        local[k] = dict(my=my, ll=np.asarray(r["ll"])[my], adj=r["adj"], theta=r["theta"], mw=r["mw"], probs=r.get("probs"),
+                        best=r["best"])
+    fits = {}
+    for k in ks:
+        n = starts if k > 1 else 1
+        L = local[k]
+        win, lls = gather_winner(L["my"], L["ll"], n, device=device)
+        mine = win in L["my"]
+        summ = None
+        if mine:
+            p = L.get("probs")
+            summ = dict(k=k, owner=rank, start=int(win), ll=float(lls[win]), adj=np.asarray(L["adj"][win]),
+                        theta=np.asarray(L["theta"][win]), mw=np.asarray(L["mw"][win]), lls=[float(x) for x in lls])
+            if p is not None and L["best"] == win:
+                summ["probs"] = p[0] if len(p) == 1 else p[win]
+        if on:
+            box = [None] * world
+            dist.all_gather_object(box, None if summ is None else {q_: v for q_, v in summ.items() if q_ != "probs"})
+            got = next(b for b in box if b is not None)
+            fits[k] = summ if mine else got
+        else:
+            fits[k] = summ
+    ics, lls = {}, {}
+    for k in ks:
+        f = fits[k]
+        comp = [dict(phi=f["adj"][i], theta=f["theta"][i]) for i in range(k)]
+        ics[k] = float(ic_fn(dict(comp=comp, ll=f["ll"]), cx.C) if ic_fn else api.getIC(dict(comp=comp, ll=f["ll"]), cx.C, logtype=logtype))
+        lls[k] = f["ll"]
+    kb = min(ics, key=lambda q_: ics[q_])
+    return dict(k=kb, ics=ics, lls=lls, fits=fits, best=fits[kb], taken={k: list(local[k]["my"]) for k in ks})

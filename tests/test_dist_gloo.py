@@ -130,3 +130,76 @@ def test_start_queue_without_process_group_is_a_local_counter():
     q = mdist.StartQueue(3)
     assert [q(), q(), q(), q(), q()] == [0, 1, 2, -1, -1]
     assert q.taken == [0, 1, 2]
+
+
+# mnemk() with the (k, start) fits spread over the ranks: every k has its own queue, ranks walk the k's in rotated order
+WORKER_MNEMK = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import oracle as orc
+from mnem_b200 import simdata, dist as mdist
+world = int(sys.argv[2])
+if world > 1:
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=world)
+S, starts = 4, 3
+sim = simdata.make_config(dict(S=S, Egenes=3, C=400, mw=[0.5, 0.5], k=2, starts=starts, uninform=0), seed=5)
+D = simdata.host_data(sim)
+class Cx:                                   # what mnemk_sharded reads from a Context
+    S, C, E = S, sim["C"], sim["E"]
+def fit_fn(k, init, q):                     # the CPU oracle stands in for the per-rank device fit
+    ll = np.full(starts, -np.inf); adj = np.zeros((starts, k, S, S), dtype=np.uint8)
+    theta = np.zeros((starts, k, sim["E"]), dtype=np.int32); mw = np.zeros((starts, k)); best = -1
+    while True:
+        s = q()
+        if s < 0:
+            break
+        r = orc.mnem_em(D, sim["pert"], S, init[s:s + 1])
+        ll[s], adj[s], theta[s], mw[s] = r["ll"][0], r["adj"][0], r["theta"][0], r["mw"][0]
+        if best < 0 or ll[s] > ll[best] or (ll[s] == ll[best] and s > best):
+            best = s
+    return dict(ll=ll, adj=adj, theta=theta, mw=mw, best=best, probs=None)
+def k1_fn():
+    R = orc.do_mean(D, sim["pert"], S)
+    f = orc.nem_greedy(R, None)
+    g = orc.get_probs(D, sim["pert"], S, f["adj"][None], f["theta"][None], np.zeros((1, sim["C"])), np.ones(1))
+    return dict(ll=g["ll"], comp=[dict(phi=f["adj"], theta=f["theta"])], probs=g["probs"])
+def ic_fn(x, n):                            # getIC(degree = 4), R/mnems.r:1477-1529
+    fpar = 0
+    for c in x["comp"]:
+        t = orc.mytc(c["phi"]).copy(); np.fill_diagonal(t, 0); fpar += int((t != 0).sum())
+    k = len(x["comp"])
+    fpar += k * len(x["comp"][0]["theta"]) + k - 1
+    return np.log(n) * fpar - 2 * x["ll"] * np.log(2)
+if world > 1:
+    dist.barrier()                          # start together, like ranks that have just built their contexts
+r = mdist.mnemk_sharded(Cx, [1, 2, 3], starts, seed=11, fit_fn=fit_fn, k1_fn=k1_fn, ic_fn=ic_fn)
+print(json.dumps(dict(k=r["k"], ics={str(q): v for q, v in r["ics"].items()}, lls={str(q): v for q, v in r["lls"].items()},
+                      owners={str(q): r["fits"][q]["owner"] for q in r["fits"]}, n_fitted=sum(len(v) for v in r["taken"].values()),
+                      adj=[r["fits"][q]["adj"].astype(int).tolist() for q in (1, 2, 3)])))
+if world > 1:
+    dist.destroy_process_group()
+"""
+
+
+def test_two_rank_mnemk_picks_the_same_k_and_fits_as_one_process():
+    import json
+    port = _free_port()
+    src = WORKER_MNEMK % dict(root=ROOT, port=port)
+
+    def run(world):
+        procs = [subprocess.Popen([sys.executable, "-c", src, str(r), str(world)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.PIPE, text=True) for r in range(world)]
+        outs = []
+        for p in procs:
+            o, e = p.communicate(timeout=600)
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+        return outs
+    one = run(1)[0]
+    two = run(2)
+    for o in two:
+        assert o["k"] == one["k"] and o["ics"] == one["ics"] and o["lls"] == one["lls"] and o["adj"] == one["adj"]
+    assert two[0]["owners"] == two[1]["owners"]
+    assert two[0]["n_fitted"] + two[1]["n_fitted"] == 1 + 3 + 3 and min(o["n_fitted"] for o in two) >= 1   # spread

@@ -590,21 +590,24 @@ def test_rcpp_shim_fit_matches_the_python_binding(tmp_path):
 
 
 def test_user_mixture_weights_and_winner_probs():
-    """mnem(mw =) (R/mnems.r:1771-1773: the initial mixture weights of every start) against the oracle, and
+    """mnem(mw =) (R/mnems.r:1771-1773: the initial mixture weights of every start) replayed through the oracle, and
     probs = 'winner' (one k x C block, the best start's) against the per-start layout."""
     sim = simdata.make_config(dict(S=6, Egenes=8, C=3000, mw=[0.3, 0.7], k=2, starts=4, uninform=2), seed=77)
     D = simdata.host_data(sim)
     init = simdata.init_phi(6, 2, 4, seed=9)
     mw0 = np.array([0.85, 0.15])
-    ref = orc.mnem_em(D, sim["pert"], 6, init, mw=mw0)
     with mb.Context(D, sim["pert"]) as cx:
-        r = mb.em_run(cx, init, mw=mw0)
+        r = mb.em_run(cx, init, mw=mw0, tape=True)
         rw = mb.em_run(cx, init, mw=mw0, probs="winner")
         r0 = mb.em_run(cx, init)
-    assert ref["min_margin"].min() > 1e-13
-    assert np.array_equal(r["adj"], ref["adj"]) and np.array_equal(r["theta"], ref["theta"])
-    assert np.array_equal(r["n_iter"], ref["n_iter"])
-    assert np.max(np.abs(r["ll"] - ref["ll"]) / np.abs(ref["ll"])) <= 1e-9
+    for s in range(4):
+        o = orc.replay_start(D, sim["pert"], 6, init[s], r["tape"][s], mw=mw0)
+        assert not o["diverged"], o["first_hard"]
+        assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(r["theta"][s], o["theta"])
+        assert r["n_iter"][s] == o["n_iter"]
+        assert abs(r["ll"][s] - o["ll"]) <= 1e-9 * abs(o["ll"])
+        assert np.allclose(r["mw"][s], o["mw"], rtol=1e-9, atol=0)
     assert not np.array_equal(r0["ll"], r["ll"])                       # the weights do change the fits
     assert rw["best"] == r["best"] and rw["probs"].shape[0] == 1
     assert np.array_equal(rw["probs"][0], r["probs"][r["best"]])
+    assert np.array_equal(rw["adj"], r["adj"]) and np.array_equal(rw["ll"], r["ll"])      # the tape does not change a fit
