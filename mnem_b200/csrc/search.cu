@@ -52,7 +52,8 @@ struct SearchDev {
     int32_t *live = nullptr;          // searches still climbing
     int32_t *tiles_done = nullptr;    // [q] tiles of the current iteration already scored
     int32_t *stage = nullptr;         // [q] 0: the pending scores are the initial score of closure(start); 1: neighbours
-    unsigned long long *busy_ns = nullptr;   // [0] ns the CTAs spent on tasks, [1] ns they were resident (utilisation of the loop)
+    unsigned long long *busy_ns = nullptr;   // [0] ns the CTAs spent on tasks, [1] ns they were resident (utilisation of the loop),
+                                             // [2] ns in finish steps, [3] ns in generation + publishing, [4] iterations closed
     uint32_t *tape = nullptr;         // decision tape (audit runs only): [q][hard_cap][32] rows of the graph after every accepted move
 };
 
@@ -73,6 +74,7 @@ struct SearchBatch {
     DevBuf<uint32_t> tape;            // see SearchDev::tape; allocated by search_enable_tape
     unsigned long long *h_busy = nullptr;     // pinned copy of busy_ns
     double busy_acc = 0.0, resident_acc = 0.0;   // accumulated over the search_run calls of this workspace
+    double fin_acc = 0.0, gen_acc = 0.0, closed_acc = 0.0, calls_acc = 0.0;
     DevBuf<unsigned> qctl;
     unsigned ring_cap = 0;
     // Host-driven loop only.  Chains: the searches are dealt round-robin (by pair) to kChains groups that iterate
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
     __shared__ unsigned long long s_task;
     __shared__ int s_last;
     const int tid = threadIdx.x;
-    unsigned long long t_begin = 0ull, t_task = 0ull, busy = 0ull;
+    unsigned long long t_begin = 0ull, t_task = 0ull, busy = 0ull, t_fin = 0ull, t_gen = 0ull, n_closed = 0ull;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     while (true) {
         if (tid == 0) {
@@ -934,11 +936,14 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
         __syncthreads();
         if (!s_last) continue;
         // ---- this CTA closes the iteration of search q ----
+        unsigned long long tp0 = 0ull, tp1 = 0ull, tp2 = 0ull;
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
         const int mode = __ldcg(d.stage + q);
         finish_body<kDictThreads, true>(d, fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes), q, mode, d.ntiles, d.partial,
                                         nullptr);
         const int go = fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes).flag[0];
         __syncthreads();
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
         if (go) {
             gen_body<kDictThreads, true>(d, gen_smem_at(s_raw), q, 1);
             __threadfence();
@@ -956,6 +961,10 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
             __threadfence();
             if (atomicSub(d.live, 1) == 1) { __threadfence(); *reinterpret_cast<volatile unsigned *>(&d.qctl[3]) = 1u; }
         }
+        if (tid == 0) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp2));
+            t_fin += tp1 - tp0; t_gen += tp2 - tp1; ++n_closed;
+        }
         __syncthreads();
     }
     if (tid == 0) {
@@ -963,6 +972,9 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         atomicAdd(&d.busy_ns[0], busy);
         atomicAdd(&d.busy_ns[1], now - t_begin);
+        atomicAdd(&d.busy_ns[2], t_fin);
+        atomicAdd(&d.busy_ns[3], t_gen);
+        atomicAdd(&d.busy_ns[4], n_closed);
     }
 }
 __global__ void search_init_kernel(int n, int S, const uint32_t *__restrict__ start_rows, uint32_t *__restrict__ Prow,
@@ -1207,8 +1219,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->rowm.alloc((size_t)nmax * 32, true)); MN_TRY(sb->chain_v.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->chain_start.alloc((size_t)nmax * 33, true)); MN_TRY(sb->nchain.alloc(nmax, true));
         MN_TRY(sb->ring.alloc(sb->ring_cap)); MN_TRY(sb->qctl.alloc(4, true)); MN_TRY(sb->live.alloc(1, true));
-        MN_TRY(sb->tiles_done.alloc(nmax, true)); MN_TRY(sb->stage.alloc(nmax, true)); MN_TRY(sb->busy_ns.alloc(2, true));
-        MN_CU(cudaMallocHost((void **)&sb->h_busy, 2 * sizeof(unsigned long long)));
+        MN_TRY(sb->tiles_done.alloc(nmax, true)); MN_TRY(sb->stage.alloc(nmax, true)); MN_TRY(sb->busy_ns.alloc(8, true));
+        MN_CU(cudaMallocHost((void **)&sb->h_busy, 8 * sizeof(unsigned long long)));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
         MN_CU(cudaMallocHost((void **)&sb->h_n_active, (2 * kChains + 1) * sizeof(int32_t)));
         for (int i = 0; i <= 2 * kChains; ++i) sb->h_n_active[i] = 0;
@@ -1232,6 +1244,11 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
 void search_destroy(SearchBatch *sb)
 {
     if (!sb) return;
+    if (getenv("MNEMCU_SEARCH_STATS") && sb->calls_acc > 0)        // phase times of the device-resident loop (diagnostic)
+        fprintf(stderr, "search loop: %.0f launches, %.0f iterations closed, CTA time busy %.1f ms of %.1f ms resident (sum over "
+                        "CTAs); per closed iteration: finish %.2f us, generate + publish %.2f us\n", sb->calls_acc, sb->closed_acc,
+                sb->busy_acc * 1e-6, sb->resident_acc * 1e-6, sb->fin_acc / std::max(1.0, sb->closed_acc) * 1e-3,
+                sb->gen_acc / std::max(1.0, sb->closed_acc) * 1e-3);
     if (sb->h_n_active) cudaFreeHost(sb->h_n_active);
     if (sb->h_busy) cudaFreeHost(sb->h_busy);
     for (int h = 0; h < kChains; ++h) {
@@ -1255,7 +1272,7 @@ static int search_check_flags(SearchBatch *sb, int32_t flags)
 static int search_loop_device(SearchBatch *sb, int n, cudaStream_t st)
 {
     const SearchDev d = sb->dev();
-    MN_CU(cudaMemsetAsync(sb->busy_ns.p, 0, 2 * sizeof(unsigned long long), st));
+    MN_CU(cudaMemsetAsync(sb->busy_ns.p, 0, 8 * sizeof(unsigned long long), st));
     MN_LAUNCH(search_seed_kernel, 1, 32, 0, st, d, n);
     const int grid = std::max(1, std::min(sb->sm_count, n * d.ntiles));
 #define MN_PERS(SPV) MN_LAUNCH(search_persistent_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, d)
@@ -1263,10 +1280,12 @@ static int search_loop_device(SearchBatch *sb, int n, cudaStream_t st)
 #undef MN_PERS
     int32_t *h_over = sb->h_n_active + 2 * kChains;
     MN_CU(cudaMemcpyAsync(h_over, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MN_CU(cudaMemcpyAsync(sb->h_busy, sb->busy_ns.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    MN_CU(cudaMemcpyAsync(sb->h_busy, sb->busy_ns.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     MN_CU(cudaStreamSynchronize(st));
     sb->busy_acc += (double)sb->h_busy[0];
     sb->resident_acc += (double)sb->h_busy[1];
+    sb->fin_acc += (double)sb->h_busy[2]; sb->gen_acc += (double)sb->h_busy[3]; sb->closed_acc += (double)sb->h_busy[4];
+    sb->calls_acc += 1.0;
     return search_check_flags(sb, *h_over);
 }
 

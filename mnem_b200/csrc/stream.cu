@@ -125,16 +125,20 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
     // warp with 60 accumulators needs 167 registers -> 12 warps per SM and 4.58 ms per pass; two warps of 15: 4.26 ms.)
     const int groups = (M + 19) / 20;
     const int MT = (M + groups - 1) / groups;
-    // Few blocks (small C): split the E-gene range over up to 8 warps so that every SM still has loads in flight.
+    // Few blocks (small C): split the E-gene range over up to 4 warps so that every SM still has loads in flight.  The split
+    // changes the ORDER of a cell's sum (ranges are summed separately and then added in ascending order), so it must depend
+    // on the shape of the data only -- never on M -- or a start's fit would depend on how many starts share its passes.
+    // (Found with full-precision synthetic data: with inputs that are multiples of 2^-16 every order gives the same sum.)
+    // The heuristics below therefore assume the nominal 20 pairs in one group whatever M is.
     int esplit = 1;
-    const long warps = (long)cx->nblk * groups;
-    while (esplit * groups < 8 && warps * esplit < 16L * cx->sm_count && cx->E / (esplit * 2) >= 64) esplit *= 2;
-    // Register-limited residency (about 45 + 4 MT registers per thread): a grid of between one and ~2.5 waves leaves a
+    const long warps = (long)cx->nblk;
+    while (esplit < 4 && warps * esplit < 16L * cx->sm_count && cx->E / (esplit * 2) >= 64) esplit *= 2;
+    // Register-limited residency (about 45 + 4 * 20 registers per thread): a grid of between one and ~2.5 waves leaves a
     // long tail, so split once more (cfg3 shape, 20 pairs: 1.32 waves at 2 warps per block, 0.189 -> 0.164 ms at 4).
     {
-        const long resident = (long)cx->sm_count * std::min(64, 65536 / ((45 + 4 * MT) * 32));
+        const long resident = (long)cx->sm_count * std::min(64, 65536 / ((45 + 4 * 20) * 32));
         const double waves = (double)(warps * esplit) / (double)resident;
-        if (waves > 1.0 && waves < 2.5 && esplit * groups < 8 && cx->E / (esplit * 2) >= 64) esplit *= 2;
+        if (waves > 1.0 && waves < 2.5 && esplit < 4 && cx->E / (esplit * 2) >= 64) esplit *= 2;
     }
     switch (MT) {
 #define MN_CASE(v) case v: return launch_estep_t<v>(cx, maskT, M, out, esplit, st);

@@ -245,6 +245,7 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
             max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None):
     """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
+    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None       # mnem(mw =), R/mnems.r:1771-1773
     D = _f(D)
     E, Cn = D.shape
     pert = np.ascontiguousarray(pert, dtype=np.int32)
@@ -257,7 +258,6 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     mw = np.zeros((starts, k))
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     infos = (EmInfo * starts)()
-    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
     o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode), int(affinity),
                _d(mw0) if mw0 is not None else None)
     best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
@@ -303,9 +303,10 @@ class Advice(C.Structure):
                 ("first_hard", C.c_char * 256)]
 
 
-def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", start=0, cap=1 << 24):
+def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", start=0, cap=1 << 24, mw=None):
     """One EM start fitted by the oracle while it writes a decision tape of its own (device record format).  Returns the
     int32 words (parse with mnem_b200.api.parse_tape) and the fit's n_iter / ll."""
+    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
     D = _f(D)
     E, Cn = D.shape
     pert = np.ascontiguousarray(pert, dtype=np.int32)
@@ -323,7 +324,7 @@ def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", st
         mw = np.zeros(k)
         tr = [np.zeros(256) for _ in range(4)]
         info = EmInfo()
-        o = EmOpts(256, int(bool(complete)), logtype, 0, 0, 0, 0)
+        o = EmOpts(256, int(bool(complete)), logtype, 0, 0, 0, 0, _d(mw0) if mw0 is not None else None)
         L_.orc_em_start(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), _u8(adj), _i32(th), _d(L), _d(mw), _d(tr[0]),
                         _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
         n = int(L_.orc_recorder_words())
@@ -343,6 +344,7 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     less than `tol` (scores, weights; relative) / `tol_ll` (log-likelihoods) -- see orc_advice in mnem_oracle.c.
     Returns the fit (like mnem_em, one start) plus report = {kind: dict(checked, forced, hard, max_forced, min_hard)},
     diverged and first_hard."""
+    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
     D = _f(D)
     E, Cn = D.shape
     pert = np.ascontiguousarray(pert, dtype=np.int32)
@@ -382,7 +384,6 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     mw = np.zeros(k)
     tr = [np.zeros(max_trace) for _ in range(4)]
     info = EmInfo()
-    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
     o = EmOpts(max_trace, int(bool(complete)), logtype, 0, 0, 0, int(affinity), _d(mw0) if mw0 is not None else None)
     lib(acc).orc_em_start_advised(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), C.byref(adv), _u8(adj), _i32(th),
                                   _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
