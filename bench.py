@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 # (profiles/r2_bench_cfg*.json, "em_iters_per_step" / starts); the device's iteration counts are those of the oracle
 # on every start the oracle has replayed (tests/test_gpu_scale_parity.py: n_iter bit-exact).  bench.py's own
 # `cpu_baseline` leg (N = 1) does not use the table: it takes the mean of the fit it has just timed.
-MEAN_EM_ITERS = {1: 4.0, 2: 6.0, 3: 10.0, 4: 10.0, 5: 12.96}
+MEAN_EM_ITERS = {1: 4.0, 2: 6.0, 3: 10.0, 4: 10.0, 5: 13.07}
 
 
 def parse():
@@ -191,7 +191,7 @@ def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0):
 
 def bench_config(args, sim, name):
     """The `config` object of the JSON line: the same for both arms."""
-    return {"workload": name, "batch": args.batch or max(1, 20 // sim["k"]),
+    return {"workload": name, "batch": args.batch or max(1, min(30 // sim["k"], sim["starts"])),
             "l2": "inputs larger than L2 (D = %.1f GB per layout)" % (8e-9 * sim["E"] * sim["C"]),
             "candidate_count": "graphs generated and scored, before unique()"}
 

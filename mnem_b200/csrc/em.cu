@@ -539,7 +539,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     MN_ARG(starts >= 1 && k >= 2 && k <= 20, "starts must be positive and k in 2..20 (k = 1 is nem() + getProbs)");
     MN_ARG(opts->max_trace >= 1 || !lls, "max_trace must be positive");
     const int E = cx->E, C = cx->C, S = cx->S;
-    int B = opts->batch > 0 ? opts->batch : std::max(1, 20 / k);
+    // EM starts per pass over D.  Default: as many as give k * B <= 30 pairs.  Up to 20 pairs the two streaming kernels are
+    // HBM-bound (E-step 0.89 of the measured copy bandwidth at 20), beyond that they are bound by the FP64 rate, but a pass
+    // still gets cheaper per start (cfg5: (2.81 + 3.43) / 4 = 1.56 ms per start and tick at B = 4, (3.94 + 4.47) / 6 =
+    // 1.40 ms at B = 6) and the device-resident search loop has more searches to fill the SMs with.
+    int B = opts->batch > 0 ? opts->batch : std::max(1, 30 / k);
     B = std::min(B, std::min(starts, 32 / k));
     MN_ARG(opts->affinity == 0 || opts->affinity == 1, "affinity must be 0 or 1");
     MN_ARG(!(opts->affinity && opts->complete), "affinity = 1 with complete = TRUE is an error in the reference too");

@@ -74,7 +74,7 @@ struct SearchBatch {
     DevBuf<uint32_t> tape;            // see SearchDev::tape; allocated by search_enable_tape
     unsigned long long *h_busy = nullptr;     // pinned copy of busy_ns
     double busy_acc = 0.0, resident_acc = 0.0;   // accumulated over the search_run calls of this workspace
-    double fin_acc = 0.0, gen_acc = 0.0, closed_acc = 0.0, calls_acc = 0.0;
+    double fin_acc = 0.0, gen_acc = 0.0, closed_acc = 0.0, calls_acc = 0.0, ph_acc[16] = {};
     DevBuf<unsigned> qctl;
     unsigned ring_cap = 0;
     // Host-driven loop only.  Chains: the searches are dealt round-robin (by pair) to kChains groups that iterate
@@ -135,6 +135,11 @@ struct GenSmem {
     uint16_t *ids;      // [kDictHash]
     uint16_t *pair;     // [32 * 32]
     int *warp;          // [NT / 32]
+    // optional staging (device-resident loop: the CTA has the whole scoring buffer to itself while it generates): hash
+    // slots and changed-column sets of the reversal / deletion candidates, so that turning slots into dense ids needs no
+    // read-back of what this CTA has just written to global memory (two dependent L2 round trips per entry otherwise)
+    uint16_t *st_ci = nullptr;   // [rest][32]
+    uint32_t *st_J = nullptr;    // [rest]
 };
 constexpr size_t kGenSmemBytes = kDictHash * 4 + kDictHash * 2 + 1024 * 2 + 64 * 4;
 
@@ -148,8 +153,20 @@ __device__ __forceinline__ GenSmem gen_smem_at(unsigned char *base)
     return g;
 }
 
+// diagnostic phase clock of the closing path (device-resident loop): thread 0 adds the time since the last mark to ph[i];
+// ph[15] holds the last time stamp.  ph == nullptr: nothing is measured.
+__device__ __forceinline__ void ph_mark(unsigned long long *ph, int i)
+{
+    if (ph && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        ph[i] += now - ph[15];
+        ph[15] = now;
+    }
+}
+
 template <int NT, bool CG>
-__device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, int q, int mode)
+__device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, int q, int mode, unsigned long long *ph = nullptr)
 {
     uint32_t *keys = sm.keys;
     uint16_t *ids = sm.ids, *s_pair = sm.pair;
@@ -184,10 +201,14 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
     uint32_t *cj = d.cand_J + (size_t)q * maxc;
     uint16_t *ci = dict ? d.cand_id + (size_t)q * maxc * 32 : nullptr;
     int total = 0;
+    uint16_t base_slot = 0;                                  // warp 0, lane j: hash slot of the current column j
     if (warp == 0) {
         d.Pcol[q * 32 + lane] = col;
-        if (dict && lane < S) d.base_id[q * 32 + lane] = (uint16_t)insert(col);
+        if (dict && lane < S) base_slot = (uint16_t)insert(col);
     }
+    const bool staged = dict && sm.st_ci != nullptr && mode != 0;
+    int nins_all = 0;                                        // number of insertions (mode 1), known to every thread
+    ph_mark(ph, 4);                                          // hash reset, current columns
     if (mode == 0) {
         if (warp == 0) {
             const uint32_t clo = warp_closure(row, S);
@@ -204,6 +225,7 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
                 const uint32_t cu = __shfl_sync(kFull, col, u);
                 if (lane < S) s_pair[u * 32 + lane] = (uint16_t)insert(col | cu);
             }
+        ph_mark(ph, 5);                                              // pair unions entered
         const uint32_t T = warp_reduce_graph(row, lane, S);          // rows of transitive.reduction(better)
         const uint32_t Tcol = warp_transpose(T, lane, S);
         // lane v owns column v: rows u that yield a candidate, per kind
@@ -224,7 +246,9 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
             base += __shfl_sync(kFull, incl, 31);
         }
         total = base;
-        if (tid == 0) { d.ncand[q] = base; if (dict) d.nins[q] = off[1]; }   // lane 0: off[1] = number of insertions
+        nins_all = __shfl_sync(kFull, off[1], 0);                            // lane 0: off[1] = number of insertions
+        if (tid == 0) { d.ncand[q] = base; if (dict) d.nins[q] = off[1]; }
+        ph_mark(ph, 11);                                             // (warp 0) reduction, kinds, offsets
         if (dict && warp == nwarp - 1) {
             // chains of nested insertion targets for the scorer (see above); lane v: row v = D_v, km[0] = sources into v
             d.rowm[q * 32 + lane] = row;
@@ -256,7 +280,11 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
             }
             if (lane == 0) d.nchain[q] = nch;
         }
-        for (int item = warp; item < 3 * S; item += nwarp) {
+        // Device-resident loop (staged): the insertion candidates are scored from the pair table and the winner's columns
+        // are rebuilt from (u, v) by the finish step, so nothing is written per insertion -- only reversals and deletions
+        // are materialised (most of the ~S^2 candidates of an iteration are insertions; this loop was 14 us of the 36 us a
+        // CTA spends between two iterations of a search).
+        for (int item = warp + (staged ? S : 0); item < 3 * S; item += nwarp) {
             const int kd = item / S, v = item - kd * S;
             uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
             int idx = __shfl_sync(kFull, kd == 0 ? off[0] : (kd == 1 ? off[1] : off[2]), v);
@@ -295,8 +323,13 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
                 if (kd == 0) J = rowv;                     // superset shared by every insertion into v (diag included)
                 cc[(size_t)idx * 32 + lane] = nc;
                 // insertions are scored from the pair table; only reversals / deletions need per-candidate ids
-                if (dict && kd != 0 && ((J >> lane) & 1u)) ci[(size_t)idx * 32 + lane] = (uint16_t)insert(nc);
+                if (dict && kd != 0 && ((J >> lane) & 1u)) {
+                    const uint16_t slot = (uint16_t)insert(nc);
+                    if (staged) sm.st_ci[(size_t)(idx - nins_all) * 32 + lane] = slot;
+                    else ci[(size_t)idx * 32 + lane] = slot;
+                }
                 if (lane == 0) {
+                    if (staged && kd != 0) sm.st_J[idx - nins_all] = J;
                     cj[idx] = J;
                     if (d.cand_kind) d.cand_kind[(size_t)q * maxc + idx] = (int8_t)kd;
                 }
@@ -304,8 +337,10 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
             }
         }
     }
+    ph_mark(ph, 12);                                         // (warp 0) its share of the candidates
     if (!dict) return;
     __syncthreads();
+    ph_mark(ph, 6);                                          // waiting for the slowest warp (chains + candidates)
     // dense ids: exclusive scan of the occupied slots (kPer consecutive slots per thread)
     int cnt = 0;
 #pragma unroll
@@ -333,17 +368,27 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
         if (base > dcap) atomicOr(d.overflow, 1);
     }
     __syncthreads();
-    // hash slots -> dense ids (cand_id / base_id written by this CTA above; __syncthreads makes them visible)
-    if (tid < S) d.base_id[q * 32 + tid] = ids[ldv<CG>(d.base_id + q * 32 + tid)];
+    ph_mark(ph, 7);                                          // dense ids
+    // hash slots -> dense ids
+    if (tid < S) d.base_id[q * 32 + tid] = ids[base_slot];         // warp 0 holds the slots of the current columns
     // insertions carry no per-candidate ids: convert from the first reversal on (mode 0: the single candidate)
-    const int nins_q = mode == 0 ? 0 : ldv<CG>(d.nins + q);   // written by thread 0 before the barriers above
-    for (int i = nins_q * 32 + tid; i < total * 32; i += NT) {
-        const int c = i >> 5, j = i & 31;
-        if ((ldv<CG>(cj + c) >> j) & 1u) ci[i] = ids[ldv<CG>(ci + i)];
+    const int nins_q = mode == 0 ? 0 : nins_all;
+    if (staged) {
+        for (int i = tid; i < (total - nins_q) * 32; i += NT) {
+            const int c = i >> 5, j = i & 31;
+            if ((sm.st_J[c] >> j) & 1u) ci[(size_t)nins_q * 32 + i] = ids[sm.st_ci[i]];
+        }
+    } else {
+        // (cand_id written by this CTA above; __syncthreads makes it visible)
+        for (int i = nins_q * 32 + tid; i < total * 32; i += NT) {
+            const int c = i >> 5, j = i & 31;
+            if ((ldv<CG>(cj + c) >> j) & 1u) ci[i] = ids[ldv<CG>(ci + i)];
+        }
     }
     if (mode != 0)
         for (int i = tid; i < 32 * 32; i += NT)
             d.pair_id[(size_t)q * 1024 + i] = ((i >> 5) < S && (i & 31) < S) ? ids[s_pair[i]] : (uint16_t)0;
+    ph_mark(ph, 8);                                          // ids of the candidates and of the pair table
 }
 
 __global__ void __launch_bounds__(256) gen_kernel(SearchDev d, int mode)
@@ -752,6 +797,16 @@ __global__ void __launch_bounds__(kDictThreads, 1) score_dict_kernel(SearchDev d
 }
 
 // ---- argmax, accept rule, graph update -------------------------------------------------------------------
+// The fixed shape in which the row tiles of a candidate are added: Gp (a power of two <= 8, so that the lanes of a
+// candidate sit in one warp) groups of TG consecutive tiles; ascending inside a group, then ascending over the groups.
+__host__ __device__ __forceinline__ void tile_groups(int ntiles, int *Gp, int *TG)
+{
+    int g = 1;
+    while (g < 8 && g * 16 < ntiles) g <<= 1;
+    *Gp = g;
+    *TG = (ntiles + g - 1) / g;
+}
+
 struct FinSmem {
     double *best;     // [NT]
     int *idx;         // [NT]
@@ -771,7 +826,7 @@ __host__ __device__ constexpr size_t fin_smem_bytes(int nt) { return (size_t)nt 
 // scores of candidate c: sum over `etiles` tile rows of src[(q*etiles + et)*maxc + c], ascending (etiles = 1: src = scores)
 template <int NT, bool CG>
 __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs, int q, int mode, int etiles,
-                                            const double *__restrict__ src, int32_t *n_active)
+                                            const double *__restrict__ src, int32_t *n_active, unsigned long long *ph = nullptr)
 {
     double *s_best = fs.best;
     int *s_idx = fs.idx;
@@ -782,24 +837,60 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
     const int nc = ldv<CG>(d.ncand + q);
     double best = -INFINITY;
     int bidx = INT_MAX;
-    for (int c = tid; c < nc; c += NT) {
-        double sc = 0.0;                                           // tiles in ascending order, whatever CTA produced them
-#pragma unroll 8
-        for (int et = 0; et < etiles; ++et) sc += ldv<CG>(src + ((size_t)q * etiles + et) * maxc + c);
-        if (isnan(sc)) sc = 0.0;                                   // scores[is.na(scores)] <- 0   R/mnems.r:235
-        if (sc > best) { best = sc; bidx = c; }                    // ascending c: first maximum kept
-    }
-    s_best[tid] = best;
-    s_idx[tid] = bidx;
-    __syncthreads();
-    for (int o = NT / 2; o > 0; o >>= 1) {
-        if (tid < o) {
-            const double ob = s_best[tid + o];
-            const int oi = s_idx[tid + o];
-            if (ob > s_best[tid] || (ob == s_best[tid] && oi < s_idx[tid])) { s_best[tid] = ob; s_idx[tid] = oi; }
+    // Score of a candidate = sum of its row tiles in a FIXED shape, whatever CTA produced them: the tiles form Gp groups
+    // (tile_groups), each group is added in ascending order, then the group sums in ascending order (reduce_tiles_kernel
+    // computes the same function).  A thread owns two neighbouring candidates and fetches a whole group (16 tiles) of both
+    // with 16-byte loads before it adds: this step is on the critical path of every greedy iteration and is bound by how
+    // fast one SM can pull the 63 x ~700 partial sums out of L2.
+    {
+        int Gp, TG;
+        tile_groups(etiles, &Gp, &TG);
+        const double *base = src + (size_t)q * etiles * maxc;      // rows of maxc doubles (maxc is even: 16-byte aligned pairs)
+        for (int c = 2 * tid; c < nc; c += 2 * NT) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int g = 0; g < Gp; ++g) {
+                const int t0 = g * TG, t1 = min(etiles, t0 + TG);
+                double p0 = 0.0, p1 = 0.0;
+                for (int e0 = t0; e0 < t1; e0 += 16) {
+                    double2 v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        v[i] = e0 + i < t1 ? ldv<CG>(reinterpret_cast<const double2 *>(base + (size_t)(e0 + i) * maxc + c))
+                                           : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (e0 + i < t1) { p0 += v[i].x; p1 += v[i].y; }
+                }
+                s0 = g == 0 ? p0 : s0 + p0;
+                s1 = g == 0 ? p1 : s1 + p1;
+            }
+            if (isnan(s0)) s0 = 0.0;                               // scores[is.na(scores)] <- 0   R/mnems.r:235
+            if (isnan(s1)) s1 = 0.0;
+            if (s0 > best) { best = s0; bidx = c; }                // ascending c: first maximum kept
+            if (c + 1 < nc && s1 > best) { best = s1; bidx = c + 1; }
         }
-        __syncthreads();
     }
+    ph_mark(ph, 1);                                          // tile sums
+    // block argmax, ties -> the lower candidate index (which.max): warp shuffles, then the warp results
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_down_sync(kFull, best, o);
+        const int oi = __shfl_down_sync(kFull, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_idx[tid >> 5] = bidx; }
+    __syncthreads();
+    if (tid < 32) {
+        best = tid < NT / 32 ? s_best[tid] : -INFINITY;
+        bidx = tid < NT / 32 ? s_idx[tid] : INT_MAX;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_down_sync(kFull, best, o);
+            const int oi = __shfl_down_sync(kFull, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if (tid == 0) { s_best[0] = best; s_idx[0] = bidx; }
+        __syncwarp();
+    }
+    ph_mark(ph, 2);                                          // argmax
     if (tid < 32) {
         best = s_best[0];
         bidx = s_idx[0];
@@ -808,8 +899,36 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
         } else if (mode == 0) {
             if (tid == 0) { d.oldscore[q] = best; d.maxtrace[q] = best; fs.flag[0] = 1; }
         } else {
-            const uint32_t ccol = ldv<CG>(d.cand_cols + ((size_t)q * maxc + bidx) * 32 + tid);
-            int np = __popc(ldv<CG>(d.Pcol + q * 32 + tid)), ncn = __popc(ccol);
+            const uint32_t pcol = ldv<CG>(d.Pcol + q * 32 + tid);
+            uint32_t ccol;
+            bool rebuilt = false;
+            if constexpr (CG) {
+                // insertion candidates are not materialised in the device-resident loop: candidate bidx < nins is the
+                // r-th missing edge u -> v of column v (ascending u), columns as in gen_body (transClose_Ins, src/mm.cpp:50-65)
+                const int nins = ldv<CG>(d.nins + q);
+                if (bidx < nins) {
+                    const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
+                    const uint32_t zmask = tid < S ? (~pcol & smask) : 0u;
+                    const int cnt = __popc(zmask);
+                    int incl = cnt;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(kFull, incl, o);
+                        if (tid >= o) incl += t;
+                    }
+                    const int offv = incl - cnt;
+                    const unsigned hit = __ballot_sync(kFull, bidx >= offv && bidx < offv + cnt);
+                    const int v = __ffs(hit) - 1;
+                    const int r = bidx - __shfl_sync(kFull, offv, v);
+                    const int u = (int)__fns(__shfl_sync(kFull, zmask, v), 0, r + 1);
+                    const uint32_t cu = __shfl_sync(kFull, pcol, u);
+                    const uint32_t b = pcol | (tid == v ? (1u << u) : 0u);
+                    ccol = (((b >> v) & 1u) ? (b | cu) : b) & smask;
+                    if (tid >= S) ccol = 0u;
+                    rebuilt = true;
+                }
+            }
+            if (!rebuilt) ccol = ldv<CG>(d.cand_cols + ((size_t)q * maxc + bidx) * 32 + tid);
+            int np = __popc(pcol), ncn = __popc(ccol);
             for (int o = 16; o > 0; o >>= 1) {
                 np += __shfl_down_sync(kFull, np, o);
                 ncn += __shfl_down_sync(kFull, ncn, o);
@@ -840,6 +959,7 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
         }
     }
     __syncthreads();       // the accepted graph (Prow), the active flag and fs.flag are visible to the whole CTA
+    ph_mark(ph, 3);                                          // accept rule, graph update
 }
 
 // finish of greedy iteration i fused with the candidate generation of iteration i + 1 (same CTA per search): one
@@ -900,7 +1020,10 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ unsigned long long s_task;
     __shared__ int s_last;
+    __shared__ unsigned long long s_ph[16];
     const int tid = threadIdx.x;
+    if (tid < 16) s_ph[tid] = 0ull;
+    __syncthreads();
     unsigned long long t_begin = 0ull, t_task = 0ull, busy = 0ull, t_fin = 0ull, t_gen = 0ull, n_closed = 0ull;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
     while (true) {
@@ -937,17 +1060,24 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
         if (!s_last) continue;
         // ---- this CTA closes the iteration of search q ----
         unsigned long long tp0 = 0ull, tp1 = 0ull, tp2 = 0ull;
-        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0));
+        if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp0)); s_ph[15] = tp0; }
         const int mode = __ldcg(d.stage + q);
         finish_body<kDictThreads, true>(d, fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes), q, mode, d.ntiles, d.partial,
-                                        nullptr);
+                                        nullptr, s_ph);
         const int go = fin_smem_at<kDictThreads>(s_raw + kGenSmemBytes).flag[0];
         __syncthreads();
         if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp1));
         if (go) {
-            gen_body<kDictThreads, true>(d, gen_smem_at(s_raw), q, 1);
+            GenSmem gs = gen_smem_at(s_raw);
+            {   // staging behind the generation and finish areas; capacity checked against the workspace in search_create
+                unsigned char *stg = s_raw + ((kGenSmemBytes + fin_smem_bytes(kDictThreads) + 15) & ~(size_t)15);
+                gs.st_J = reinterpret_cast<uint32_t *>(stg);
+                gs.st_ci = reinterpret_cast<uint16_t *>(stg + (((size_t)d.maxc * 4 + 15) & ~(size_t)15));
+            }
+            gen_body<kDictThreads, true>(d, gs, q, 1, s_ph);
             __threadfence();
             __syncthreads();
+            ph_mark(s_ph, 9);                                // fence
             if (tid == 0) {
                 d.stage[q] = 1;
                 if (*reinterpret_cast<volatile int32_t *>(d.overflow) & 1) {      // dictionary overflow: stop everything
@@ -961,6 +1091,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
             __threadfence();
             if (atomicSub(d.live, 1) == 1) { __threadfence(); *reinterpret_cast<volatile unsigned *>(&d.qctl[3]) = 1u; }
         }
+        ph_mark(s_ph, 10);                                   // publish / retire
         if (tid == 0) {
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tp2));
             t_fin += tp1 - tp0; t_gen += tp2 - tp1; ++n_closed;
@@ -975,6 +1106,7 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
         atomicAdd(&d.busy_ns[2], t_fin);
         atomicAdd(&d.busy_ns[3], t_gen);
         atomicAdd(&d.busy_ns[4], n_closed);
+        for (int i = 1; i <= 12; ++i) atomicAdd(&d.busy_ns[8 + i], s_ph[i]);
     }
 }
 __global__ void search_init_kernel(int n, int S, const uint32_t *__restrict__ start_rows, uint32_t *__restrict__ Prow,
@@ -1103,8 +1235,8 @@ static int launch_score(SearchBatch *sb, int n, cudaStream_t st)
     return 0;
 }
 
-// scores[q][c] = sum over the row tiles, ascending -- fully parallel over candidates, so the single-CTA finish step
-// of the host-driven loop reads one value per candidate instead of one per (candidate, tile)
+// scores[q][c] = sum over the row tiles in the fixed shape of tile_groups -- fully parallel over candidates, so the
+// single-CTA finish step of the host-driven loop reads one value per candidate instead of one per (candidate, tile)
 __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles, const int32_t *__restrict__ ncand,
                                                            const double *__restrict__ partial, double *__restrict__ scores,
                                                            const int32_t *__restrict__ qlist)
@@ -1112,9 +1244,15 @@ __global__ void __launch_bounds__(256) reduce_tiles_kernel(int maxc, int ntiles,
     const int q = qlist ? qlist[blockIdx.y] : blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncand[q]) return;
+    int Gp, TG;
+    tile_groups(ntiles, &Gp, &TG);                                  // the same shape as finish_body
     double sc = 0.0;
+    for (int g = 0; g < Gp; ++g) {
+        double p = 0.0;
 #pragma unroll 8
-    for (int et = 0; et < ntiles; ++et) sc += partial[((size_t)q * ntiles + et) * maxc + c];
+        for (int et = g * TG; et < min(ntiles, (g + 1) * TG); ++et) p += partial[((size_t)q * ntiles + et) * maxc + c];
+        sc = g == 0 ? p : sc + p;
+    }
     scores[(size_t)q * maxc + c] = sc;
 }
 
@@ -1177,7 +1315,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
     SearchBatch *sb = new SearchBatch();
     sb->nmax = nmax; sb->E = E; sb->S = S;
     sb->etiles = (E + kRows - 1) / kRows;
-    sb->maxc = std::max(1, 3 * S * (S - 1));
+    sb->maxc = std::max(2, 3 * S * (S - 1));          // even: finish_body reads the partial sums as double2
     const int ntiles = (E + kDictRows - 1) / kDictRows;
     {
         int dev = 0, sms = 0;
@@ -1191,7 +1329,11 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         int fit = 1;
         while (score_smem_bytes(fit + 1) + 1536 <= 232448) ++fit;   // 1.5 KB of static shared memory in the kernels
         sb->dcap = std::max(1, std::min(need + need / 2, fit));     // 50 % slack where shared memory allows (S <= 26)
-        sb->dict_smem = std::max(score_smem_bytes(sb->dcap), kGenSmemBytes + fin_smem_bytes(kDictThreads));
+        // generation phase of the device-resident loop: hash set + finish scratch + the staged ids of the reversal /
+        // deletion candidates (at most S(S-1) of each kind), see GenSmem
+        const size_t stage_need = ((kGenSmemBytes + fin_smem_bytes(kDictThreads) + 15) & ~(size_t)15) +
+                                  (((size_t)sb->maxc * 4 + 15) & ~(size_t)15) + (size_t)(2 * S * (S - 1) + S) * 64;
+        sb->dict_smem = std::max(score_smem_bytes(sb->dcap), stage_need);
         // per device: set on every workspace creation (cheap), the attribute belongs to the current context
 #define MN_ATTR(SPV)                                                                                               \
         cudaFuncSetAttribute(score_dict_kernel<SPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb->dict_smem); \
@@ -1219,8 +1361,8 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         MN_TRY(sb->rowm.alloc((size_t)nmax * 32, true)); MN_TRY(sb->chain_v.alloc((size_t)nmax * 32, true));
         MN_TRY(sb->chain_start.alloc((size_t)nmax * 33, true)); MN_TRY(sb->nchain.alloc(nmax, true));
         MN_TRY(sb->ring.alloc(sb->ring_cap)); MN_TRY(sb->qctl.alloc(4, true)); MN_TRY(sb->live.alloc(1, true));
-        MN_TRY(sb->tiles_done.alloc(nmax, true)); MN_TRY(sb->stage.alloc(nmax, true)); MN_TRY(sb->busy_ns.alloc(8, true));
-        MN_CU(cudaMallocHost((void **)&sb->h_busy, 8 * sizeof(unsigned long long)));
+        MN_TRY(sb->tiles_done.alloc(nmax, true)); MN_TRY(sb->stage.alloc(nmax, true)); MN_TRY(sb->busy_ns.alloc(24, true));
+        MN_CU(cudaMallocHost((void **)&sb->h_busy, 24 * sizeof(unsigned long long)));
         MN_TRY(sb->oldscore.alloc(nmax)); MN_TRY(sb->maxtrace.alloc(nmax)); MN_TRY(sb->nscored.alloc(nmax, true));
         MN_CU(cudaMallocHost((void **)&sb->h_n_active, (2 * kChains + 1) * sizeof(int32_t)));
         for (int i = 0; i <= 2 * kChains; ++i) sb->h_n_active[i] = 0;
@@ -1249,6 +1391,13 @@ void search_destroy(SearchBatch *sb)
                         "CTAs); per closed iteration: finish %.2f us, generate + publish %.2f us\n", sb->calls_acc, sb->closed_acc,
                 sb->busy_acc * 1e-6, sb->resident_acc * 1e-6, sb->fin_acc / std::max(1.0, sb->closed_acc) * 1e-3,
                 sb->gen_acc / std::max(1.0, sb->closed_acc) * 1e-3);
+    if (getenv("MNEMCU_SEARCH_STATS") && sb->calls_acc > 0) {
+        static const char *nm[13] = {"", "tile sums", "argmax", "accept + update", "hash reset", "pair unions",
+                                     "wait for the slowest warp", "dense ids", "candidate / pair ids", "fence", "publish",
+                                     "warp 0: reduction, kinds, offsets", "warp 0: its candidates"};
+        for (int i = 1; i <= 12; ++i)
+            fprintf(stderr, "  %-34s %6.2f us\n", nm[i], sb->ph_acc[i] / std::max(1.0, sb->closed_acc) * 1e-3);
+    }
     if (sb->h_n_active) cudaFreeHost(sb->h_n_active);
     if (sb->h_busy) cudaFreeHost(sb->h_busy);
     for (int h = 0; h < kChains; ++h) {
@@ -1272,7 +1421,7 @@ static int search_check_flags(SearchBatch *sb, int32_t flags)
 static int search_loop_device(SearchBatch *sb, int n, cudaStream_t st)
 {
     const SearchDev d = sb->dev();
-    MN_CU(cudaMemsetAsync(sb->busy_ns.p, 0, 8 * sizeof(unsigned long long), st));
+    MN_CU(cudaMemsetAsync(sb->busy_ns.p, 0, 24 * sizeof(unsigned long long), st));
     MN_LAUNCH(search_seed_kernel, 1, 32, 0, st, d, n);
     const int grid = std::max(1, std::min(sb->sm_count, n * d.ntiles));
 #define MN_PERS(SPV) MN_LAUNCH(search_persistent_kernel<SPV>, grid, kDictThreads, sb->dict_smem, st, d)
@@ -1280,12 +1429,13 @@ static int search_loop_device(SearchBatch *sb, int n, cudaStream_t st)
 #undef MN_PERS
     int32_t *h_over = sb->h_n_active + 2 * kChains;
     MN_CU(cudaMemcpyAsync(h_over, sb->overflow.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MN_CU(cudaMemcpyAsync(sb->h_busy, sb->busy_ns.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    MN_CU(cudaMemcpyAsync(sb->h_busy, sb->busy_ns.p, 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     MN_CU(cudaStreamSynchronize(st));
     sb->busy_acc += (double)sb->h_busy[0];
     sb->resident_acc += (double)sb->h_busy[1];
     sb->fin_acc += (double)sb->h_busy[2]; sb->gen_acc += (double)sb->h_busy[3]; sb->closed_acc += (double)sb->h_busy[4];
     sb->calls_acc += 1.0;
+    for (int i = 1; i <= 12; ++i) sb->ph_acc[i] += (double)sb->h_busy[8 + i];
     return search_check_flags(sb, *h_over);
 }
 

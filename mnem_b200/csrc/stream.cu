@@ -28,7 +28,7 @@ namespace mn {
 // (1 issue slot per pair and cell); left alone it if-converts to DADD + 2 FSEL, three issue slots per add.
 // ---------------------------------------------------------------------------------------------------------
 template <int MT>
-__global__ void __launch_bounds__(256) estep_kernel(const double *__restrict__ Dblk, int E,
+__global__ void __launch_bounds__(MT > 11 ? 256 : 384) estep_kernel(const double *__restrict__ Dblk, int E,
                                                     const uint32_t *__restrict__ maskT,
                                                     const int32_t *__restrict__ blk_seg, int M, int eper,
                                                     int groups, PairPtrs out)
@@ -120,11 +120,16 @@ static int launch_estep_t(const mnemcu_ctx *cx, const uint32_t *maskT, int M, co
 int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairPtrs &out, cudaStream_t st)
 {
     MN_ARG(M >= 1 && M <= 32, "E-step serves 1..32 (start, component) pairs per launch");
-    // Pairs per warp: up to 20 (40 FP64 accumulators per lane, 125 registers); above that two warps of the same CTA
-    // split the pairs and the second one re-reads the block from L1/L2, not from HBM.  (Measured at 30 pairs, cfg5: one
-    // warp with 60 accumulators needs 167 registers -> 12 warps per SM and 4.58 ms per pass; two warps of 15: 4.26 ms.)
-    const int groups = (M + 19) / 20;
+    // Pairs per warp: up to 20 (40 FP64 accumulators per lane, 125 registers); above that several warps of the same CTA
+    // split the pairs and all but the first re-read the block from L1/L2, not from HBM.
+    // Measured at 30 pairs, cfg5 (16 GB per pass): one warp with 60 accumulators 4.58 ms; two warps of 15 pairs 4.25 ms;
+    // THREE warps of 10 pairs 3.94 ms (85 registers, 24 warps per SM; 4 x 8: 4.45 ms).  At that point the kernel is at
+    // 82 % of the FP64 add rate (30 x E x C predicated DADDs per pass), which binds before HBM does.
+    int mtmax = M <= 20 ? 20 : 11;
+    if (const char *e = getenv("MNEMCU_ESTEP_MT")) mtmax = std::max(1, std::min(20, atoi(e)));     // experiments
+    const int groups = (M + mtmax - 1) / mtmax;
     const int MT = (M + groups - 1) / groups;
+    MN_ARG(groups <= 3, "E-step: at most three warps share a cell block");       // 3 groups x 4 E-gene ranges = 384 threads
     // Few blocks (small C): split the E-gene range over up to 4 warps so that every SM still has loads in flight.  The split
     // changes the ORDER of a cell's sum (ranges are summed separately and then added in ascending order), so it must depend
     // on the shape of the data only -- never on M -- or a start's fit would depend on how many starts share its passes.
