@@ -101,6 +101,11 @@ struct Slot {
 struct Engine {
     mnemcu_ctx *cx = nullptr;
     int k = 0, B = 0, M = 0, T = 10, complete = 0, affinity = 0;    // affinity: mnem(affinity =), 1 = hard assignments
+    // Slots 0..Be-1 are the ones in use (Be = B until the queue of starts is drained; then finished slots are squeezed
+    // out, see compact()): the passes over D serve Me() = k * Be pairs, so the tail of a fit -- and every rank of an
+    // N-GPU job spends a good part of its time there -- streams 5 pairs at HBM speed instead of 30 at the FP64 limit.
+    int Be = 0;
+    int Me() const { return k * Be; }
     double logtype = 2.0;
     cudaStream_t st = nullptr;
     std::vector<Slot> slots;
@@ -156,7 +161,7 @@ struct Engine {
 
     int init(mnemcu_ctx *c, int k_, int B_, int complete_, double logtype_, bool with_search)
     {
-        cx = c; k = k_; B = B_; M = k * B; complete = complete_; logtype = logtype_;
+        cx = c; k = k_; B = B_; M = k * B; Be = B; complete = complete_; logtype = logtype_;
         MN_ARG(k >= 1 && B >= 1 && M <= 32, "k * batch must be in 1..32");
         MN_ARG(logtype > 0 && logtype != 1.0, "logtype must be a valid log base");
         MN_CU(cudaSetDevice(cx->device));
@@ -277,13 +282,13 @@ struct Engine {
             ms.mw[j] = d_mw.p + b * 32;
             ms.anypos[j] = flag(b, slots[b].cur);
         }
-        return launch_affinity(cx, ms, k, gamma_stride(M), affinity, complete, logtype, st);
+        return launch_affinity(cx, ms, k, gamma_stride(Me()), affinity, complete, logtype, st);
     }
 
     int op_mstats(bool unweighted = false)
     {
         MN_TRY(tic());
-        MN_TRY(launch_mstats(cx, unweighted ? nullptr : gam.p, M, partial.p, R.p, st));
+        MN_TRY(launch_mstats(cx, unweighted ? nullptr : gam.p, Me(), partial.p, R.p, st));
         MN_TRY(toc(&stats.ms_mstats));
         stats.passes_mstats++;
         return 0;
@@ -294,10 +299,10 @@ struct Engine {
     {
         if (list.empty()) return 0;
         if (cx->multi) {
-            MN_TRY(launch_mstats_groups(cx, partial.p, M, Rg.p, st));
-            MN_TRY(launch_theta_groups(cx, Rg.p, M, d_clo_cols.p, d_theta_tmp.p, st));
+            MN_TRY(launch_mstats_groups(cx, partial.p, Me(), Rg.p, st));
+            MN_TRY(launch_theta_groups(cx, Rg.p, Me(), d_clo_cols.p, d_theta_tmp.p, st));
         } else {
-            MN_TRY(launch_theta(d_Rptr.p, M, cx->E, cx->S, d_clo_cols.p, 1, d_theta_tmp.p, nullptr, st));
+            MN_TRY(launch_theta(d_Rptr.p, Me(), cx->E, cx->S, d_clo_cols.p, 1, d_theta_tmp.p, nullptr, st));
         }
         for (int b : list)
             MN_CU(cudaMemcpyAsync(d_theta.p + (size_t)b * k * cx->E, d_theta_tmp.p + (size_t)b * k * cx->E,
@@ -349,9 +354,9 @@ struct Engine {
     // E-step for all slots into their `nw` buffers
     int op_estep()
     {
-        MN_TRY(launch_build_masks(cx, d_clo.p, d_theta.p, M, maskT.p, st));
+        MN_TRY(launch_build_masks(cx, d_clo.p, d_theta.p, Me(), maskT.p, st));
         PairPtrs pp{};
-        for (int b = 0; b < B; ++b) {
+        for (int b = 0; b < Be; ++b) {
             MN_CU(cudaMemsetAsync(flag(b, slots[b].nw), 0, sizeof(int32_t), st));
             for (int i = 0; i < k; ++i) {
                 pp.L[b * k + i] = buf(b, slots[b].nw) + (size_t)i * cx->Cp;
@@ -359,10 +364,53 @@ struct Engine {
             }
         }
         MN_TRY(tic());
-        MN_TRY(launch_estep(cx, maskT.p, M, pp, st));
+        MN_TRY(launch_estep(cx, maskT.p, Me(), pp, st));
         MN_TRY(toc(&stats.ms_estep));
         stats.passes_estep++;
-        stats.estep_bytes += 8.0 * cx->E * cx->C + 8.0 * (double)M * cx->C;
+        stats.estep_bytes += 8.0 * cx->E * cx->C + 8.0 * (double)Me() * cx->C;
+        return 0;
+    }
+
+    // everything slot `from` holds on the device and on the host moves to the (free) slot `to`
+    int move_slot(int from, int to)
+    {
+        const size_t kE = (size_t)k * cx->E;
+        auto cp = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st); };
+        for (int i = 0; i < 3; ++i) MN_CU(cp(buf(to, i), buf(from, i), sizeof(double) * kCp));
+        MN_CU(cp(d_flag.p + to * 4, d_flag.p + from * 4, sizeof(int32_t) * 4));
+        MN_CU(cp(d_theta.p + to * kE, d_theta.p + from * kE, sizeof(int32_t) * kE));
+        MN_CU(cp(d_theta_best.p + to * kE, d_theta_best.p + from * kE, sizeof(int32_t) * kE));
+        for (DevBuf<uint32_t> *g : {&d_res1, &d_clo, &d_clo_cols, &d_best_rows})
+            MN_CU(cp(g->p + (size_t)to * k * 32, g->p + (size_t)from * k * 32, sizeof(uint32_t) * k * 32));
+        MN_CU(cp(d_mw.p + to * 32, d_mw.p + from * 32, sizeof(double) * 32));
+        MN_CU(cp(d_mwtmp.p + to * 32, d_mwtmp.p + from * 32, sizeof(double) * 32));
+        MN_CU(cp(d_ll.p + to * 128, d_ll.p + from * 128, sizeof(double) * 128));
+        std::swap(slots[to], slots[from]);
+        slots[from].start = -1;
+        return 0;
+    }
+
+    // Once no start is left to refill a finished slot: move the active slots to the front and shrink the passes to them.
+    // A start's fit does not depend on which slot it sits in nor on how many pairs share its passes (tested bit for bit).
+    int compact()
+    {
+        for (;;) {
+            int hi = -1, lo = -1;
+            for (int b = 0; b < Be; ++b) {
+                if (slots[b].start >= 0) hi = b;
+                else if (lo < 0) lo = b;
+            }
+            if (hi < 0 || lo < 0 || lo > hi) break;
+            MN_TRY(move_slot(hi, lo));
+        }
+        int nb = 0;
+        while (nb < Be && slots[nb].start >= 0) ++nb;
+        nb = std::max(1, nb);
+        if (nb != Be) {
+            // gamma is [Cp][gamma_stride(pairs)] with zero padding columns: a new stride needs a clean buffer
+            if (gamma_stride(k * nb) != gamma_stride(Me())) MN_CU(cudaMemsetAsync(gam.p, 0, sizeof(double) * gam.n, st));
+            Be = nb;
+        }
         return 0;
     }
 
@@ -651,10 +699,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             MN_TRY(begin_slot(b, s0));
         }
         long guard_ticks = 0;
+        bool drained = false;
         while (running > 0) {
             ++guard_ticks;
             std::vector<int> act, ini, em;
-            for (int b = 0; b < B; ++b)
+            for (int b = 0; b < en.Be; ++b)
                 if (en.slots[b].start >= 0) {
                     act.push_back(b);
                     (en.slots[b].phase == 0 ? ini : em).push_back(b);
@@ -778,8 +827,10 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                     MN_TRY(finish_slot(b));
                     const int s1 = take_start();
                     if (s1 >= 0) MN_TRY(begin_slot(b, s1));
+                    else drained = true;
                 }
             }
+            if (drained && running > 0) MN_TRY(en.compact());
             if (guard_ticks > 100000) return set_err(MNEMCU_ERR_ARG, "EM did not terminate");
         }
         return 0;
