@@ -319,6 +319,15 @@ def run_ours(args):
                 "launches_per_step": st["passes_estep"],
                 "pairs_per_launch": (bytes_launch - 8.0 * E * Cn) / (8.0 * Cn),
                 "share_of_step": st["ms_estep"] / max(st["ms_total"], 1e-9)}
+    # above 20 pairs per launch the pass is bound by the FP64 add rate before HBM (one predicated DADD per pair, E-gene and
+    # cell; 64 FP64 lanes per SM and clock): report that roofline next to the HBM one
+    pairs = roofline["pairs_per_launch"]
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    mhz = clocks["sm_mhz"] or clocks["sm_max_mhz"] or 1965.0
+    fp64_peak = sms * 64.0 * mhz * 1e6
+    fp64_rate = pairs * E * float(Cn) / t_estep if t_estep > 0 else 0.0
+    roofline["fp64_adds"] = {"achieved": fp64_rate, "peak": fp64_peak, "unit": "FP64 adds/s", "frac": fp64_rate / fp64_peak,
+                             "peak_source": "%d SMs x 64 lanes x %.0f MHz (sampled SM clock)" % (sms, mhz)}
     # the kernel that decides `value`: the device-resident greedy search (one persistent launch per EM tick).  Live numbers
     # from this run; pipe utilisation from the committed ncu capture of the same kernel (profiles/search_ncu.json).
     cand_rank0 = st["cand_scored"] / max(1e-9, st["ms_search"] * 1e-3)
