@@ -371,7 +371,9 @@ def run_ours(args):
             Dh = hnp.T
             with mb.Context.synthetic(sim, device=local) as c0:
                 mb._lib.check(mb.load_library().mnemcu_ctx_read_data(c0._h, 0, Cn, mb._lib.dp(hnp)))
-            times, iters = [], []
+            times, iters, parts = [], [], []
+            sampler2 = ClockSampler(local)
+            sampler2.start()
             # N > 1: every rank uploads 1/N of the columns from ITS host copy and the slices are exchanged over NVLink
             # (one NCCL all-gather) instead of pushing N full copies of D through PCIe and the host memory bus
             per = -(-Cn // world)
@@ -391,9 +393,12 @@ def run_ours(args):
                     torch.cuda.synchronize()
                     cxe = mb.Context.from_device(Dd.data_ptr(), E, Cn, sim["pert"], device=local)
                     del Dd
+                torch.cuda.synchronize()
+                t_up = time.time() - t0
                 with cxe:
                     # probs="winner": the k x C log ratios of the best start come back to the host, as in mnem()'s result
                     r = mb.em_run(cxe, init, complete=sim["complete"], batch=args.batch, probs="winner", next_start=queue)
+                    t_em = time.time() - t0 - t_up
                 my = sorted(queue.taken)
                 mdist.gather_winner(my, r["ll"][my], sim["starts"], device=dev)     # the winner is part of the result
                 torch.cuda.synchronize()
@@ -401,13 +406,18 @@ def run_ours(args):
                 barrier()
                 if i >= 1:
                     times.append(dt)
+                    parts.append((t_up, t_em, r["stats"]["ms_total"] * 1e-3))
                     iters.append(reduce_sum([r["stats"]["em_iters"]])[0])
             per_start = k * S * S + 4 * k * E + 8 * k + 8 + 4 + 4 * 8 * 256          # adj, theta, mw, ll, n_iter, traces
             e2e = {"value": float(np.mean(iters) / np.mean(times)), "unit": "EM iterations/s",
                    "h2d_bytes_per_step": int(8 * E * Cn + world * (4 * Cn + sim["starts"] * k * S * S)),
                    "nvlink_bytes_per_step": int(8 * E * Cn * (world - 1)),
                    "d2h_bytes_per_step": int(sim["starts"] * per_start + world * 8 * k * Cn),   # + every rank's best probs
-                   "seconds_per_step": float(np.mean(times)), "steps": len(times)}
+                   "seconds_per_step": float(np.mean(times)), "steps": len(times), "seconds_each": [float(x) for x in times],
+                   "clocks": sampler2.stop(),
+                   "seconds_upload_and_layout_rank0": float(np.mean([p_[0] for p_ in parts])),
+                   "seconds_em_wall_rank0": float(np.mean([p_[1] for p_ in parts])),
+                   "seconds_em_device_rank0": float(np.mean([p_[2] for p_ in parts]))}
             del hnp, Dh
         del host
 

@@ -61,6 +61,8 @@ struct SearchBatch {
     int nmax = 0, E = 0, S = 0, etiles = 0, maxc = 0;
     int dcap = 0;                     // dictionary capacity (entries)
     int marginal = 0;                 // scoreAdj(marginal = TRUE): log-sum-exp over the columns instead of the row maximum
+    int generic = 0;                  // fallback after a dictionary overflow: generic scorer, no dictionary (search_run)
+    int32_t last_flags = 0;           // overflow flags of the last loop (1: dictionary full, 2: move limit)
     double logtype = 2.0;
     size_t dict_smem = 0;
     int sm_count = 148;
@@ -92,7 +94,8 @@ struct SearchBatch {
         d.E = E; d.S = S; d.maxc = maxc; d.dcap = dcap; d.ntiles = (E + kDictRows - 1) / kDictRows; d.nsm = sm_count;
         d.hard_cap = 4 * S * S + 16;      // a strict hill-climb cannot take more moves than this in practice
         d.Rptr = Rptr.p; d.Prow = Prow.p; d.Pcol = Pcol.p; d.cand_cols = cand_cols.p; d.cand_J = cand_J.p;
-        d.dict_masks = dict_masks.p; d.rowm = rowm.p; d.cand_id = cand_id.p; d.base_id = base_id.p; d.pair_id = pair_id.p;
+        d.dict_masks = (marginal || generic) ? nullptr : dict_masks.p;      // no dictionary for the generic scorer
+        d.rowm = rowm.p; d.cand_id = cand_id.p; d.base_id = base_id.p; d.pair_id = pair_id.p;
         d.chain_v = chain_v.p; d.chain_start = chain_start.p; d.ncand = ncand.p; d.active = active.p; d.niter = niter.p;
         d.nd = nd.p; d.nins = nins.p; d.overflow = overflow.p; d.nchain = nchain.p; d.partial = partial.p;
         d.scores = scores.p; d.oldscore = oldscore.p; d.maxtrace = maxtrace.p; d.nscored = nscored.p; d.ring = ring.p;
@@ -1277,7 +1280,7 @@ static int launch_gen(SearchBatch *sb, int n, int mode, cudaStream_t st)
 static int launch_score_dict(SearchBatch *sb, int n, int G, const int32_t *qlist, cudaStream_t st)
 {
     const int S = sb->S;
-    if (sb->marginal) {   // the dictionary trick needs a row MAXIMUM; the marginal score re-sums the changed columns per candidate
+    if (sb->marginal || sb->generic) {   // the dictionary trick needs a row MAXIMUM; the marginal score re-sums the changed columns per candidate
         MN_TRY(launch_score(sb, n, st));
         dim3 rg((sb->maxc + 255) / 256, n);
         MN_LAUNCH(reduce_tiles_kernel, rg, 256, 0, st, sb->maxc, sb->etiles, sb->ncand.p, sb->partial.p, sb->scores.p,
@@ -1329,6 +1332,7 @@ int search_create(int nmax, int E, int S, SearchBatch **out)
         int fit = 1;
         while (score_smem_bytes(fit + 1) + 1536 <= 232448) ++fit;   // 1.5 KB of static shared memory in the kernels
         sb->dcap = std::max(1, std::min(need + need / 2, fit));     // 50 % slack where shared memory allows (S <= 26)
+        if (const char *e = getenv("MNEMCU_DICT_CAP")) sb->dcap = std::max(1, std::min(sb->dcap, atoi(e)));   // tests: force the fallback
         // generation phase of the device-resident loop: hash set + finish scratch + the staged ids of the reversal /
         // deletion candidates (at most S(S-1) of each kind), see GenSmem
         const size_t stage_need = ((kGenSmemBytes + fin_smem_bytes(kDictThreads) + 15) & ~(size_t)15) +
@@ -1411,6 +1415,7 @@ void search_destroy(SearchBatch *sb)
 
 static int search_check_flags(SearchBatch *sb, int32_t flags)
 {
+    sb->last_flags = flags;
     if (flags & 1) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
     if (flags & 2)
         return set_err(MNEMCU_ERR_ARG, "a greedy search did not converge within %d moves", 4 * sb->S * sb->S + 16);
@@ -1452,7 +1457,7 @@ static int search_loop_host(SearchBatch *sb, int n, cudaStream_t st)
     // lengths, so pairs -- not single searches -- are dealt round-robin.
     int want = 2;                                      // default number of chains
     if (const char *e = getenv("MNEMCU_CHAINS")) want = std::max(1, std::min(kChains, atoi(e)));
-    const int nch = (sb->marginal || n < 2 * want) ? 1 : want;
+    const int nch = (sb->marginal || sb->generic || n < 2 * want) ? 1 : want;
     struct Chain { int n = 0, off = 0, pending = -1, G = 1; bool done = false; cudaStream_t st = nullptr; };
     Chain ch[kChains];
     {
@@ -1524,7 +1529,23 @@ int search_run(SearchBatch *sb, int n, const double *const *R_ptrs_host, const u
     MN_TRY(launch_gen(sb, n, 0, st));
     bool host_loop = sb->marginal != 0;
     if (const char *e = getenv("MNEMCU_SEARCH")) host_loop = host_loop || strcmp(e, "host") == 0;
-    MN_TRY(host_loop ? search_loop_host(sb, n, st) : search_loop_device(sb, n, st));
+    int rc = host_loop ? search_loop_host(sb, n, st) : search_loop_device(sb, n, st);
+    if (rc && (sb->last_flags & 1) && !sb->marginal) {
+        // More distinct column masks in one neighbourhood than the shared-memory table holds (capacity is a heuristic for
+        // S >= 27): run these searches again from their start graphs with the generic scorer, which re-sums the changed
+        // columns of every candidate and needs no dictionary.  Slower, never wrong; scores may differ from the dictionary
+        // path in the last bits (different row-tile shape).
+        sb->generic = 1;
+        auto again = [&]() -> int {
+            MN_CU(cudaMemsetAsync(sb->overflow.p, 0, sizeof(int32_t), st));
+            MN_LAUNCH(search_init_kernel, n, 32, 0, st, n, S, start_rows_dev, sb->Prow.p, sb->active.p, sb->niter.p, sb->nscored.p);
+            MN_TRY(launch_gen(sb, n, 0, st));
+            return search_loop_host(sb, n, st);
+        };
+        rc = again();
+        sb->generic = 0;
+    }
+    if (rc) return rc;
     MN_LAUNCH(search_final_kernel, n, 32, 0, st, S, sb->Prow.p, sb->adj_rows.p, sb->closed_rows.p, sb->closed_cols.p);
     MN_TRY(launch_theta(sb->Rptr.p, n, sb->E, S, sb->closed_cols.p, 0, sb->theta.p, nullptr, st));
     return 0;

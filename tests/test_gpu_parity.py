@@ -611,3 +611,22 @@ def test_user_mixture_weights_and_winner_probs():
     assert rw["best"] == r["best"] and rw["probs"].shape[0] == 1
     assert np.array_equal(rw["probs"][0], r["probs"][r["best"]])
     assert np.array_equal(rw["adj"], r["adj"]) and np.array_equal(rw["ll"], r["ll"])      # the tape does not change a fit
+
+
+def test_dictionary_overflow_falls_back_to_the_generic_scorer(monkeypatch):
+    """More distinct column masks in a neighbourhood than the shared-memory table holds must not fail the call: the
+    searches are run again with the generic scorer (every changed column re-summed, no dictionary).  Forced here by
+    capping the table at 8 entries; graphs, theta and iteration counts equal the normal path and the oracle."""
+    rng = np.random.default_rng(12)
+    S, E, n = 9, 150, 5
+    R = rng.normal(size=(n, E, S)) * 3
+    normal = mb.nem_greedy(R, None)
+    monkeypatch.setenv("MNEMCU_DICT_CAP", "8")
+    capped = mb.nem_greedy(R, None)
+    monkeypatch.delenv("MNEMCU_DICT_CAP")
+    for q in range(n):
+        ref = orc.nem_greedy(R[q], None)
+        assert ref["min_margin"] > 1e-13
+        assert np.array_equal(capped["adj"][q], ref["adj"]) and np.array_equal(capped["subtopo"][q], ref["theta"])
+        assert np.array_equal(capped["adj"][q], normal["adj"][q]) and capped["n_iter"][q] == normal["n_iter"][q]
+        assert abs(capped["score"][q] - ref["score"]) <= 1e-9 * abs(ref["score"])
