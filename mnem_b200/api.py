@@ -577,33 +577,45 @@ def getIC(x, n_cells, man=False, degree=4, logtype=2, pen=2):
     return (pen if man else np.log(n_cells)) * fpar - 2 * LL
 
 
-def bootstrap(x, D, pert=None, size=1000, p=1.0, logtype=2, complete=False, seed=0, chunk=256):
+def bootstrap(x, D, pert=None, size=1000, p=1.0, logtype=2, complete=False, seed=0, chunk=256, part=(0, 1), fit_fn=None):
     """bootstrap(x, size, p) R/mnems.r:2348-2369: edge support of every component graph.
 
     For component i the data are weighted by its responsibilities and collapsed (doMean inside nem()), the E-gene
     rows are resampled with replacement `size` times, nem() is run from the empty graph on every resample -- all of
     them as ONE batch of device searches -- and the transitive closures are averaged.  The row samples come from a
-    seeded NumPy generator (R's sample() stream cannot be reproduced outside R); returns (support [k,S,S], idx)."""
+    seeded NumPy generator (R's sample() stream cannot be reproduced outside R); returns (support [k,S,S], idx).
+
+    part = (r, n): fit only the resamples r, r + n, r + 2n, ... and return their closure COUNTS divided by `size` -- the
+    share of rank r of n; the shares add up to the full support (mnem_b200.dist.bootstrap_sharded all-reduces them).
+    fit_fn(R_batch) -> closed graphs [n, S, S] replaces the device searches in CPU tests."""
     cx, own = _ctx(D, pert)
     try:
         k = len(x["comp"])
         post = getAffinity(x["probs"], mw=x["mw"], logtype=logtype, complete=complete)
         R = doMean(cx, post)                                   # [k, E, S]: rowsums of t(t(data) * post[i, ]) per S-gene
         R = R[None] if R.ndim == 2 else R
-        E = cx.E
-        ne = int(np.ceil(p * E))
-        rng = np.random.default_rng(seed)
-        idx = rng.integers(0, E, size=(k, size, ne))           # sample(seq_len(nrow), ceiling(p*nrow), replace = TRUE)
-        support = np.zeros((k, cx.S, cx.S))
-        for i in range(k):
-            for j0 in range(0, size, chunk):
-                sel = idx[i, j0:j0 + chunk]
-                fits = nem_greedy(R[i][sel], None)             # [n, ne, S] searches from the empty start
-                support[i] += transitive_closure(fits["adj"]).sum(0)
-        return support / size, idx
+        return _bootstrap_core(R, k, cx.S, size, p, seed, chunk, part, fit_fn)
     finally:
         if own:
             cx.close()
+
+
+def _bootstrap_core(R, k, S, size, p, seed, chunk, part, fit_fn):
+    E = R.shape[1]
+    ne = int(np.ceil(p * E))
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, E, size=(k, size, ne))               # sample(seq_len(nrow), ceiling(p*nrow), replace = TRUE)
+    mine = np.arange(part[0], size, part[1])
+    support = np.zeros((k, S, S))
+    if fit_fn is None:
+        def fit_fn(Rb):
+            return transitive_closure(nem_greedy(Rb, None)["adj"])      # [n, ne, S] searches from the empty start
+    for i in range(k):
+        for j0 in range(0, len(mine), chunk):
+            sel = idx[i, mine[j0:j0 + chunk]]
+            if len(sel):
+                support[i] += np.asarray(fit_fn(R[i][sel])).sum(0)
+    return support / size, idx
 
 
 def mnemk(D, pert=None, ks=(1, 2, 3, 4, 5), **kw):

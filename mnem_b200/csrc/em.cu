@@ -584,7 +584,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                              int32_t *best_out, mnemcu_em_stats *stats_out)
 {
     MN_ARG(cx && init_phi && opts && adj_out && theta_out && mw_out && ll_out && n_iter_out && best_out, "NULL pointer");
-    MN_ARG(starts >= 1 && k >= 2 && k <= 20, "starts must be positive and k in 2..20 (k = 1 is nem() + getProbs)");
+    MN_ARG(starts >= 1 && k >= 2 && k <= MNEMCU_MAX_K, "starts must be positive and k in 2..32 (k = 1 is nem() + getProbs)");
     MN_ARG(opts->max_trace >= 1 || !lls, "max_trace must be positive");
     const int E = cx->E, C = cx->C, S = cx->S;
     // EM starts per pass over D.  Default: as many as give k * B <= 30 pairs.  Up to 20 pairs the two streaming kernels are

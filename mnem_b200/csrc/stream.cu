@@ -125,10 +125,15 @@ int launch_estep(const mnemcu_ctx *cx, const uint32_t *maskT, int M, const PairP
     // Measured at 30 pairs, cfg5 (16 GB per pass): one warp with 60 accumulators 4.58 ms; two warps of 15 pairs 4.25 ms;
     // THREE warps of 10 pairs 3.94 ms (85 registers, 24 warps per SM; 4 x 8: 4.45 ms).  At that point the kernel is at
     // 82 % of the FP64 add rate (30 x E x C predicated DADDs per pass), which binds before HBM does.
-    int mtmax = M <= 20 ? 20 : 11;
-    if (const char *e = getenv("MNEMCU_ESTEP_MT")) mtmax = std::max(1, std::min(20, atoi(e)));     // experiments
-    const int groups = (M + mtmax - 1) / mtmax;
-    const int MT = (M + groups - 1) / groups;
+    // 25 pairs: two warps of 13 pairs 3.76 ms, three warps of 9 pairs 4.72 ms (the 9-pair instantiation schedules badly).
+    int groups = M <= 20 ? 1 : (M <= 26 ? 2 : 3);
+    int MT = (M + groups - 1) / groups;
+    if (groups == 3) MT = std::max(MT, 10);
+    if (const char *e = getenv("MNEMCU_ESTEP_MT")) {                                    // experiments
+        MT = std::max(1, std::min(20, atoi(e)));
+        groups = (M + MT - 1) / MT;
+        MT = (M + groups - 1) / groups;
+    }
     MN_ARG(groups <= 3, "E-step: at most three warps share a cell block");       // 3 groups x 4 E-gene ranges = 384 threads
     // Few blocks (small C): split the E-gene range over up to 4 warps so that every SM still has loads in flight.  The split
     // changes the ORDER of a cell's sum (ranges are summed separately and then added in ascending order), so it must depend

@@ -146,3 +146,27 @@ def mnemk_sharded(cx, ks, starts, seed=0, phi=None, complete=False, logtype=2, b
         lls[k] = f["ll"]
     kb = min(ics, key=lambda q_: ics[q_])
     return dict(k=kb, ics=ics, lls=lls, fits=fits, best=fits[kb], taken={k: list(local[k]["my"]) for k in ks})
+
+
+def bootstrap_sharded(x, cx, size=1000, p=1.0, logtype=2, complete=False, seed=0, device=None, R=None, fit_fn=None):
+    """bootstrap() (R/mnems.r:2348-2369) with the `size` resamples dealt round-robin to the ranks: every rank draws the SAME
+    seeded row samples, fits its share as one batch of device searches per component and the closure counts are summed
+    by one all_reduce of k * S * S doubles.  Returns (support [k, S, S], idx) on every rank -- equal to the single-process
+    result (the counts are small integers: their sum is exact in any order).
+    R / fit_fn: collapsed data [k, E, S] and a replacement for the device searches (CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import api
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    part = (dist.get_rank(), dist.get_world_size()) if on else (0, 1)
+    if R is None:
+        sup, idx = api.bootstrap(x, cx, size=size, p=p, logtype=logtype, complete=complete, seed=seed, part=part)
+    else:
+        R = np.asarray(R)
+        sup, idx = api._bootstrap_core(R, R.shape[0], R.shape[2], size, p, seed, 256, part, fit_fn)
+    if on:
+        t = torch.as_tensor(sup * size, dtype=torch.float64, device=device)      # integer counts
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        sup = t.cpu().numpy() / size
+    return sup, idx

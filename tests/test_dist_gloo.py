@@ -203,3 +203,47 @@ def test_two_rank_mnemk_picks_the_same_k_and_fits_as_one_process():
         assert o["k"] == one["k"] and o["ics"] == one["ics"] and o["lls"] == one["lls"] and o["adj"] == one["adj"]
     assert two[0]["owners"] == two[1]["owners"]
     assert two[0]["n_fitted"] + two[1]["n_fitted"] == 1 + 3 + 3 and min(o["n_fitted"] for o in two) >= 1   # spread
+
+
+# bootstrap(): the resamples dealt to the ranks, closure counts all-reduced
+WORKER_BOOT = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+import oracle as orc
+from mnem_b200 import dist as mdist
+world = int(sys.argv[2])
+if world > 1:
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=world)
+rng = np.random.default_rng(5)
+k, E, S = 2, 40, 5
+R = rng.normal(size=(k, E, S)) * 2
+def fit_fn(Rb):                              # the CPU oracle stands in for the batch of device searches
+    return np.stack([orc.mytc(orc.nem_greedy(r, None)["adj"]) for r in Rb])
+sup, idx = mdist.bootstrap_sharded(None, None, size=23, p=0.8, seed=4, R=R, fit_fn=fit_fn)
+print(json.dumps(dict(sup=sup.tolist(), idx_sum=int(idx.sum()))))
+if world > 1:
+    dist.destroy_process_group()
+"""
+
+
+def test_two_rank_bootstrap_equals_one_process():
+    import json
+    port = _free_port()
+    src = WORKER_BOOT % dict(root=ROOT, port=port)
+
+    def run(world):
+        procs = [subprocess.Popen([sys.executable, "-c", src, str(r), str(world)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.PIPE, text=True) for r in range(world)]
+        outs = []
+        for p in procs:
+            o, e = p.communicate(timeout=600)
+            assert p.returncode == 0, e[-3000:]
+            outs.append(json.loads(o.strip().splitlines()[-1]))
+        return outs
+    one = run(1)[0]
+    two = run(2)
+    assert two[0] == two[1] == one
+    sup = np.array(one["sup"])
+    assert sup.shape == (2, 5, 5) and (np.diagonal(sup, axis1=1, axis2=2) == 1.0).all() and sup.min() >= 0 and sup.max() <= 1

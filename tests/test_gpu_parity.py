@@ -630,3 +630,17 @@ def test_dictionary_overflow_falls_back_to_the_generic_scorer(monkeypatch):
         assert np.array_equal(capped["adj"][q], ref["adj"]) and np.array_equal(capped["subtopo"][q], ref["theta"])
         assert np.array_equal(capped["adj"][q], normal["adj"][q]) and capped["n_iter"][q] == normal["n_iter"][q]
         assert abs(capped["score"][q] - ref["score"]) <= 1e-9 * abs(ref["score"])
+
+
+def test_em_with_many_components():
+    """k up to MNEMCU_MAX_K = 32 components (one start then fills a whole pass): k = 24 replayed through the oracle."""
+    sim = simdata.make_config(dict(S=5, Egenes=4, C=2400, mw=[1 / 24] * 24, k=24, starts=2, uninform=0), seed=31)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(5, 24, 2, seed=8)
+    with mb.Context(D, sim["pert"]) as cx:
+        r = mb.em_run(cx, init, tape=True)
+    for s in range(2):
+        o = orc.replay_start(D, sim["pert"], 5, init[s], r["tape"][s])
+        assert not o["diverged"], o["first_hard"]
+        assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(r["theta"][s], o["theta"])
+        assert abs(r["ll"][s] - o["ll"]) <= 1e-9 * abs(o["ll"])
