@@ -337,7 +337,7 @@ def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", st
 
 
 def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e-13, tol_ll=1e-12, max_trace=256,
-                 affinity=0, acc="ld", mw=None):
+                 affinity=0, acc="ld", mw=None, max_iter_guard=0):
     """One EM start replayed against the decision tape of a device fit (mnem_b200.api.parse_tape(...)[start]).
 
     The oracle runs the start in its own arithmetic and takes the tape's choice wherever its own decision differs by
@@ -384,7 +384,8 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     mw = np.zeros(k)
     tr = [np.zeros(max_trace) for _ in range(4)]
     info = EmInfo()
-    o = EmOpts(max_trace, int(bool(complete)), logtype, 0, 0, 0, int(affinity), _d(mw0) if mw0 is not None else None)
+    o = EmOpts(max_trace, int(bool(complete)), logtype, 0, int(max_iter_guard), 0, int(affinity),
+               _d(mw0) if mw0 is not None else None)
     lib(acc).orc_em_start_advised(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), C.byref(adv), _u8(adj), _i32(th),
                                   _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
     n = info.n_iter

@@ -297,14 +297,20 @@ def test_em_small_gaussian(batch):
 
 def test_em_many_pairs_few_cells():
     """20 and 30 (start, component) pairs per pass on a small matrix: the E-step then splits the E-gene range over up to
-    8 warps of a CTA and combines their partial sums through shared memory (up to 112 KB).  With k = 5 on 1200 cells the
-    greedy decisions are rounding-level ties (oracle margin 1e-16), so the fit is pinned against the one-start-per-pass
-    run (bit-identical: a start's result does not depend on what shares its passes) and the E-step against the oracle."""
+    4 warps of a CTA and combines their partial sums through shared memory.  With k = 5 on 1200 cells some greedy
+    decisions are rounding-level ties (oracle margin 1e-16), so the fit is REPLAYED through the oracle (every decision
+    equal or within 1e-13), and it must not depend on what shares its passes (bit-identical for batch 1, 4, 6)."""
     sim = simdata.make_config(dict(S=8, Egenes=40, C=1200, mw=[0.2] * 5, k=5, starts=6, uninform=0), seed=31)
     D = simdata.host_data(sim) + np.random.default_rng(7).normal(size=(sim["E"], sim["C"])) * 0.5
     init = simdata.init_phi(8, 5, 6, seed=8)
     with mb.Context(D, sim["pert"]) as cx:
-        one = mb.em_run(cx, init, complete=True, batch=1, max_iter_guard=12)
+        one = mb.em_run(cx, init, complete=True, batch=1, max_iter_guard=12, tape=True)
+        for s in range(6):
+            o = orc.replay_start(D, sim["pert"], 8, init[s], one["tape"][s], complete=True, max_iter_guard=12)
+            assert not o["diverged"], o["first_hard"]
+            assert np.array_equal(one["adj"][s], o["adj"]) and np.array_equal(one["theta"][s], o["theta"])
+            assert one["n_iter"][s] == o["n_iter"] and abs(one["ll"][s] - o["ll"]) <= RTOL * abs(o["ll"])
+            close(one["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
         for batch in (4, 6):
             r = mb.em_run(cx, init, complete=True, batch=batch, max_iter_guard=12)
             for key in ("adj", "theta", "ll", "mw", "n_iter", "probs"):
