@@ -91,7 +91,7 @@ __global__ void matmul_kernel(const double *__restrict__ A, const double *__rest
 
 using namespace mn;
 
-extern "C" int mnemcu_version(void) { return 100; }
+extern "C" int mnemcu_version(void) { return 200; }   // 2.0: em_opts gained tape, probs_mode, mw
 extern "C" const char *mnemcu_last_error(void) { return g_err; }
 extern "C" int64_t mnemcu_launch_count(void) { return (int64_t)g_launches.load(); }
 extern "C" int mnemcu_device_count(int *n)

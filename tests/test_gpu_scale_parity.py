@@ -50,7 +50,10 @@ def run_case(name, batch=0, starts=None):
     import oracle as orc
     from mnem_b200 import simdata
     sim, init = msg.build_case(name)
-    if starts:
+    if starts and starts > init.shape[0]:      # more starts than the golden case holds: the same seeded sequence, longer
+        init = simdata.init_phi(sim["S"], sim["k"], starts, seed=2000 + msg.CASES[name][0])
+        assert np.array_equal(init[:len(msg.build_case(name)[1])], msg.build_case(name)[1])
+    elif starts:
         init = init[:starts]
     nst, k = init.shape[:2]
     S, E = sim["S"], sim["E"]
@@ -144,6 +147,7 @@ def test_data_passes_match_oracle_at_scale(name):
         assert np.max(np.abs(R[rows] - g["dm_R"]) / np.maximum(np.abs(g["dm_R"]), scale[None, :])) <= RTOL
 
 
-if __name__ == "__main__":
+if __name__ == "__main__":           # python tests/test_gpu_scale_parity.py cfg5_full[:starts] ...
     for c in (sys.argv[1:] or CASES):
-        print(json.dumps(run_case(c)))
+        name, _, n = c.partition(":")
+        print(json.dumps(run_case(name, starts=int(n) if n else None)))
