@@ -377,7 +377,7 @@ def run_ours(args):
             # N > 1: every rank uploads 1/N of the columns from ITS host copy and the slices are exchanged over NVLink
             # (one NCCL all-gather) instead of pushing N full copies of D through PCIe and the host memory bus
             per = -(-Cn // world)
-            for i in range(max(1, min(args.warmup, 1)) + max(1, min(args.steps, 2))):
+            for i in range(max(1, min(args.warmup, 1)) + int(os.environ.get("MNEM_E2E_STEPS", max(1, min(args.steps, 2))))):
                 queue = mdist.StartQueue(sim["starts"])
                 barrier()
                 t0 = time.time()
@@ -416,6 +416,7 @@ def run_ours(args):
                    "seconds_per_step": float(np.mean(times)), "steps": len(times), "seconds_each": [float(x) for x in times],
                    "clocks": sampler2.stop(),
                    "seconds_upload_and_layout_rank0": float(np.mean([p_[0] for p_ in parts])),
+                   "seconds_upload_each_rank0": [float(p_[0]) for p_ in parts],
                    "seconds_em_wall_rank0": float(np.mean([p_[1] for p_ in parts])),
                    "seconds_em_device_rank0": float(np.mean([p_[2] for p_ in parts]))}
             del hnp, Dh
