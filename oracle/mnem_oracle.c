@@ -9,11 +9,23 @@
  * reference cannot be executed in this environment (no R, no Rcpp/RcppEigen headers), so every function
  * below cites the reference lines it follows (paths relative to /root/reference).
  *
- * PARITY PINNING.  Pinned by reference-owned vectors: getLL/getAffinity against the 9 fitted objects of
- * data/app.rda that carry `probs` (tests/golden/app_rda_ll.npz), transitive.closure against the roxygen
- * example R/mnems.r:546-548.  The data contraction, doMean, scoreAdj and the greedy search have NO
- * reference-owned expected values (the reference's only unit test is an RNG-dependent property):
- * for those rows parity is UNPINNED and the oracle is a reading of the source.
+ * PARITY PINNING.  Pinned by the reference itself:
+ *   - the five routines of src/mm.cpp (transClose_W/_Ins/_Del, maxCol_row, eigenMapMatMult's marshalling) against the
+ *     reference's own file compiled UNMODIFIED into oracle/_ref/libmm_ref.so (oracle/Makefile, stub headers in
+ *     oracle/rstub/; tests/test_ref_mm.py);
+ *   - getLL / getAffinity against the 9 fitted objects of data/app.rda that carry `probs`
+ *     (tests/golden/app_rda_golden.npz); transitive.reduction against the 45 shipped component graphs (they are its
+ *     fixed points, R/mnems.r:374); getIC replayed on the shipped fits; transitive.closure against the roxygen example
+ *     R/mnems.r:546-548.
+ * The data contraction, doMean, scoreAdj's sum and the greedy search have NO reference-owned expected values (the
+ * reference's only unit test is an RNG-dependent property and R cannot be run here): for those rows parity is
+ * UNPINNED and the oracle is a reading of the source, cross-checked by an independent NumPy reading
+ * (tests/test_oracle_selfcheck.py).
+ *
+ * Besides the plain restatement the file holds two harness aids (see "Decision replay"): a recorder that writes the
+ * decisions of an oracle fit as a tape, and a replay that follows the tape of a device fit wherever the oracle's own
+ * decision differs by less than the rounding error -- the way fits are compared at sizes where the reference's
+ * decisions are at rounding level.
  *
  * Numerics.  R's sum/colSums/rowSums accumulate in `long double` (80-bit x87 on x86-64 builds) and round
  * once; `%*%` (reference BLAS) and Eigen's GEBP (SSE2, no FMA, one accumulator per output, depth <= 100)
