@@ -32,6 +32,7 @@ constexpr int kDictThreads = 512;
 constexpr int kChains = 4;         // most independent iteration chains of the host-driven loop (see search_run_host)
 constexpr int kUP = 8;             // insertion sources per work item of the dictionary scorer
 constexpr int kMaxChunk = 4;       // most row tiles per task of the device-resident loop
+constexpr unsigned long long kStallNs = 5000000000ull;   // watchdog of the device-resident loop: 5 s without a task
 
 // Device view of a search workspace: one by-value kernel argument instead of twenty pointers.
 struct SearchDev {
@@ -1003,7 +1004,11 @@ __device__ __forceinline__ void publish_search(const SearchDev &d, int q)
     for (int i = 0; i < nch; ++i)
         d.ring[(r + i) & d.ring_mask] = task_encode(q, i * chunk, min(chunk, d.ntiles - i * chunk));
     __threadfence();
-    while (atomicCAS(&d.qctl[2], r, r + (unsigned)nch) != r) __nanosleep(40);       // commit in reservation order
+    unsigned spins = 0;
+    while (atomicCAS(&d.qctl[2], r, r + (unsigned)nch) != r) {                      // commit in reservation order
+        __nanosleep(40);
+        if (*reinterpret_cast<volatile unsigned *>(&d.qctl[3]) || ++spins > (1u << 27)) break;   // aborted run: do not wait
+    }
 }
 
 __global__ void search_seed_kernel(SearchDev d, int n)
@@ -1029,11 +1034,15 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
     __syncthreads();
     unsigned long long t_begin = 0ull, t_task = 0ull, busy = 0ull, t_fin = 0ull, t_gen = 0ull, n_closed = 0ull;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+    bool first = true;
     while (true) {
         if (tid == 0) {
-            if (t_task) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); busy += now - t_task; }
+            if (!first) { unsigned long long now; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now)); busy += now - t_task; }
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_task));          // start of this wait (watchdog reference)
+            first = false;
             const unsigned idx = atomicAdd(&d.qctl[0], 1u);
             unsigned long long task = ~0ull;
+            unsigned spins = 0;
             while (true) {
                 if (*reinterpret_cast<volatile unsigned *>(&d.qctl[3])) break;      // every search has ended (or the run was aborted)
                 const unsigned committed = *reinterpret_cast<volatile unsigned *>(&d.qctl[2]);
@@ -1043,6 +1052,16 @@ __global__ void __launch_bounds__(kDictThreads, 1) search_persistent_kernel(Sear
                     break;
                 }
                 __nanosleep(100);
+                if ((++spins & 4095u) == 0u) {
+                    // watchdog: the longest legitimate wait is one iteration of one search (well under a millisecond); a
+                    // CTA that has seen no task for kStallNs aborts the run instead of spinning on the GPU for ever
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (now - t_task > kStallNs && t_task != 0ull) {
+                        atomicOr(d.overflow, 4);
+                        *reinterpret_cast<volatile unsigned *>(&d.qctl[3]) = 1u;
+                    }
+                }
             }
             s_task = task;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_task));
@@ -1419,6 +1438,7 @@ static int search_check_flags(SearchBatch *sb, int32_t flags)
     if (flags & 1) return set_err(MNEMCU_ERR_NOMEM, "mask dictionary overflow (more than %d distinct columns)", sb->dcap);
     if (flags & 2)
         return set_err(MNEMCU_ERR_ARG, "a greedy search did not converge within %d moves", 4 * sb->S * sb->S + 16);
+    if (flags & 4) return set_err(MNEMCU_ERR_CUDA, "the device-resident search loop stalled (watchdog)");
     return 0;
 }
 
