@@ -172,6 +172,9 @@ typedef struct {
                           * returns (R/mnems.r:2222-2240) without keeping k x C doubles per start on the host */
     const double *mw;    /* mnem(mw =): k initial mixture weights of every start (R/mnems.r:1771-1773, handed to the first
                           * getProbs :1906-1913); NULL = rep(1, k)/k */
+    int nullcomp;        /* mnem(nullcomp = TRUE): the LAST of the k components is the null component (R/mnems.r:1832-1834,
+                          * 1894-1900): its graph is empty, its theta 0, its log ratios 0 (R/mnems_low.r:607-608) and it has
+                          * no M-step (R/mnems.r:2012, 2076-2080); the last graph of every start in init_phi is ignored */
 } mnemcu_em_opts;
 
 typedef struct {

@@ -106,6 +106,7 @@ struct Engine {
     // N-GPU job spends a good part of its time there -- streams 5 pairs at HBM speed instead of 30 at the FP64 limit.
     int Be = 0;
     int Me() const { return k * Be; }
+    int nullcomp = 0;             // mnem(nullcomp = TRUE): component k-1 of every slot is the null component
     double logtype = 2.0;
     cudaStream_t st = nullptr;
     std::vector<Slot> slots;
@@ -307,6 +308,9 @@ struct Engine {
         for (int b : list)
             MN_CU(cudaMemcpyAsync(d_theta.p + (size_t)b * k * cx->E, d_theta_tmp.p + (size_t)b * k * cx->E,
                                   sizeof(int32_t) * (size_t)k * cx->E, cudaMemcpyDeviceToDevice, st));
+        if (nullcomp)                                                    // tmp <- 0 for the null component, R/mnems_low.r:607-608
+            for (int b : list)
+                MN_CU(cudaMemsetAsync(d_theta.p + ((size_t)b * k + k - 1) * cx->E, 0, sizeof(int32_t) * cx->E, st));
         if (tape_on) MN_TRY(tape_theta(list, 1));
         return 0;
     }
@@ -420,7 +424,7 @@ struct Engine {
         if (list.empty()) return 0;
         std::vector<int32_t> pairs, ht(M, 0);
         for (int b : list)
-            for (int i = 0; i < k; ++i) pairs.push_back(b * k + i);
+            for (int i = 0; i < k - (nullcomp ? 1 : 0); ++i) pairs.push_back(b * k + i);      // no M-step for a null component
         for (int b = 0; b < B; ++b)
             for (int i = 0; i < k; ++i) ht[b * k + i] = slots[b].have_theta ? 1 : 0;
         const int np = (int)pairs.size();
@@ -598,6 +602,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     Engine en;
     MN_TRY(en.init(cx, k, B, opts->complete, opts->logtype, true));
     en.affinity = opts->affinity;
+    en.nullcomp = opts->nullcomp ? 1 : 0;
     MN_ARG(opts->tape_cap >= 0 && (opts->tape || opts->tape_cap == 0), "tape_cap without a tape buffer");
     if (opts->tape) { en.tape_on = true; MN_TRY(search_enable_tape(en.sb)); }
     cudaStream_t st = en.st;
@@ -679,6 +684,10 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         s.start = sidx;
         s.phase = 0; s.inner = 0; s.cur = 0; s.best = 0; s.nw = 1;
         MN_TRY(en.load_graphs(b, init_phi + (size_t)sidx * kSS));
+        if (en.nullcomp) {                                                        // res1[[k]]$adj <- adj * 0, subtopo * 0  :1894-1898
+            MN_CU(cudaMemsetAsync(en.d_res1.p + ((size_t)b * k + k - 1) * 32, 0, sizeof(uint32_t) * 32, st));
+            MN_CU(cudaMemsetAsync(en.d_theta.p + ((size_t)b * k + k - 1) * E, 0, sizeof(int32_t) * E, st));
+        }
         MN_CU(cudaMemsetAsync(en.buf(b, 0), 0, sizeof(double) * en.kCp, st));      // probs <- matrix(0, k, C)  :1905
         MN_CU(cudaMemsetAsync(en.flag(b, 0), 0, sizeof(int32_t), st));
         MN_TRY(en.set_mw(b, opts->mw));                                           // mw <- rep(1, k)/k unless given  :1771-1773

@@ -24,7 +24,7 @@ class NemInfo(C.Structure):
 
 class EmOpts(C.Structure):
     _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
-                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int), ("mw0", c_dp)]
+                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int), ("mw0", c_dp), ("nullcomp", C.c_int)]
 
 
 class EmInfo(C.Structure):
@@ -243,7 +243,7 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 
 # ---- EM --------------------------------------------------------------------------------------------------
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
-            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None):
+            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None, nullcomp=False):
     """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
     mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None       # mnem(mw =), R/mnems.r:1771-1773
     D = _f(D)
@@ -259,7 +259,7 @@ def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faith
     tr = [np.zeros((starts, max_trace)) for _ in range(4)]
     infos = (EmInfo * starts)()
     o = EmOpts(max_trace, int(bool(complete)), logtype, int(faithful_cost), max_iter_guard, int(noise_mode), int(affinity),
-               _d(mw0) if mw0 is not None else None)
+               _d(mw0) if mw0 is not None else None, int(bool(nullcomp)))
     best = lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, starts, _u8(pb), C.byref(o), int(nthreads), _u8(adj),
                                 _i32(theta), _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
     adj = _ungraphs(adj, starts * k, S).reshape(starts, k, S, S)
@@ -337,7 +337,7 @@ def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", st
 
 
 def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e-13, tol_ll=1e-12, max_trace=256,
-                 affinity=0, acc="ld", mw=None, max_iter_guard=0):
+                 affinity=0, acc="ld", mw=None, max_iter_guard=0, nullcomp=False):
     """One EM start replayed against the decision tape of a device fit (mnem_b200.api.parse_tape(...)[start]).
 
     The oracle runs the start in its own arithmetic and takes the tape's choice wherever its own decision differs by
@@ -360,12 +360,12 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     for it in range(n_em):
         for i in range(k):
             for j in range(2):
-                m = tape["searches"][(it, i, j)]
+                m = tape["searches"].get((it, i, j), np.zeros((0, S), dtype=np.uint32))      # no search: the null component
                 rows.append(m.reshape(-1, S))
                 q = (it * k + i) * 2 + j
                 off[q + 1] = off[q] + len(m)
     rows = np.ascontiguousarray(np.concatenate(rows + [np.zeros((1, S), dtype=np.uint32)]), dtype=np.uint32)
-    pick = np.array([tape["pick"][(it, i)] for it in range(n_em) for i in range(k)] + [0], dtype=np.int32)
+    pick = np.array([tape["pick"].get((it, i), 0) for it in range(n_em) for i in range(k)] + [0], dtype=np.int32)
     theta = np.ascontiguousarray(np.stack([tape["theta"][it] for it in range(n_em)] + [np.zeros((k, E), dtype=np.int32)]),
                                  dtype=np.int32)
     accept = np.array([tape["accept"][it] for it in range(n_em)] + [0], dtype=np.int32)
@@ -385,7 +385,7 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     tr = [np.zeros(max_trace) for _ in range(4)]
     info = EmInfo()
     o = EmOpts(max_trace, int(bool(complete)), logtype, 0, int(max_iter_guard), 0, int(affinity),
-               _d(mw0) if mw0 is not None else None)
+               _d(mw0) if mw0 is not None else None, int(bool(nullcomp)))
     lib(acc).orc_em_start_advised(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), C.byref(adv), _u8(adj), _i32(th),
                                   _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
     n = info.n_iter

@@ -553,6 +553,7 @@ static __thread const uint32_t *g_adv_rows = NULL;  /* moves of the search about
 static __thread int g_adv_nmoves = 0;
 static __thread double *g_adv_W = NULL;             /* if set, nem_greedy leaves the subweights of its final graph here */
 static __thread int g_adv_probs = 0;                /* the next getProbs call is the theta-free one on tape */
+static __thread int g_nullcomp = 0;                 /* getProbs(nullcomp = TRUE): the last component's log ratios are 0 */
 
 /* The oracle can also WRITE a tape of its own fit, in the device's record format (include/mnemcu.h).  Used to test the
  * replay on the CPU: the tape of the double-accumulator build replayed by the long-double build is the same situation
@@ -871,8 +872,9 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
                 }
                 for (int i = 0; i < k; i++) {
                     orc_max_col_row(Wall + (size_t)i * (S + 1) * E, E, S + 1, th + (size_t)i * E);   /* values 1..S+1 */
-                    if (adv_here) adv_init_theta(Wall + (size_t)i * (S + 1) * E, E, S, th + (size_t)i * E,
-                                                 g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
+                    if (adv_here && !(g_nullcomp && i == k - 1))
+                        adv_init_theta(Wall + (size_t)i * (S + 1) * E, E, S, th + (size_t)i * E,
+                                       g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
                 }
                 free(Wall);
             } else {
@@ -915,7 +917,8 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
                             }
                     }
                     orc_max_col_row(Wtmp, E, S + 1, thi);                         /* values 1..S+1 */
-                    if (adv_here) adv_init_theta(Wtmp, E, S, thi, g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
+                    if (adv_here && !(g_nullcomp && i == k - 1))
+                        adv_init_theta(Wtmp, E, S, thi, g_adv->init_theta + ((size_t)count * k + i) * E, count, i);
                 } else {
                     for (int e = 0; e < E; e++) { int t = theta[(size_t)i * E + e]; thi[e] = t == 0 ? S + 1 : t; }  /* :621-622 */
                 }
@@ -934,6 +937,10 @@ double orc_get_probs_a(const double *D, int E, int C, const int32_t *pert, int S
                 }
             }
             have0 = 1;
+        }
+        if (g_nullcomp) {                                                        /* :607-608, 633: tmp <- 0 */
+            for (int c = 0; c < C; c++) probs0[(k - 1) + (size_t)c * k] = 0.0;
+            for (int e = 0; e < E; e++) th[(size_t)(k - 1) * E + e] = S + 1;
         }
         if (rec_probs) rec_theta(1, count, th, (size_t)k * E, S, 1);
         double ll0 = orc_get_ll(probs0, k, C, mw, complete, logtype);            /* :643 */
@@ -983,6 +990,8 @@ typedef struct {
                              * legitimate outcomes can be enumerated */
     int affinity;           /* mnem(affinity =): 0 soft responsibilities, 1 hard assignments in every getAffinity call */
     const double *mw0;      /* mnem(mw =): initial mixture weights (R/mnems.r:1771-1773); NULL = rep(1, k)/k */
+    int nullcomp;           /* mnem(nullcomp = TRUE): the LAST of the k components is the null component (R/mnems.r:1832-1834,
+                             * 1894-1900): empty graph, theta 0, log ratios 0 (R/mnems_low.r:607-608), no M-step (:2012, 2076-2080) */
 } orc_em_opts;
 
 typedef struct {
@@ -1045,6 +1054,8 @@ void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, in
     double mw[256], bestmw[256], mwnew[256];
     for (int i = 0; i < k; i++) mw[i] = o->mw0 ? o->mw0[i] : 1.0 / k;             /* R/mnems.r:1771-1773 */
     memcpy(res1_adj, init_phi, (size_t)k * SS);                                   /* :1885-1893 */
+    if (o->nullcomp) memset(res1_adj + (size_t)(k - 1) * SS, 0, SS);              /* :1894-1898 */
+    g_nullcomp = o->nullcomp;
     memset(res1_th, 0, sizeof(int32_t) * (size_t)k * E);
     memset(probs, 0, sizeof(double) * kc);                                        /* :1905 */
     const int affinity = o->affinity;
@@ -1108,6 +1119,14 @@ void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, in
             do_mean_multi(D, E, C, pert, S, k, post, (size_t)k, Rall);
         }
         for (int i = 0; i < k; i++) {                                             /* :1976-2086 */
+            if (o->nullcomp && i == k - 1) {                                      /* :2012, 2076-2080: no M-step, adj * 0, subtopo * 0 */
+                memset(res_adj + (size_t)i * SS, 0, SS);
+                memset(res_th + (size_t)i * E, 0, sizeof(int32_t) * E);
+                for (int q = 0; q < SS; q++) edgechange += abs(0 - (int)res1_adj[(size_t)i * SS + q]);
+                if (have_res1_theta)
+                    for (int e = 0; e < E; e++) thetachange += 0 != res1_th[(size_t)i * E + e];
+                continue;
+            }
             uint8_t a0[ORC_MAXS * ORC_MAXS], a1[ORC_MAXS * ORC_MAXS];
             int32_t *t0 = (int32_t *)malloc(sizeof(int32_t) * E), *t1 = (int32_t *)malloc(sizeof(int32_t) * E);
             orc_nem_info i0, i1;
@@ -1233,7 +1252,7 @@ void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, in
     free(probs); free(probsold); free(newp); free(post); free(scratch); free(gam); free(Rk); free(Rall);
     free(res1_adj); free(res_adj); free(res1_th); free(res_th); free(bestadj); free(bestth); free(bestprobs);
     free(Wfin0); free(Wfin1);
-    g_adv = NULL; g_adv_probs = 0;
+    g_adv = NULL; g_adv_probs = 0; g_nullcomp = 0;
 }
 int orc_advice_size(void) { return (int)sizeof(orc_advice); }
 

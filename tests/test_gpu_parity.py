@@ -650,3 +650,26 @@ def test_em_with_many_components():
         assert not o["diverged"], o["first_hard"]
         assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(r["theta"][s], o["theta"])
         assert abs(r["ll"][s] - o["ll"]) <= 1e-9 * abs(o["ll"])
+
+
+def test_null_component():
+    """mnem(nullcomp = TRUE) (R/mnems.r:1832-1834, 1894-1900, 2012, 2076-2080; R/mnems_low.r:607-608): component k + 1 has
+    an empty graph, theta 0 and log ratios 0, and takes part in the mixture only.  Replayed through the oracle."""
+    sim = simdata.make_config(dict(S=6, Egenes=8, C=3000, mw=[0.5, 0.5], k=2, starts=3, uninform=2), seed=41)
+    D = simdata.host_data(sim)
+    D[:, ::7] = np.random.default_rng(3).normal(size=D[:, ::7].shape)          # cells no component explains: the null one takes them
+    init2 = simdata.init_phi(6, 2, 3, seed=5)
+    fit = mb.mnem(D, sim["pert"], phi=init2, nullcomp=True)
+    assert len(fit["comp"]) == 3 and not fit["comp"][2]["phi"].any() and not fit["comp"][2]["theta"].any()
+    assert np.all(fit["probs"][2] == 0.0) and fit["mw"][2] > 1e-4
+    init3 = np.concatenate([init2, np.zeros_like(init2[:, :1])], axis=1)
+    with mb.Context(D, sim["pert"]) as cx:
+        r = mb.em_run(cx, init3, nullcomp=True, tape=True)
+    for s in range(3):
+        o = orc.replay_start(D, sim["pert"], 6, init3[s], r["tape"][s], nullcomp=True)
+        assert not o["diverged"], o["first_hard"]
+        assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(r["theta"][s], o["theta"])
+        assert r["n_iter"][s] == o["n_iter"] and abs(r["ll"][s] - o["ll"]) <= RTOL * abs(o["ll"])
+        close(r["mw"][s], o["mw"], rtol=RTOL)
+        close(r["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
+    assert r["best"] == fit["best_start"] and np.array_equal(r["adj"][r["best"]][2], np.zeros((6, 6)))

@@ -124,3 +124,21 @@ def test_inner_threads_do_not_change_a_single_bit():
                 assert np.array_equal(x[key], y[key]), key
             for key in ("lls", "mwevo"):
                 assert all(np.array_equal(p, q) for p, q in zip(x[key], y[key])), key
+
+
+def test_null_component_of_the_oracle():
+    """mnem(nullcomp = TRUE): the last component keeps an empty graph, theta 0 and log ratios 0 (R/mnems_low.r:607-608,
+    R/mnems.r:2076-2080) and still receives mixture weight."""
+    import oracle as orc
+    from mnem_b200 import simdata
+    sim = simdata.make_config(dict(S=5, Egenes=6, C=900, mw=[0.5, 0.5], k=2, starts=2, uninform=0), seed=13)
+    D = simdata.host_data(sim)
+    D[:, ::5] = np.random.default_rng(1).normal(size=D[:, ::5].shape)
+    init = simdata.init_phi(5, 2, 2, seed=2)
+    init3 = np.concatenate([init, np.ones_like(init[:, :1])], axis=1)        # the last graph is ignored
+    r = orc.mnem_em(D, sim["pert"], 5, init3, nullcomp=True)
+    for s in range(2):
+        assert not r["adj"][s][2].any() and not r["theta"][s][2].any()
+        assert np.all(r["probs"][s][2] == 0.0) and 1e-4 < r["mw"][s][2] < 0.9
+    plain = orc.mnem_em(D, sim["pert"], 5, init3)
+    assert plain["adj"][0][2].any() or plain["theta"][0][2].any()
