@@ -127,7 +127,7 @@ def cpu_sample(sim, init, n_threads, cells, guard=1):
                 starts=len(ph))
 
 
-def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0):
+def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0, greedy_comps=None):
     """EM iterations/s of the CPU restatement for the FULL workload, from bounded component timings.
 
     Per start the reference spends (R/mnems.r:1905-1915, 1976-2108; the oracle's orc_em_start with faithful_cost):
@@ -156,16 +156,20 @@ def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0):
         t0 = time.time()
         R = [orc.do_mean(D, pert, S, post[i]) for i in range(k)]
         t["domean"] = (time.time() - t0) / k
+        # both restarts (empty start, previous graph) of the first `ng` components are timed; the searches do not depend on
+        # the number of cells, so a short step may time fewer of the 2k searches of an EM iteration (their mean is used)
+        ng = k if greedy_comps is None else max(1, min(k, greedy_comps))
         t0 = time.time()
-        fits = [orc.nem_greedy(R[i], None) for i in range(k)] + [orc.nem_greedy(R[i], phi[i]) for i in range(k)]
-        t["greedy"] = (time.time() - t0) / (2 * k)
+        fits = [orc.nem_greedy(R[i], None) for i in range(ng)] + [orc.nem_greedy(R[i], phi[i]) for i in range(ng)]
+        t["greedy"] = (time.time() - t0) / (2 * ng)
         nsc = sum(f["n_scored"] for f in fits)
-        adj = np.stack([f["adj"] for f in fits[:k]])
-        th = np.stack([f["theta"] for f in fits[:k]])
+        adj = np.stack([fits[i]["adj"] if i < ng else phi[i] for i in range(k)])
+        th = np.stack([fits[i]["theta"] if i < ng else g0["theta_used"][i] for i in range(k)])
         t0 = time.time()
         orc.get_probs(D, pert, S, adj, th, g0["probs"], g0["mw"], complete=sim["complete"], faithful_cost=True)
         t["estep"] = time.time() - t0
         t["scored"] = nsc
+        t["n_searches"] = 2 * ng
         return t
 
     t0 = time.time()
@@ -180,7 +184,8 @@ def cpu_extrapolated(sim, init, n_threads, cells, mean_iters, c0=0):
     value = n_threads * mean_iters / T
     return dict(value=float(value), seconds=wall, t_init_full=t_init, t_em_full=t_em, cells=c, starts=n_threads,
                 mean_iters=mean_iters,
-                cand_scores_per_s=float(sum(t["scored"] for t in ts) / max(1e-9, sum(2 * k * t["greedy"] for t in ts)) * n_threads),
+                cand_scores_per_s=float(sum(t["scored"] for t in ts) / max(1e-9, sum(t["n_searches"] * t["greedy"] for t in ts)) * n_threads),
+                seconds_greedy=float(np.mean([t["n_searches"] * t["greedy"] for t in ts])),
                 sample=("oracle port (C restatement of cbg-ethz/mnem 1.23.0, not R), %d start(s) concurrently, cells %d..%d of %d "
                         "(%.1f s): per start getProbs(theta=NULL) %.2f s, doMean %.3f s, getProbs(theta) %.2f s (each scaled by "
                         "%d/%d cells), nem_greedy %.2f s per search (independent of the cell count); redundant passes kept; "
@@ -215,13 +220,29 @@ def run_reference(args):
     except AttributeError:
         ncpu = os.cpu_count() or 1
     nthr = max(1, min(ncpu, sim["starts"]))
-    cells = args.cpu_cells or max(2000, sim["C"] // 32)
-    vals = []
-    for i in range(args.warmup + args.steps):
+    # Size of a step.  The whole run (W + K steps) should end within a few minutes whatever K is (the driver asks for 25
+    # steps): MNEM_REF_BUDGET_S seconds (default 300) are spread over the steps.  The first step takes a small slice and
+    # measures the cost per cell; the following steps take slices sized to the per-step budget, at most C / (W + K) cells so
+    # that the slices stay disjoint, at most C / 32.
+    n_steps = max(1, args.warmup + args.steps)
+    per_step = float(os.environ.get("MNEM_REF_BUDGET_S", "300")) / n_steps
+    cap = max(2000, min(sim["C"] // 32, sim["C"] // n_steps))
+    cells = args.cpu_cells or max(2000, min(cap, sim["C"] // 256))
+    few = per_step < 25.0                         # short steps time 2 of the 2k searches of an EM iteration
+    vals, c0 = [], 0
+    for i in range(n_steps):
         first = (i * nthr) % max(1, len(init) - nthr + 1)
-        r = cpu_extrapolated(sim, init[first:first + nthr], nthr, cells, MEAN_EM_ITERS.get(args.config, 10.0), c0=i * cells)
+        t0 = time.time()
+        r = cpu_extrapolated(sim, init[first:first + nthr], nthr, cells, MEAN_EM_ITERS.get(args.config, 10.0), c0=c0,
+                             greedy_comps=1 if few else None)
+        took = time.time() - t0
+        c0 += cells
+        r["cells_step"], r["seconds_step"] = cells, took
         if i >= args.warmup:
             vals.append(r)
+        if not args.cpu_cells:
+            per_cell = max(1e-9, (took - r["seconds_greedy"]) / cells)
+            cells = int(max(2000, min(cap, (per_step - r["seconds_greedy"]) / per_cell)))
     v = float(np.mean([x["value"] for x in vals]))
     sample = "%d timed steps on disjoint slices, the last: %s" % (len(vals), vals[-1]["sample"])
     line = {"impl": "reference", "metric": "em_iterations_per_s", "value": v, "unit": "EM iterations/s",
@@ -229,7 +250,8 @@ def run_reference(args):
             "ms_per_step": 1e3 * float(np.mean([x["seconds"] for x in vals])), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(args, sim, name),
-            "values_per_step": [x["value"] for x in vals],
+            "values_per_step": [x["value"] for x in vals], "cells_per_step": [x["cells_step"] for x in vals],
+            "seconds_per_step_wall": [x["seconds_step"] for x in vals],
             "cpu_baseline": {"value": v, "unit": "EM iterations/s", "cores": nthr, "kind": "port", "sample": sample},
             "cand_scores_per_s": float(np.mean([x["cand_scores_per_s"] for x in vals])),
             "e2e": {"value": v, "unit": "EM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
