@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 # (profiles/r2_bench_cfg*.json, "em_iters_per_step" / starts); the device's iteration counts are those of the oracle
 # on every start the oracle has replayed (tests/test_gpu_scale_parity.py: n_iter bit-exact).  bench.py's own
 # `cpu_baseline` leg (N = 1) does not use the table: it takes the mean of the fit it has just timed.
-MEAN_EM_ITERS = {1: 4.0, 2: 6.0, 3: 10.0, 4: 10.0, 5: 13.07}
+MEAN_EM_ITERS = {1: 4.0, 2: 5.3, 3: 11.98, 4: 10.0, 5: 13.07}
 
 
 def parse():
