@@ -175,6 +175,10 @@ typedef struct {
     int nullcomp;        /* mnem(nullcomp = TRUE): the LAST of the k components is the null component (R/mnems.r:1832-1834,
                           * 1894-1900): its graph is empty, its theta 0, its log ratios 0 (R/mnems_low.r:607-608) and it has
                           * no M-step (R/mnems.r:2012, 2076-2080); the last graph of every start in init_phi is ignored */
+    const int32_t *theta; /* mnem(theta =): starts * k * E fixed E-gene attachments in 0..S (start-major), or NULL.  They go
+                          * into res1 (R/mnems.r:1890-1892: the first getProbs takes its theta-given path) and are handed to
+                          * every nem() call as `subtopo` (:2007-2011), which returns them unchanged: the graphs are still
+                          * searched, theta never moves */
 } mnemcu_em_opts;
 
 typedef struct {

@@ -30,7 +30,7 @@ class EmOpts(C.Structure):
     _fields_ = [("complete", C.c_int), ("logtype", C.c_double), ("batch", C.c_int), ("max_trace", C.c_int),
                 ("max_iter_guard", C.c_int), ("next_start", NEXT_START_FN), ("next_start_user", C.c_void_p),
                 ("affinity", C.c_int), ("tape", C.POINTER(C.c_int32)), ("tape_cap", C.c_int64),
-                ("probs_mode", C.c_int), ("mw", C.POINTER(C.c_double)), ("nullcomp", C.c_int)]
+                ("probs_mode", C.c_int), ("mw", C.POINTER(C.c_double)), ("nullcomp", C.c_int), ("theta", C.POINTER(C.c_int32))]
 
 
 class EmStats(C.Structure):

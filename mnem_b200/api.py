@@ -451,7 +451,7 @@ def parse_tape(words, k, E, S):
 
 
 def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, max_iter_guard=0, want_probs=True,
-           next_start=None, affinity=0, tape=False, probs="all", mw=None, nullcomp=False):
+           next_start=None, affinity=0, tape=False, probs="all", mw=None, nullcomp=False, theta=None):
     """mnemcu_em_run on a Context: all starts, returns per-start arrays + winner + stats.
 
     next_start: optional callable returning the next start index to fit (or -1 when none is left) -- the ticket
@@ -465,6 +465,11 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
         mw0 = np.ascontiguousarray(mw, dtype=np.float64)
         if mw0.shape != (k,):
             raise ValueError("mw must hold k weights")
+    th_fixed = None
+    if theta is not None:                  # mnem(theta =): fixed attachments, one [k, E] block per start (R/mnems.r:1890-1892)
+        th_fixed = np.ascontiguousarray(theta, dtype=np.int32)
+        if th_fixed.shape != (starts, k, E):
+            raise ValueError("theta must be [starts, k, E]")
     pb, _, _ = _graphs(init_phi.reshape(starts * k, S, S), S)
     adj = np.zeros(starts * k * S * S, dtype=np.uint8)
     theta = np.zeros((starts, k, E), dtype=np.int32)
@@ -493,7 +498,8 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
         tape_buf = np.zeros(starts * (2 * k * 64 * (S * S // 2 + 8) * S + (64 + 100) * (k * E + 16)) + 1024, dtype=np.int32)
     o = EmOpts(int(bool(complete)), float(logtype), int(batch), int(max_trace), int(max_iter_guard), cb, None, int(affinity),
                tape_buf.ctypes.data_as(C.POINTER(C.c_int32)) if tape else None, tape_buf.size if tape else 0,
-               1 if winner_only else 0, dp(mw0) if mw0 is not None else None, int(bool(nullcomp)))
+               1 if winner_only else 0, dp(mw0) if mw0 is not None else None, int(bool(nullcomp)),
+               i32p(th_fixed) if th_fixed is not None else None)
     check(load_library().mnemcu_em_run(cx._h, starts, k, u8p(pb), C.byref(o), u8p(adj), i32p(theta), dp(probs), dp(mw),
                                        dp(ll), i32p(nit), dp(tr[0]), dp(tr[1]), dp(tr[2]), dp(tr[3]), C.byref(best),
                                        C.byref(st)))
@@ -510,8 +516,10 @@ def em_run(cx, init_phi, complete=False, logtype=2.0, batch=0, max_trace=256, ma
 
 
 def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, seed=0, batch=0, max_iter_guard=0,
-         Rho=None, affinity=0, mw=None, nullcomp=False):
-    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho, affinity, mw, nullcomp).
+         Rho=None, affinity=0, mw=None, nullcomp=False, theta=None):
+    """mnem(D, inference='em', search='greedy', k, starts, phi, complete, logtype, Rho, affinity, mw, nullcomp, theta).
+
+    theta: [starts, k, E] fixed E-gene attachments (0..S), mnem(theta =): the graphs are searched, theta never moves.
 
     nullcomp = True adds a null component as component k + 1 (R/mnems.r:1832-1834): empty graph, theta 0, log ratios 0.
 
@@ -533,7 +541,7 @@ def mnem(D, pert=None, k=None, starts=3, phi=None, complete=False, logtype=2, se
         if k == 1:
             return _mnem_k1(cx, phi[0, 0], complete, logtype)
         r = em_run(cx, phi, complete=complete, logtype=logtype, batch=batch, max_iter_guard=max_iter_guard, affinity=affinity,
-                   mw=mw, nullcomp=nullcomp)
+                   mw=mw, nullcomp=nullcomp, theta=theta)
         b = r["best"]
         limits = [dict(adj=r["adj"][s], theta=r["theta"][s], probs=r["probs"][s], mw=r["mw"][s], ll=r["ll"][s],
                        lls=r["lls"][s], phievo=r["phievo"][s], thetaevo=r["thetaevo"][s], mwevo=r["mwevo"][s])

@@ -107,6 +107,8 @@ struct Engine {
     int Be = 0;
     int Me() const { return k * Be; }
     int nullcomp = 0;             // mnem(nullcomp = TRUE): component k-1 of every slot is the null component
+    bool fixed_theta = false;     // mnem(theta =): theta of a slot never moves (d_theta_fixed holds it)
+    DevBuf<int32_t> d_theta_fixed;
     double logtype = 2.0;
     cudaStream_t st = nullptr;
     std::vector<Slot> slots;
@@ -384,6 +386,7 @@ struct Engine {
         MN_CU(cp(d_flag.p + to * 4, d_flag.p + from * 4, sizeof(int32_t) * 4));
         MN_CU(cp(d_theta.p + to * kE, d_theta.p + from * kE, sizeof(int32_t) * kE));
         MN_CU(cp(d_theta_best.p + to * kE, d_theta_best.p + from * kE, sizeof(int32_t) * kE));
+        if (fixed_theta) MN_CU(cp(d_theta_fixed.p + to * kE, d_theta_fixed.p + from * kE, sizeof(int32_t) * kE));
         for (DevBuf<uint32_t> *g : {&d_res1, &d_clo, &d_clo_cols, &d_best_rows})
             MN_CU(cp(g->p + (size_t)to * k * 32, g->p + (size_t)from * k * 32, sizeof(uint32_t) * k * 32));
         MN_CU(cp(d_mw.p + to * 32, d_mw.p + from * 32, sizeof(double) * 32));
@@ -439,6 +442,12 @@ struct Engine {
         MN_LAUNCH(pick_kernel, np, 128, 0, st, cx->E, cx->S, d_pairs.p, d_have_theta.p, search_maxtrace(sb),
                   search_adj_rows(sb), search_closed_rows(sb), search_theta(sb), search_niter(sb), search_nscored(sb),
                   d_res1.p, d_clo.p, d_theta.p, d_edge.p, d_thch.p, d_counters.p);
+        if (fixed_theta)                                                  // nem(subtopo = thetaX) returns thetaX: theta never moves
+            for (int b : list) {
+                const size_t kE = (size_t)k * cx->E;
+                MN_CU(cudaMemcpyAsync(d_theta.p + b * kE, d_theta_fixed.p + b * kE, sizeof(int32_t) * kE, cudaMemcpyDeviceToDevice, st));
+                MN_CU(cudaMemsetAsync(d_thch.p + (size_t)b * k, 0, sizeof(int32_t) * k, st));
+            }
         MN_TRY(toc(&stats.ms_search));
         if (tape_on) { MN_TRY(tape_searches(pairs)); MN_TRY(tape_theta(list, 4)); }
         return 0;
@@ -603,6 +612,11 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
     MN_TRY(en.init(cx, k, B, opts->complete, opts->logtype, true));
     en.affinity = opts->affinity;
     en.nullcomp = opts->nullcomp ? 1 : 0;
+    if (opts->theta) {
+        for (size_t i = 0; i < (size_t)starts * k * E; ++i) MN_ARG(opts->theta[i] >= 0 && opts->theta[i] <= S, "theta outside 0..S");
+        en.fixed_theta = true;
+        MN_TRY(en.d_theta_fixed.alloc((size_t)en.M * E));
+    }
     MN_ARG(opts->tape_cap >= 0 && (opts->tape || opts->tape_cap == 0), "tape_cap without a tape buffer");
     if (opts->tape) { en.tape_on = true; MN_TRY(search_enable_tape(en.sb)); }
     cudaStream_t st = en.st;
@@ -684,9 +698,18 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
         s.start = sidx;
         s.phase = 0; s.inner = 0; s.cur = 0; s.best = 0; s.nw = 1;
         MN_TRY(en.load_graphs(b, init_phi + (size_t)sidx * kSS));
+        if (en.fixed_theta) {                                                     // res1[[i]]$subtopo <- theta[[s]][[i]]  :1890-1892
+            MN_CU(cudaMemcpyAsync(en.d_theta_fixed.p + (size_t)b * kE, opts->theta + (size_t)sidx * kE, sizeof(int32_t) * kE,
+                                  cudaMemcpyHostToDevice, st));
+            MN_CU(cudaMemcpyAsync(en.d_theta.p + (size_t)b * kE, en.d_theta_fixed.p + (size_t)b * kE, sizeof(int32_t) * kE,
+                                  cudaMemcpyDeviceToDevice, st));
+            MN_CU(cudaStreamSynchronize(st));                                     // opts->theta is pageable caller memory
+        }
         if (en.nullcomp) {                                                        // res1[[k]]$adj <- adj * 0, subtopo * 0  :1894-1898
             MN_CU(cudaMemsetAsync(en.d_res1.p + ((size_t)b * k + k - 1) * 32, 0, sizeof(uint32_t) * 32, st));
             MN_CU(cudaMemsetAsync(en.d_theta.p + ((size_t)b * k + k - 1) * E, 0, sizeof(int32_t) * E, st));
+            if (en.fixed_theta)
+                MN_CU(cudaMemsetAsync(en.d_theta_fixed.p + ((size_t)b * k + k - 1) * E, 0, sizeof(int32_t) * E, st));
         }
         MN_CU(cudaMemsetAsync(en.buf(b, 0), 0, sizeof(double) * en.kCp, st));      // probs <- matrix(0, k, C)  :1905
         MN_CU(cudaMemsetAsync(en.flag(b, 0), 0, sizeof(int32_t), st));
@@ -740,7 +763,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             MN_TRY(en.op_affinity(act));
             MN_TRY(en.op_mstats());
             // ---- structure ----
-            MN_TRY(en.op_theta_init(ini));
+            if (!en.fixed_theta) MN_TRY(en.op_theta_init(ini));                   // fixed theta: the theta-given path of getProbs
             MN_TRY(en.op_search(em));
             // ---- E-step ----
             MN_TRY(en.op_estep());
@@ -753,7 +776,9 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                 for (int t = 0; t < T; ++t) MN_TRY(en.op_stats(em, wnew, true, true, t, false));
                 std::vector<int> inew;
                 for (int b : ini) inew.push_back(en.slots[b].nw);
-                MN_TRY(en.op_stats(ini, inew, false, false, 0, false));
+                // theta-free getProbs: one inner iteration per tick.  Fixed theta: the contraction is the same in all T inner
+                // iterations (R/mnems_low.r:621-631), so the whole call is this one tick: T evaluations of (ll, mw) on it
+                for (int t = 0; t < (en.fixed_theta ? T : 1); ++t) MN_TRY(en.op_stats(ini, inew, false, false, t, false));
             }
             MN_CU(cudaMemcpyAsync(en.h_ll, en.d_ll.p, sizeof(double) * B * 128, cudaMemcpyDeviceToHost, st));
             MN_CU(cudaMemcpyAsync(en.h_chg, en.d_edge.p, sizeof(int32_t) * en.M, cudaMemcpyDeviceToHost, st));
@@ -764,7 +789,14 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
             std::vector<int> outer, outer_guard;
             for (int b : ini) {
                 Slot &s = en.slots[b];
-                const double ll0 = en.h_ll[b * 128];
+                for (int t = 0; t < (en.fixed_theta ? T - 1 : 0); ++t) {          // fixed theta: inner iterations 0 .. T-2 of this tick
+                    const double llt = en.h_ll[b * 128 + t];
+                    if (en.tape_on) en.rec({6, s.start, s.inner, llt - s.llold_inner > 0 ? 1 : 0});
+                    if (llt - s.llold_inner > 0) s.best = s.nw;
+                    s.llold_inner = llt;
+                    ++s.inner;
+                }
+                const double ll0 = en.h_ll[b * 128 + (en.fixed_theta ? T - 1 : 0)];
                 if (en.tape_on) en.rec({6, s.start, s.inner, ll0 - s.llold_inner > 0 ? 1 : 0});
                 if (ll0 - s.llold_inner > 0) s.best = s.nw;
                 s.cur = s.nw;
@@ -775,7 +807,7 @@ extern "C" int mnemcu_em_run(mnemcu_ctx *cx, int starts, int k, const uint8_t *i
                     s.probs_ll = s.llold_inner;
                     s.phase = 1;
                     s.time0 = true;
-                    s.have_theta = false;
+                    s.have_theta = en.fixed_theta;                                    // res1 carries subtopo from the start
                     outer_guard.push_back(b);
                 }
             }

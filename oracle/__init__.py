@@ -24,7 +24,7 @@ class NemInfo(C.Structure):
 
 class EmOpts(C.Structure):
     _fields_ = [("max_trace", C.c_int), ("complete", C.c_int), ("logtype", C.c_double), ("faithful_cost", C.c_int),
-                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int), ("mw0", c_dp), ("nullcomp", C.c_int)]
+                ("max_iter_guard", C.c_int), ("noise_mode", C.c_int), ("affinity", C.c_int), ("mw0", c_dp), ("nullcomp", C.c_int), ("theta0", c_i32p)]
 
 
 class EmInfo(C.Structure):
@@ -243,8 +243,23 @@ def get_probs(D, pert, S, phi, theta, L_in, mw, complete=False, logtype=2.0, fai
 
 # ---- EM --------------------------------------------------------------------------------------------------
 def mnem_em(D, pert, S, init_phi, complete=False, logtype=2.0, nthreads=1, faithful_cost=False, max_trace=256,
-            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None, nullcomp=False):
-    """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner."""
+            max_iter_guard=0, noise_mode=0, affinity=0, acc="ld", mw=None, nullcomp=False, theta=None):
+    """mnem(D, phi=init_phi) EM phase.  init_phi: [starts, k, S, S].  Returns per-start limits and the winner.
+    theta: optional [starts, k, E] fixed attachments (mnem(theta =)): the starts are then fitted one call each."""
+    if theta is not None:
+        theta = np.ascontiguousarray(theta, dtype=np.int32)
+        parts = []
+        for s_ in range(len(init_phi)):
+            parts.append(_mnem_em_one_theta(D, pert, S, np.asarray(init_phi)[s_:s_ + 1], theta[s_], complete, logtype, max_trace,
+                                            max_iter_guard, noise_mode, affinity, acc, mw, nullcomp))
+        out = {q: (np.concatenate([p_[q] for p_ in parts]) if isinstance(parts[0][q], np.ndarray) else sum((p_[q] for p_ in parts), []))
+               for q in parts[0] if q != "best"}
+        best = 0
+        for s_ in range(1, len(init_phi)):
+            if out["ll"][best] <= out["ll"][s_]:
+                best = s_
+        out["best"] = best
+        return out
     mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None       # mnem(mw =), R/mnems.r:1771-1773
     D = _f(D)
     E, Cn = D.shape
@@ -337,7 +352,7 @@ def record_start(D, pert, S, init_phi, complete=False, logtype=2.0, acc="ld", st
 
 
 def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e-13, tol_ll=1e-12, max_trace=256,
-                 affinity=0, acc="ld", mw=None, max_iter_guard=0, nullcomp=False):
+                 affinity=0, acc="ld", mw=None, max_iter_guard=0, nullcomp=False, theta=None):
     """One EM start replayed against the decision tape of a device fit (mnem_b200.api.parse_tape(...)[start]).
 
     The oracle runs the start in its own arithmetic and takes the tape's choice wherever its own decision differs by
@@ -345,6 +360,7 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     Returns the fit (like mnem_em, one start) plus report = {kind: dict(checked, forced, hard, max_forced, min_hard)},
     diverged and first_hard."""
     mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
+    th0 = np.ascontiguousarray(theta, dtype=np.int32) if theta is not None else None      # mnem(theta =): fixed attachments
     D = _f(D)
     E, Cn = D.shape
     pert = np.ascontiguousarray(pert, dtype=np.int32)
@@ -353,8 +369,9 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     assert C.sizeof(Advice) == lib(acc).orc_advice_size()
     T = len(tape["init_theta"])
     n_em = int(tape["n_iter"])
-    init_theta = np.ascontiguousarray(np.stack([tape["init_theta"][t] for t in range(T)]), dtype=np.int32)
-    init_best = np.array([tape["init_best"][t] for t in range(T)], dtype=np.int32)
+    init_theta = np.ascontiguousarray(np.stack([tape["init_theta"][t] for t in range(T)] + [np.zeros((k, E), dtype=np.int32)]),
+                                      dtype=np.int32)                  # (T = 0 with fixed theta: nothing to replay there)
+    init_best = np.array([tape["init_best"][t] for t in range(T)] + [0], dtype=np.int32)
     off = np.zeros(n_em * k * 2 + 1, dtype=np.int64)
     rows = []
     for it in range(n_em):
@@ -385,7 +402,7 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
     tr = [np.zeros(max_trace) for _ in range(4)]
     info = EmInfo()
     o = EmOpts(max_trace, int(bool(complete)), logtype, 0, int(max_iter_guard), 0, int(affinity),
-               _d(mw0) if mw0 is not None else None, int(bool(nullcomp)))
+               _d(mw0) if mw0 is not None else None, int(bool(nullcomp)), _i32(th0) if th0 is not None else None)
     lib(acc).orc_em_start_advised(_d(D), E, Cn, _i32(pert), S, k, _u8(pb), C.byref(o), C.byref(adv), _u8(adj), _i32(th),
                                   _d(L), _d(mw), _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), C.byref(info))
     n = info.n_iter
@@ -396,6 +413,33 @@ def replay_start(D, pert, S, init_phi, tape, complete=False, logtype=2.0, tol=1e
                 phievo=tr[1][:n].copy(), thetaevo=tr[2][:n].copy(), mwevo=tr[3][:n].copy(), n_raw=info.n_raw,
                 n_dec=info.n_dec, n_dec_tight=info.n_dec_tight, min_margin=info.min_margin, report=report,
                 diverged=bool(adv.diverged), first_hard=adv.first_hard.decode("utf-8", "replace"))
+
+
+def _mnem_em_one_theta(D, pert, S, init1, theta1, complete, logtype, max_trace, max_iter_guard, noise_mode, affinity, acc, mw,
+                       nullcomp):
+    """mnem_em for ONE start with fixed theta (orc_em_opts.theta0 belongs to a start)."""
+    D = _f(D)
+    E, Cn = D.shape
+    pert = np.ascontiguousarray(pert, dtype=np.int32)
+    k = init1.shape[1]
+    mw0 = np.ascontiguousarray(mw, dtype=np.float64) if mw is not None else None
+    th0 = np.ascontiguousarray(theta1, dtype=np.int32)
+    pb = _graphs(init1.reshape(k, S, S))
+    adj = np.zeros(k * S * S, dtype=np.uint8)
+    theta = np.zeros((1, k, E), dtype=np.int32)
+    L = np.zeros((1, Cn, k))
+    mwo = np.zeros((1, k))
+    tr = [np.zeros((1, max_trace)) for _ in range(4)]
+    infos = (EmInfo * 1)()
+    o = EmOpts(max_trace, int(bool(complete)), logtype, 0, max_iter_guard, int(noise_mode), int(affinity),
+               _d(mw0) if mw0 is not None else None, int(bool(nullcomp)), _i32(th0))
+    lib(acc).orc_mnem_em(_d(D), E, Cn, _i32(pert), S, k, 1, _u8(pb), C.byref(o), 1, _u8(adj), _i32(theta), _d(L), _d(mwo),
+                         _d(tr[0]), _d(tr[1]), _d(tr[2]), _d(tr[3]), infos)
+    n = infos[0].n_iter
+    return dict(best=0, adj=_ungraphs(adj, k, S).reshape(1, k, S, S), theta=theta, probs=np.transpose(L, (0, 2, 1)).copy(), mw=mwo,
+                ll=np.array([infos[0].ll]), n_iter=np.array([n]), min_margin=np.array([infos[0].min_margin]),
+                min_accept_margin=np.array([infos[0].min_accept_margin]), n_raw=np.array([infos[0].n_raw]),
+                lls=[tr[0][0, :n].copy()], phievo=[tr[1][0, :n].copy()], thetaevo=[tr[2][0, :n].copy()], mwevo=[tr[3][0, :n].copy()])
 
 
 def final_mw(L, mw_best, complete=False, logtype=2.0, affinity=0, acc="ld"):

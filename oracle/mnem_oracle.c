@@ -992,6 +992,9 @@ typedef struct {
     const double *mw0;      /* mnem(mw =): initial mixture weights (R/mnems.r:1771-1773); NULL = rep(1, k)/k */
     int nullcomp;           /* mnem(nullcomp = TRUE): the LAST of the k components is the null component (R/mnems.r:1832-1834,
                              * 1894-1900): empty graph, theta 0, log ratios 0 (R/mnems_low.r:607-608), no M-step (:2012, 2076-2080) */
+    const int32_t *theta0;  /* mnem(theta =): k*E fixed attachments (0..S) of THIS start, or NULL.  R/mnems.r:1890-1892 puts them
+                             * into res1, so the first getProbs takes its theta-given path; :2007-2011, 2033 hand them to nem() as
+                             * `subtopo`, which returns them unchanged (R/mnems.r:362-372; the llr score ignores subtopo, :439-454) */
 } orc_em_opts;
 
 typedef struct {
@@ -1057,10 +1060,11 @@ void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, in
     if (o->nullcomp) memset(res1_adj + (size_t)(k - 1) * SS, 0, SS);              /* :1894-1898 */
     g_nullcomp = o->nullcomp;
     memset(res1_th, 0, sizeof(int32_t) * (size_t)k * E);
+    if (o->theta0) { memcpy(res1_th, o->theta0, sizeof(int32_t) * (size_t)k * E); have_res1_theta = 1; }   /* :1890-1892 */
     memset(probs, 0, sizeof(double) * kc);                                        /* :1905 */
     const int affinity = o->affinity;
-    double probs_ll = orc_get_probs_a(D, E, C, pert, S, k, res1_adj, NULL, probs, mw, affinity, complete, logtype,
-                                      o->faithful_cost, newp, mwnew, NULL);       /* :1906-1911 */
+    double probs_ll = orc_get_probs_a(D, E, C, pert, S, k, res1_adj, o->theta0 ? res1_th : NULL, probs, mw, affinity, complete,
+                                      logtype, o->faithful_cost, newp, mwnew, NULL);   /* :1906-1911 */
     memcpy(probs, newp, sizeof(double) * kc);
     for (int i = 0; i < k; i++) mw[i] = mwnew[i];                                  /* :1913 */
     mw_update_a(probs, k, C, mw, affinity, complete, logtype, 1, scratch);        /* :1936-1940 */
@@ -1170,7 +1174,8 @@ void orc_em_start_advised(const double *D, int E, int C, const int32_t *pert, in
             if (g_rec) { rec_w(3); rec_w(g_rec_start); rec_w(count); rec_w(i); rec_w(pick1); }
             memcpy(res_adj + (size_t)i * SS, pick1 ? a1 : a0, SS);
             memcpy(res_th + (size_t)i * E, pick1 ? t1 : t0, sizeof(int32_t) * E);
-            if (adv_it && adv_on())
+            if (o->theta0) memcpy(res_th + (size_t)i * E, o->theta0 + (size_t)i * E, sizeof(int32_t) * E);   /* subtopo = thetaX */
+            if (adv_it && adv_on() && !o->theta0)
                 adv_theta(ADV_THETA, pick1 ? Wfin1 : Wfin0, E, S, res_th + (size_t)i * E,
                           adv->theta + ((size_t)count * k + i) * E, count, i);
             for (int q = 0; q < SS; q++)                                          /* :2080-2081 */

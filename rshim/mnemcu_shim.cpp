@@ -243,7 +243,7 @@ List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0
         mw0.assign(m.begin(), m.end());
     }
     mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr, affinity, nullptr, 0, 0,
-                        mw0.empty() ? nullptr : mw0.data(), 0};
+                        mw0.empty() ? nullptr : mw0.data(), 0, nullptr};
     mnemcu_em_stats st;
     chk(mnemcu_em_run(cx, starts, k, phi.data(), &o, adj.data(), theta.data(), probs.data(), mwout.data(), ll.data(),
                       nit.data(), lls.data(), pe.data(), te.data(), me.data(), &best, &st));

@@ -18,11 +18,11 @@
 
 static int layout()
 {
-    std::printf("em_opts %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mnemcu_em_opts), offsetof(mnemcu_em_opts, complete),
+    std::printf("em_opts %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mnemcu_em_opts), offsetof(mnemcu_em_opts, complete),
                 offsetof(mnemcu_em_opts, logtype), offsetof(mnemcu_em_opts, batch), offsetof(mnemcu_em_opts, max_trace),
                 offsetof(mnemcu_em_opts, max_iter_guard), offsetof(mnemcu_em_opts, next_start),
                 offsetof(mnemcu_em_opts, next_start_user), offsetof(mnemcu_em_opts, affinity), offsetof(mnemcu_em_opts, tape),
-                offsetof(mnemcu_em_opts, tape_cap), offsetof(mnemcu_em_opts, probs_mode), offsetof(mnemcu_em_opts, mw), offsetof(mnemcu_em_opts, nullcomp));
+                offsetof(mnemcu_em_opts, tape_cap), offsetof(mnemcu_em_opts, probs_mode), offsetof(mnemcu_em_opts, mw), offsetof(mnemcu_em_opts, nullcomp), offsetof(mnemcu_em_opts, theta));
     std::printf("em_stats %zu %zu %zu %zu %zu\n", sizeof(mnemcu_em_stats), offsetof(mnemcu_em_stats, em_iters),
                 offsetof(mnemcu_em_stats, ms_total), offsetof(mnemcu_em_stats, estep_bytes), offsetof(mnemcu_em_stats, tape_words));
     std::printf("version %d\n", mnemcu_version());

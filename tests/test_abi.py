@@ -102,7 +102,7 @@ def test_struct_layouts_agree_between_c_and_ctypes():
     o = [int(x) for x in out["em_opts"].split()]
     f = _lib.EmOpts
     assert o == [C.sizeof(f), f.complete.offset, f.logtype.offset, f.batch.offset, f.max_trace.offset, f.max_iter_guard.offset,
-                 f.next_start.offset, f.next_start_user.offset, f.affinity.offset, f.tape.offset, f.tape_cap.offset, f.probs_mode.offset, f.mw.offset, f.nullcomp.offset]
+                 f.next_start.offset, f.next_start_user.offset, f.affinity.offset, f.tape.offset, f.tape_cap.offset, f.probs_mode.offset, f.mw.offset, f.nullcomp.offset, f.theta.offset]
     s = [int(x) for x in out["em_stats"].split()]
     g = _lib.EmStats
     assert s == [C.sizeof(g), g.em_iters.offset, g.ms_total.offset, g.estep_bytes.offset, g.tape_words.offset]

@@ -673,3 +673,31 @@ def test_null_component():
         close(r["mw"][s], o["mw"], rtol=RTOL)
         close(r["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
     assert r["best"] == fit["best_start"] and np.array_equal(r["adj"][r["best"]][2], np.zeros((6, 6)))
+
+
+def test_fixed_theta():
+    """mnem(theta =) (R/mnems.r:1890-1892, 2007-2011): the E-gene attachments are given and never move -- the first
+    getProbs takes its theta-given path, every M-step still searches the graphs (the llr score ignores subtopo,
+    R/mnems.r:439-454) and returns the given theta.  Replayed through the oracle."""
+    sim = simdata.make_config(dict(S=6, Egenes=8, C=2500, mw=[0.4, 0.6], k=2, starts=3, uninform=2), seed=23)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(6, 2, 3, seed=4)
+    rng = np.random.default_rng(2)
+    th = np.stack([np.where(rng.random(sim["theta_true"].shape) < 0.8, sim["theta_true"], rng.integers(0, 7, sim["theta_true"].shape))
+                   for _ in range(3)]).astype(np.int32)
+    with mb.Context(D, sim["pert"]) as cx:
+        r = mb.em_run(cx, init, theta=th, tape=True)
+        free = mb.em_run(cx, init)
+    assert np.array_equal(r["theta"], th) and all((t == 0).all() for t in r["thetaevo"])
+    assert not np.array_equal(free["theta"], th)
+    for s in range(3):
+        o = orc.replay_start(D, sim["pert"], 6, init[s], r["tape"][s], theta=th[s])
+        assert not o["diverged"], o["first_hard"]
+        assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(o["theta"], th[s])
+        assert r["n_iter"][s] == o["n_iter"] and abs(r["ll"][s] - o["ll"]) <= RTOL * abs(o["ll"])
+        assert np.array_equal(r["phievo"][s], o["phievo"])
+        close(r["lls"][s], o["lls"], rtol=RTOL)
+        close(r["mw"][s], o["mw"], rtol=RTOL)
+        close(r["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
+    ref = orc.mnem_em(D, sim["pert"], 6, init, theta=th)
+    assert ref["min_margin"].min() <= 1e-13 or all(np.array_equal(r["adj"][s], ref["adj"][s]) for s in range(3))
