@@ -10,7 +10,8 @@ mnem_cuda_enabled <- function() identical(getOption("mnem.backend", "r"), "cuda"
 ## replaces the `lapply(seq_len(starts), do_inits)` of R/mnems.r:2166-2170 for inference = "em", search = "greedy",
 ## marginal = FALSE; `init` is mnem()'s phi list (R/mnems.r:1790-1793).  Multi-knock-down columns ("1_3") or an
 ## explicit Rho take the Rho path (R/mnems_low.r:613-616, 896-904).
-mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0, Rho = NULL, affinity = 0, mw = NULL) {
+mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0, Rho = NULL, affinity = 0, mw = NULL,
+                               nullcomp = FALSE, theta = NULL) {
     if (is.null(Rho) && any(grepl("_", colnames(data)))) Rho <- getRho(data)
     if (is.null(Rho)) {
         pert <- as.integer(colnames(data))                   # after modData(): "1".."S"
@@ -20,7 +21,11 @@ mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0, Rho = 
         S <- nrow(Rho)
         ctx <- mnemcu_context_rho(data, Rho, device)
     }
-    out <- mnemcu_em(ctx, init, complete, logtype, 0L, 256L, as.integer(affinity), mw)
+    if (nullcomp) {                                          # res1[[k + 1]]$adj <- adj * 0  (R/mnems.r:1894-1898)
+        init <- lapply(init, function(g) c(g, list(g[[1]] * 0)))
+        if (!is.null(theta)) theta <- lapply(theta, function(t) c(t, list(t[[1]] * 0L)))
+    }
+    out <- mnemcu_em(ctx, init, complete, logtype, 0L, 256L, as.integer(affinity), mw, nullcomp, theta)
     for (s in seq_along(out$limits)) {                       # names the rest of mnem() expects (R/mnems.r:2153-2163)
         out$limits[[s]]$k <- length(init[[s]])
         out$limits[[s]]$subtopo <- NULL
@@ -33,7 +38,8 @@ mnem_cuda_do_inits <- function(data, init, complete, logtype, device = 0, Rho = 
 
 ## In mnem() (R/mnems.r:2166): 
 ##   if (mnem_cuda_enabled() && is.null(parallel)) {
-##       limits <- mnem_cuda_do_inits(data, init, complete, logtype, affinity = affinity, mw = mw)
+##       limits <- mnem_cuda_do_inits(data, init, complete, logtype, affinity = affinity, mw = mw,
+##                                    nullcomp = nullcomp, theta = theta)
 ##   } else if (!is.null(parallel)) { limits <- sfLapply(seq_len(starts), do_inits) } else { ... }
 ## snowfall (`parallel = n`) and the CUDA backend must not be combined: one CUDA context per process.
 

@@ -218,9 +218,11 @@ List mnemcu_getProbs(SEXP ctx, NumericMatrix probs, List res, NumericVector mw, 
 // ---- the EM phase of mnem(D, phi = init) (R/mnems.r:1884-2165, 2222-2230) ---------------------------------------
 // init: list over starts of lists over components of S x S matrices, exactly mnem()'s `phi` argument
 // [[Rcpp::export]]
-// affinity: mnem(affinity =) 0 / 1 (R/mnems.r:1393-1417); mw: mnem(mw =) or NULL for rep(1, k)/k (:1771-1773)
+// affinity: mnem(affinity =) 0 / 1 (R/mnems.r:1393-1417); mw: mnem(mw =) or NULL for rep(1, k)/k (:1771-1773);
+// nullcomp: mnem(nullcomp = TRUE) -- init then carries k + 1 graphs per start, the last one the null component
+// (:1832-1834, 1894-1898); theta_fixed: mnem(theta =), list over starts of lists over components of integer vectors, or NULL
 List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0, int max_trace = 256, int affinity = 0,
-               Nullable<NumericVector> mw = R_NilValue)
+               Nullable<NumericVector> mw = R_NilValue, bool nullcomp = false, Nullable<List> theta_fixed = R_NilValue)
 {
     mnemcu_ctx *cx = ctx_of(ctx);
     int E, C, S;
@@ -242,8 +244,20 @@ List mnemcu_em(SEXP ctx, List init, bool complete, double logtype, int batch = 0
         if ((int)m.size() != k) stop("mw must hold one weight per component");
         mw0.assign(m.begin(), m.end());
     }
+    std::vector<int32_t> th0;
+    if (theta_fixed.isNotNull()) {
+        List tl(theta_fixed);
+        if ((int)tl.size() != starts) stop("theta must hold one list per start");
+        th0.resize((size_t)starts * k * E);
+        for (int s = 0; s < starts; ++s)
+            for (int i = 0; i < k; ++i) {
+                IntegerVector t = as<IntegerVector>(as<List>(tl[s])[i]);
+                if ((int)t.size() != E) stop("theta vectors must have one entry per E-gene");
+                std::copy(t.begin(), t.end(), th0.begin() + ((size_t)s * k + i) * E);
+            }
+    }
     mnemcu_em_opts o = {complete, logtype, batch, max_trace, 0, nullptr, nullptr, affinity, nullptr, 0, 0,
-                        mw0.empty() ? nullptr : mw0.data(), 0, nullptr};
+                        mw0.empty() ? nullptr : mw0.data(), nullcomp ? 1 : 0, th0.empty() ? nullptr : th0.data()};
     mnemcu_em_stats st;
     chk(mnemcu_em_run(cx, starts, k, phi.data(), &o, adj.data(), theta.data(), probs.data(), mwout.data(), ll.data(),
                       nit.data(), lls.data(), pe.data(), te.data(), me.data(), &best, &st));

@@ -34,7 +34,7 @@ static int fit(const char *path)
             }
             phi[s] = comps;
         }
-        List out = mnemcu_em(ctx, phi, complete != 0, 2.0, 0, 64, 0, R_NilValue);
+        List out = mnemcu_em(ctx, phi, complete != 0, 2.0, 0, 64, 0, R_NilValue, false, R_NilValue);
         const int best = IntegerVector(out["best"])[0] - 1;
         List limits(out["limits"]);
         List lim(limits[best]);
