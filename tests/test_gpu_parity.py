@@ -701,3 +701,28 @@ def test_fixed_theta():
         close(r["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
     ref = orc.mnem_em(D, sim["pert"], 6, init, theta=th)
     assert ref["min_margin"].min() <= 1e-13 or all(np.array_equal(r["adj"][s], ref["adj"][s]) for s in range(3))
+
+
+@pytest.mark.parametrize("S,Egenes,Cn,k,uninform", [(2, 1, 7, 2, 0), (2, 1, 64, 2, 1), (3, 2, 65, 2, 0), (3, 1, 130, 3, 2), (4, 3, 33, 2, 0),
+                                                   (5, 1, 200, 4, 0), (7, 2, 129, 2, 3)])
+def test_tiny_and_ragged_shapes(S, Egenes, Cn, k, uninform):
+    """Degenerate sizes: a single E-gene per S-gene, fewer cells than a 64-cell block, cell counts one past a block, more
+    components than the data support.  Every fit is replayed through the oracle (C <= 100 also switches getProbs to its
+    100 inner iterations, R/mnems_low.r:584-588)."""
+    sim = simdata.make_config(dict(S=S, Egenes=Egenes, C=Cn, mw=[1.0 / k] * k, k=k, starts=3, uninform=uninform), seed=100 + S + Cn)
+    D = simdata.host_data(sim)
+    init = simdata.init_phi(S, k, 3, seed=S * Cn)
+    with mb.Context(D, sim["pert"]) as cx:
+        r = mb.em_run(cx, init, tape=True, max_iter_guard=30)
+        rb = mb.em_run(cx, init, batch=1, max_iter_guard=30)
+    assert np.array_equal(r["adj"], rb["adj"]) and np.array_equal(r["ll"], rb["ll"])
+    for s in range(3):
+        o = orc.replay_start(D, sim["pert"], S, init[s], r["tape"][s], max_iter_guard=30)
+        assert not o["diverged"], o["first_hard"]
+        assert np.array_equal(r["adj"][s], o["adj"]) and np.array_equal(r["theta"][s], o["theta"])
+        assert r["n_iter"][s] == o["n_iter"]
+        if np.isfinite(o["ll"]):
+            assert abs(r["ll"][s] - o["ll"]) <= RTOL * max(abs(o["ll"]), 1e-300)
+            close(r["probs"][s], o["probs"], rtol=RTOL, atol=1e-9)
+        else:
+            assert r["ll"][s] == o["ll"] or (np.isnan(r["ll"][s]) and np.isnan(o["ll"]))
