@@ -288,7 +288,9 @@ __device__ __forceinline__ void gen_body(const SearchDev &d, const GenSmem sm, i
         // are rebuilt from (u, v) by the finish step, so nothing is written per insertion -- only reversals and deletions
         // are materialised (most of the ~S^2 candidates of an iteration are insertions; this loop was 14 us of the 36 us a
         // CTA spends between two iterations of a search).
-        for (int item = warp + (staged ? S : 0); item < 3 * S; item += nwarp) {
+        // (the last warp builds the chains meanwhile: in the staged loop it takes no candidates, the others share them)
+        const int nwork = (staged && nwarp > 1) ? nwarp - 1 : nwarp;
+        for (int item = warp + (staged ? S : 0); item < 3 * S && warp < nwork; item += nwork) {
             const int kd = item / S, v = item - kd * S;
             uint32_t m = __shfl_sync(kFull, kd == 0 ? km[0] : (kd == 1 ? km[1] : km[2]), v);
             int idx = __shfl_sync(kFull, kd == 0 ? off[0] : (kd == 1 ? off[1] : off[2]), v);
@@ -841,6 +843,19 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
     const int nc = ldv<CG>(d.ncand + q);
     double best = -INFINITY;
     int bidx = INT_MAX;
+    // warp 0 fetches the scalars of the accept step now: their L2 round trips hide behind the tile sums
+    uint32_t pf_pcol = 0u;
+    double pf_old = 0.0, pf_maxtrace = 0.0;
+    unsigned long long pf_nscored = 0ull;
+    int pf_niter = 0, pf_nins = 0;
+    if (tid < 32 && mode != 0) {
+        pf_pcol = ldv<CG>(d.Pcol + q * 32 + tid);
+        pf_old = ldv<CG>(d.oldscore + q);
+        pf_maxtrace = ldv<CG>(d.maxtrace + q);
+        pf_nscored = ldv<CG>(d.nscored + q);
+        pf_niter = ldv<CG>(d.niter + q);
+        if constexpr (CG) pf_nins = ldv<CG>(d.nins + q);
+    }
     // Score of a candidate = sum of its row tiles in a FIXED shape, whatever CTA produced them: the tiles form Gp groups
     // (tile_groups), each group is added in ascending order, then the group sums in ascending order (reduce_tiles_kernel
     // computes the same function).  A thread owns two neighbouring candidates and fetches a whole group (16 tiles) of both
@@ -903,13 +918,13 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
         } else if (mode == 0) {
             if (tid == 0) { d.oldscore[q] = best; d.maxtrace[q] = best; fs.flag[0] = 1; }
         } else {
-            const uint32_t pcol = ldv<CG>(d.Pcol + q * 32 + tid);
+            const uint32_t pcol = pf_pcol;
             uint32_t ccol;
             bool rebuilt = false;
             if constexpr (CG) {
                 // insertion candidates are not materialised in the device-resident loop: candidate bidx < nins is the
                 // r-th missing edge u -> v of column v (ascending u), columns as in gen_body (transClose_Ins, src/mm.cpp:50-65)
-                const int nins = ldv<CG>(d.nins + q);
+                const int nins = pf_nins;
                 if (bidx < nins) {
                     const uint32_t smask = S == 32 ? 0xffffffffu : ((1u << S) - 1u);
                     const uint32_t zmask = tid < S ? (~pcol & smask) : 0u;
@@ -939,19 +954,18 @@ __device__ __forceinline__ void finish_body(const SearchDev &d, const FinSmem fs
             }
             np = __shfl_sync(kFull, np, 0);
             ncn = __shfl_sync(kFull, ncn, 0);
-            const double old = ldv<CG>(d.oldscore + q);
+            const double old = pf_old;
             // R/mnems.r:279-283: better score, or equal score and fewer edges
             const bool accept = best > old || (best == old && np > ncn);
             const uint32_t newrow = warp_transpose(ccol, tid, S);
-            if (tid == 0) d.nscored[q] = ldv<CG>(d.nscored + q) + (unsigned long long)nc;
+            if (tid == 0) d.nscored[q] = pf_nscored + (unsigned long long)nc;
             if (accept) {
                 d.Prow[q * 32 + tid] = newrow;
-                if (d.tape) d.tape[((size_t)q * d.hard_cap + ldv<CG>(d.niter + q)) * 32 + tid] = newrow;
-                __syncwarp();                      // lane 0 advances niter below
+                if (d.tape) d.tape[((size_t)q * d.hard_cap + pf_niter) * 32 + tid] = newrow;
                 if (tid == 0) {
                     d.oldscore[q] = best;
-                    if (best > ldv<CG>(d.maxtrace + q)) d.maxtrace[q] = best;
-                    const int it = ldv<CG>(d.niter + q) + 1;
+                    if (best > pf_maxtrace) d.maxtrace[q] = best;
+                    const int it = pf_niter + 1;
                     d.niter[q] = it;
                     if (n_active) atomicAdd(n_active, 1);
                     if (it >= d.hard_cap) { d.active[q] = 0; atomicOr(d.overflow, 2); }    // not converged: reported by the host
