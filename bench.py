@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--config", type=int, default=5)
     ap.add_argument("--starts", type=int, default=0, help="override the config's number of EM starts")
     ap.add_argument("--cells", type=int, default=0, help="override the config's number of cells")
-    ap.add_argument("--batch", type=int, default=0, help="EM starts per pass over D (0: k*batch <= 20)")
+    ap.add_argument("--batch", type=int, default=0, help="EM starts per pass over D (0: k*batch <= 30)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=0, help="cells in the CPU-baseline sample (0: auto)")

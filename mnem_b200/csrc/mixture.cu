@@ -89,6 +89,49 @@ __global__ void __launch_bounds__(256) affinity_kernel(MixSlots s, MixGeom g, in
     }
 }
 
+// The EM driver's gamma is cell-major [Cp][gw] with the mixtures of a tick side by side in a row (the B operand the
+// M-step statistics kernel stages with one bulk copy per pipeline stage).  One thread per cell would write k doubles
+// per mixture at a stride of a whole row, so a CTA takes kAffCells cells x all listed mixtures, collects the rows in shared
+// memory and writes them out row by row.  Same arithmetic per cell as affinity_kernel (soft affinity only).
+constexpr int kAffCells = 128;
+template <bool kComplete, int KT>
+__global__ void __launch_bounds__(2 * kAffCells) affinity_rows_kernel(MixSlots s, MixGeom g, int k_rt, double b, double lb,
+                                                                      double shrink_k)
+{
+    extern __shared__ double aff_tile[];                           // [kAffCells][wp]
+    constexpr int KA = KT > 0 ? KT : MNEMCU_MAX_K;
+    const int k = KT > 0 ? KT : k_rt;
+    const int w = s.n * k, wp = w | 1;                             // odd row pitch: conflict-free 8-byte columns
+    const int cl = threadIdx.x & (kAffCells - 1);
+    const int c0 = blockIdx.x * kAffCells, c = c0 + cl;
+    const bool live = c < g.ncell && !(g.valid && g.valid[c] < 0);
+    for (int j = threadIdx.x / kAffCells; j < s.n; j += 2) {       // the two halves of the CTA alternate over the mixtures
+        double *t = aff_tile + cl * wp + j * k;
+        if (!live || k == 1) {                                      // padding: 0; k == 1: R/mnems.r:1435-1437
+#pragma unroll
+            for (int i = 0; i < k; ++i) t[i] = live ? 1.0 : 0.0;
+            continue;
+        }
+        double mw[KA], xs[KA], xraw[KA];
+#pragma unroll
+        for (int i = 0; i < k; ++i) mw[i] = s.mw[j] ? s.mw[j][i] : 1.0 / k;
+        const bool shift_on = kComplete && s.anypos[j] && *s.anypos[j] != 0;
+        const double cs = cell_terms<kComplete, KT>(s.L[j] + c * g.sc, g.si, k, mw, shift_on, shrink_k, b, lb, xs, xraw);
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            double v = xs[i] / cs;
+            if (isnan(v)) v = 0.0;
+            t[i] = v;
+        }
+    }
+    __syncthreads();
+    const int nc = min(kAffCells, g.ncell - c0);
+    for (int idx = threadIdx.x; idx < nc * w; idx += 2 * kAffCells) {
+        const int cc = idx / w, q = idx - cc * w, j = q / k, i = q - j * k;
+        s.gam[j][(long long)(c0 + cc) * g.gsc + i] = aff_tile[cc * wp + q];
+    }
+}
+
 __device__ __forceinline__ double block_sum_256(double v, double *sm)
 {   // fixed tree: warp shuffle, then the 8 warp results in order
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
@@ -229,6 +272,25 @@ int launch_affinity_geom(const MixSlots &s, const MixGeom &g, int k, int hard, i
 {
     double lb, sk;
     consts(logtype, k, &lb, &sk);
+    if (!hard && g.gsi == 1 && g.gsc > 1 && s.n * k <= 32) {           // the EM driver's row layout (k * batch <= 32)
+        const int nblk = (g.ncell + kAffCells - 1) / kAffCells;
+        const size_t smem = sizeof(double) * kAffCells * ((s.n * k) | 1);
+#define MN_AFF(KT)                                                                                                        \
+    do {                                                                                                                  \
+        if (complete) MN_LAUNCH((affinity_rows_kernel<true, KT>), nblk, 2 * kAffCells, smem, st, s, g, k, logtype, lb, sk); \
+        else MN_LAUNCH((affinity_rows_kernel<false, KT>), nblk, 2 * kAffCells, smem, st, s, g, k, logtype, lb, sk);         \
+    } while (0)
+        switch (k) {
+            case 2: MN_AFF(2); break;
+            case 3: MN_AFF(3); break;
+            case 4: MN_AFF(4); break;
+            case 5: MN_AFF(5); break;
+            case 6: MN_AFF(6); break;
+            default: MN_AFF(0); break;
+        }
+#undef MN_AFF
+        return 0;
+    }
     dim3 grid((g.ncell + 255) / 256, s.n);
     if (complete) MN_LAUNCH(affinity_kernel<true>, grid, 256, 0, st, s, g, k, hard, logtype, lb, sk);
     else MN_LAUNCH(affinity_kernel<false>, grid, 256, 0, st, s, g, k, hard, logtype, lb, sk);

@@ -720,7 +720,7 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                         // intact for the next target of the chain.
                         double V[kUP];
 #pragma unroll
-                        for (int i = 0; i < kUP; ++i) V[i] = ((zm >> i) & 1u) ? (B[i] > A0 ? B[i] : A0) : 0.0;
+                        for (int i = 0; i < kUP; ++i) V[i] = B[i] > A0 ? B[i] : A0;   // non-candidates: summed, never stored
 #pragma unroll
                         for (int dd = 16, n = kUP / 2; n >= 1; dd >>= 1, n >>= 1) {
                             const bool hi = (lane & dd) != 0;
