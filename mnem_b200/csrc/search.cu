@@ -682,9 +682,13 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                 const int h = item / kParts, u0 = (item - h * kParts) * kUP;
                 while (*reinterpret_cast<volatile int *>(&s_aflag[h]) != gen) { }     // the chain's floors are in shared memory
                 __threadfence_block();
-                double B[kUP];                                        // B[i] = max over the columns seen so far of T[col_j | col_(u0+i)]
+                // B[i] = max over the columns seen so far of T[col_j | col_u], u = u0 + (i ^ hsw): lanes 16..31 keep the upper
+                // half of the sources in the lower slots, so the first stage of the row butterfly below sends slots
+                // kUP/2.. and keeps slots 0..kUP/2-1 in every lane (no selects)
+                double B[kUP];
 #pragma unroll
                 for (int i = 0; i < kUP; ++i) B[i] = -INFINITY;
+                const int hsw = (lane & 16) ? kUP / 2 : 0;
                 uint32_t seen = 0u;
                 const int cend = s_cstart[h + 1];
                 const unsigned char *Tl = reinterpret_cast<const unsigned char *>(T + lane);
@@ -703,7 +707,7 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                         uint32_t ofs[kUP];
 #pragma unroll
                         for (int w4 = 0; w4 < kUP / 4; ++w4) {
-                            const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + u0 + w4 * 4);
+                            const uint4 x = *reinterpret_cast<const uint4 *>(pid + j * 32 + u0 + ((w4 * 4) ^ hsw));
                             ofs[w4 * 4 + 0] = x.x; ofs[w4 * 4 + 1] = x.y; ofs[w4 * 4 + 2] = x.z; ofs[w4 * 4 + 3] = x.w;
                         }
 #pragma unroll
@@ -722,7 +726,9 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
 #pragma unroll
                         for (int i = 0; i < kUP; ++i) V[i] = B[i] > A0 ? B[i] : A0;   // non-candidates: summed, never stored
 #pragma unroll
-                        for (int dd = 16, n = kUP / 2; n >= 1; dd >>= 1, n >>= 1) {
+                        for (int i = 0; i < kUP / 2; ++i) V[i] += __shfl_xor_sync(kFull, V[i + kUP / 2], 16);
+#pragma unroll
+                        for (int dd = 8, n = kUP / 4; n >= 1; dd >>= 1, n >>= 1) {
                             const bool hi = (lane & dd) != 0;
 #pragma unroll
                             for (int i = 0; i < n; ++i) {
@@ -767,9 +773,15 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
             uint32_t lastJ = 0u;
             double A = -INFINITY;
             bool haveA = false;
+            // changed-column sets and ids are fetched two candidates ahead (L2 round trips off the critical path; the ids of
+            // lanes outside J are never used, so the loads do not wait for J)
+            uint32_t Jn0 = ldv<CG>(cJ + cbeg), idn0 = ldv<CG>(cI + (size_t)cbeg * 32 + lane);
+            uint32_t Jn1 = ldv<CG>(cJ + min(cbeg + 1, nc - 1)), idn1 = ldv<CG>(cI + (size_t)min(cbeg + 1, nc - 1) * 32 + lane);
             for (int c = cbeg; c < cend; ++c) {
-                uint32_t J = ldv<CG>(cJ + c);
-                const uint32_t myid = ((J >> lane) & 1u) ? ldv<CG>(cI + (size_t)c * 32 + lane) : 0u;
+                uint32_t J = Jn0;
+                const uint32_t myid = idn0;
+                Jn0 = Jn1; idn0 = idn1;
+                if (c + 2 < cend) { Jn1 = ldv<CG>(cJ + c + 2); idn1 = ldv<CG>(cI + (size_t)(c + 2) * 32 + lane); }
                 if (!haveA || J != lastJ) {
                     A = unchanged_max(J);
                     lastJ = J;
