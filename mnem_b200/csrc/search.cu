@@ -644,12 +644,17 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                     const int v = s_vlist[ci];
                     uint32_t m = ~s_rowm[v] & smask & ~outside;
                     outside |= m;
-                    while (m) {
-                        const int j = __ffs(m) - 1;
+                    while (m) {                                        // four look-ups in flight (a maximum: any order)
+                        int j[4];
+                        j[0] = __ffs(m) - 1;
                         m &= m - 1;
-                        const int id = __shfl_sync(kFull, bid, j);
-                        const double w = T[id * kDictRows + lane];
-                        sc = w > sc ? w : sc;
+#pragma unroll
+                        for (int t = 1; t < 4; ++t) { j[t] = m ? __ffs(m) - 1 : j[0]; m &= m - 1; }
+                        double w[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) w[t] = T[__shfl_sync(kFull, bid, j[t]) * kDictRows + lane];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) sc = w[t] > sc ? w[t] : sc;
                     }
                     sm.A0[v * 32 + lane] = sc > 0.0 ? sc : 0.0;
                 }
@@ -680,8 +685,7 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
             if (item < nv * kParts) {
                 // insertions into the targets of chain `item / kParts`, bottom-up, for the sources u in [u0, u0 + kUP)
                 const int h = item / kParts, u0 = (item - h * kParts) * kUP;
-                while (*reinterpret_cast<volatile int *>(&s_aflag[h]) != gen) { }     // the chain's floors are in shared memory
-                __threadfence_block();
+                bool floors_ready = false;                            // waited for at the first target, after its look-ups
                 // B[i] = max over the columns seen so far of T[col_j | col_u], u = u0 + (i ^ hsw): lanes 16..31 keep the upper
                 // half of the sources in the lower slots, so the first stage of the row butterfly below sends slots
                 // kUP/2.. and keeps slots 0..kUP/2-1 in every lane (no selects)
@@ -717,6 +721,11 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                         }
                     }
                     if (zm & ((1u << kUP) - 1u)) {                    // warp-uniform: any candidate among these sources?
+                        if (!floors_ready) {                              // the chain's floors are in shared memory once its flag is up
+                            while (*reinterpret_cast<volatile int *>(&s_aflag[h]) != gen) { }
+                            __threadfence_block();
+                            floors_ready = true;
+                        }
                         const double A0 = sm.A0[v * 32 + lane];
                         // value of candidate u in this row: max(0, A_v, B[u]).  Rows are added pairwise over the lane bits
                         // 16, 8, 4, 2, 1 (the shape of every row reduction here); the first three stages halve the number
@@ -788,12 +797,15 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                     haveA = true;
                 }
                 double best = A;
-                while (J) {
-                    const int j = __ffs(J) - 1;
+                while (J) {                                 // two look-ups in flight
+                    const int j0 = __ffs(J) - 1;
                     J &= J - 1;
-                    const int id = __shfl_sync(kFull, myid, j);
-                    const double t = T[id * kDictRows + lane];
-                    best = t > best ? t : best;        // plain compare: NaN never wins, like which.max
+                    const int j1 = J ? __ffs(J) - 1 : j0;
+                    J &= J - 1;
+                    const double ta = T[__shfl_sync(kFull, myid, j0) * kDictRows + lane];
+                    const double tb = T[__shfl_sync(kFull, myid, j1) * kDictRows + lane];
+                    best = ta > best ? ta : best;      // plain compare: NaN never wins, like which.max
+                    best = tb > best ? tb : best;
                 }
                 double val = best > 0.0 ? best : 0.0;
                 for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
