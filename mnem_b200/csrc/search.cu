@@ -31,7 +31,7 @@ constexpr int kDictRows = 32;     // E-gene rows per tile of the dictionary scor
 constexpr int kDictThreads = 512;
 constexpr int kChains = 4;         // most independent iteration chains of the host-driven loop (see search_run_host)
 constexpr int kUP = 8;             // insertion sources per work item of the dictionary scorer
-constexpr int kMaxChunk = 4;       // most row tiles per task of the device-resident loop
+constexpr int kMaxChunk = 8;       // most row tiles per task of the device-resident loop
 constexpr unsigned long long kStallNs = 5000000000ull;   // watchdog of the device-resident loop: 5 s without a task
 
 // Device view of a search workspace: one by-value kernel argument instead of twenty pointers.
@@ -558,7 +558,7 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
     uint32_t *dmask = sm.dmask, *pid = sm.pid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = kDictThreads / 32;
-    constexpr int kRestChunk = 4;
+    constexpr int kRestChunk = 2;
     constexpr int kParts = (SP + kUP - 1) / kUP;    // work items per chain
     static_assert(kUP == 8, "the row reduction below halves 8 -> 4 -> 2 -> 1 over the lane bits 16, 8, 4");
     for (int i = tid; i < ndq; i += kDictThreads) dmask[i] = ldv<CG>(d.dict_masks + (size_t)q * dcap + i);
@@ -778,38 +778,48 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
                 }
                 return A;
             };
-            const int cbeg = ni + (item - nv * kParts) * kRestChunk, cend = min(nc, cbeg + kRestChunk);
-            uint32_t lastJ = 0u;
-            double A = -INFINITY;
-            bool haveA = false;
-            // changed-column sets and ids are fetched two candidates ahead (L2 round trips off the critical path; the ids of
-            // lanes outside J are never used, so the loads do not wait for J)
-            uint32_t Jn0 = ldv<CG>(cJ + cbeg), idn0 = ldv<CG>(cI + (size_t)cbeg * 32 + lane);
-            uint32_t Jn1 = ldv<CG>(cJ + min(cbeg + 1, nc - 1)), idn1 = ldv<CG>(cI + (size_t)min(cbeg + 1, nc - 1) * 32 + lane);
-            for (int c = cbeg; c < cend; ++c) {
-                uint32_t J = Jn0;
-                const uint32_t myid = idn0;
-                Jn0 = Jn1; idn0 = idn1;
-                if (c + 2 < cend) { Jn1 = ldv<CG>(cJ + c + 2); idn1 = ldv<CG>(cI + (size_t)(c + 2) * 32 + lane); }
-                if (!haveA || J != lastJ) {
-                    A = unchanged_max(J);
-                    lastJ = J;
-                    haveA = true;
+            // two candidates per item, worked on together: their look-ups and row sums are independent dependent chains,
+            // so the warp has twice the work in flight (this part of a tile is latency-bound)
+            static_assert(kRestChunk == 2, "the reversal / deletion items take candidates in pairs");
+            const int ca = ni + (item - nv * kParts) * kRestChunk;
+            const bool two = ca + 1 < nc;
+            const int cb = two ? ca + 1 : ca;
+            uint32_t Ja = ldv<CG>(cJ + ca), Jb = ldv<CG>(cJ + cb);
+            const uint32_t ida = ldv<CG>(cI + (size_t)ca * 32 + lane), idb = ldv<CG>(cI + (size_t)cb * 32 + lane);
+            double besta = unchanged_max(Ja);
+            double bestb = Jb == Ja ? besta : unchanged_max(Jb);
+            if (!two) Jb = 0u;
+            while (Ja | Jb) {                               // up to four look-ups in flight; ids of lanes outside J are never used
+                if (Ja) {
+                    const int j0 = __ffs(Ja) - 1;
+                    Ja &= Ja - 1;
+                    const int j1 = Ja ? __ffs(Ja) - 1 : j0;
+                    Ja &= Ja - 1;
+                    const double t0a = T[__shfl_sync(kFull, ida, j0) * kDictRows + lane];
+                    const double t1a = T[__shfl_sync(kFull, ida, j1) * kDictRows + lane];
+                    besta = t0a > besta ? t0a : besta;      // plain compare: NaN never wins, like which.max
+                    besta = t1a > besta ? t1a : besta;
                 }
-                double best = A;
-                while (J) {                                 // two look-ups in flight
-                    const int j0 = __ffs(J) - 1;
-                    J &= J - 1;
-                    const int j1 = J ? __ffs(J) - 1 : j0;
-                    J &= J - 1;
-                    const double ta = T[__shfl_sync(kFull, myid, j0) * kDictRows + lane];
-                    const double tb = T[__shfl_sync(kFull, myid, j1) * kDictRows + lane];
-                    best = ta > best ? ta : best;      // plain compare: NaN never wins, like which.max
-                    best = tb > best ? tb : best;
+                if (Jb) {
+                    const int j0 = __ffs(Jb) - 1;
+                    Jb &= Jb - 1;
+                    const int j1 = Jb ? __ffs(Jb) - 1 : j0;
+                    Jb &= Jb - 1;
+                    const double t0b = T[__shfl_sync(kFull, idb, j0) * kDictRows + lane];
+                    const double t1b = T[__shfl_sync(kFull, idb, j1) * kDictRows + lane];
+                    bestb = t0b > bestb ? t0b : bestb;
+                    bestb = t1b > bestb ? t1b : bestb;
                 }
-                double val = best > 0.0 ? best : 0.0;
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(kFull, val, o);
-                if (lane == 0) ptile[c] = val;
+            }
+            double va = besta > 0.0 ? besta : 0.0, vb = bestb > 0.0 ? bestb : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                va += __shfl_xor_sync(kFull, va, o);
+                vb += __shfl_xor_sync(kFull, vb, o);
+            }
+            if (lane == 0) {
+                ptile[ca] = va;
+                if (two) ptile[cb] = vb;
             }
         }
         parity ^= 1;
