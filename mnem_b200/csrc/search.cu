@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
 // scoreAdj for every candidate of one search over a set of 32-row tiles.  block = 16 warps, lane = E-gene row of the tile.
 // Per tile:
 // (1) table T[entry][row] = sum of the R columns in the entry's mask, ascending S-gene order (the order of the Eigen
-//     product in src/mm.cpp:10); each warp takes every 16th entry, two at a time.
+//     product in src/mm.cpp:10); each warp takes every 16th entry, four at a time.
 // (2) floors: for every insertion target v the maximum A_v over the columns OUTSIDE D_v (row v of the graph) of the
 //     current subweights, floored at 0, one target per warp; one more warp keeps the four largest current subweights of
 //     each row for the reversal / deletion candidates (whose changed sets are arbitrary).
@@ -510,8 +510,10 @@ __global__ void __launch_bounds__(kRows) score_kernel(int E, int S, int maxc, in
 //     insertions: one item = one chain of nested targets (see gen_body) x 8 sources u.  The item walks the chain
 //     bottom-up; for every NEW column j of D_v the 8 look-ups T[col_j | col_u] update the running maxima B[u] held in
 //     registers; at every target the values max(A_v, B[u]) of the 32 rows are added by a butterfly that halves the
-//     number of candidates per lane in its first three stages.
-//     reversals / deletions: per candidate, changed columns by id, unchanged-column maximum from the four largest.
+//     number of candidates per lane in its first three stages (lanes 16..31 hold the sources in swapped halves, so the
+//     first stage needs no selects).  The item waits for its chain's floors only when it reaches the first target.
+//     reversals / deletions: two candidates per item, worked on together; changed columns by id, unchanged-column
+//     maximum from the four largest.
 // Per-candidate sums of every tile go to partial[q][tile][c]; tiles are added in ascending order later.  Every row
 // reduction pairs the rows as (l, l^16), (l, l^8), ...: the same function of the 32 row values, so equal rows give
 // bit-equal sums whatever the candidate kind (exact score ties decide graphs, R/mnems.r:236, 279-283).
