@@ -351,7 +351,7 @@ def run_ours(args):
     roofline["fp64_adds"] = {"achieved": fp64_rate, "peak": fp64_peak, "unit": "FP64 adds/s", "frac": fp64_rate / fp64_peak,
                              "peak_source": "%d SMs x 64 lanes x %.0f MHz (sampled SM clock)" % (sms, mhz)}
     roofline["note"] = ("%.0f pairs per pass: above 20 pairs the pass is bound by the FP64 add rate (fp64_adds.frac), not by HBM; "
-                        "with 20 pairs per pass (--batch 4 at k = 5) the same kernel runs at 0.89 of the HBM peak but the whole fit is ~8 % "
+                        "with 20 pairs per pass (--batch 4 at k = 5) the same kernel runs at 0.89 of the HBM peak but the whole fit is ~8 %% "
                         "slower (153 against 166 EM iterations/s when both were measured, profiles/README.md)" % pairs)
     # the kernel that decides `value`: the device-resident greedy search (one persistent launch per EM tick).  Live numbers
     # from this run; pipe utilisation from the committed ncu capture of the same kernel (profiles/search_ncu.json).

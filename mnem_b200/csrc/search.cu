@@ -626,15 +626,18 @@ __device__ __forceinline__ void score_tiles(const SearchDev &d, unsigned char *s
         ++gen;
         __syncthreads();
         // (2) + (3) work items: [0, nv) floors of chain h; [nv] top four of the current row (if there are reversal /
-        // deletion candidates); then the insertion items (chain x 8 sources), then the other candidates in fours.  The
+        // deletion candidates); then the insertion items (chain x 8 sources), then the other candidates in pairs.  The
         // floor items come first in the queue, so whoever needs a floor finds its producer already at work and waits on
         // a shared-memory flag instead of a block-wide barrier.
+        // A warp draws the ticket of its NEXT item before it starts on the current one, so the shared-memory atomic and its
+        // broadcast are off the critical path.  No deadlock: the items that others wait for (floors, top four) have the lowest
+        // tickets and never wait themselves, so a reserved one is always behind an item that finishes.
         const int nA = nv + (nrest > 0 ? 1 : 0);
-        while (true) {
-            int item = 0;
-            if (lane == 0) item = atomicAdd(&s_ctr[parity], 1);
-            item = __shfl_sync(kFull, item, 0);
-            if (item >= nA + nv * kParts + nchunks) break;
+        const int nitems = nA + nv * kParts + nchunks;
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&s_ctr[parity], 1);
+        for (int item = __shfl_sync(kFull, ticket, 0); item < nitems; item = __shfl_sync(kFull, ticket, 0)) {
+            if (lane == 0) ticket = atomicAdd(&s_ctr[parity], 1);
             if (item < nv) {
                 // floors A_v = max(0, max over the columns outside D_v of the current subweights) for the targets of chain
                 // `item`, top-down: the complements grow, so the running maximum carries over
