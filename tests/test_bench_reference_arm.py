@@ -48,3 +48,16 @@ def test_reference_arm_other_ranks_leave_quietly():
     out = run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert not [l for l in out if l.startswith("{")]
     assert "MAPS_LIBMNEMCU=0" in out
+
+
+def test_product_arm_refuses_to_run_without_a_device():
+    """No CPU fallback: without a CUDA device the product arm exits non-zero with a message and prints no result line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode != 0
+    assert "no CPU path" in (r.stdout + r.stderr)
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
